@@ -1,0 +1,366 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference from /root/reference on CPU and
+assert that the oracle restatement (oracle/) reproduces it.  Build-container only.
+
+    python tools/make_golden.py [mb] [mc] [ma]
+
+Each fixture stores seeds + (small) tensors; big inputs / weights are rebuilt from tests/synth.py.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import synth  # noqa: E402
+from ref_harness import NoiseInjector, import_ref  # noqa: E402
+
+from oracle import ma as o_ma  # noqa: E402
+from oracle import mb as o_mb  # noqa: E402
+from oracle import mc as o_mc  # noqa: E402
+from oracle import optim as o_opt  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(8)
+
+
+def close(a, b, tol, what, floor=1e-3):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    ref = b.abs().max().item() if b.numel() else 0.0
+    ok = err <= tol * max(ref, floor)
+    print(f"   {'ok ' if ok else 'BAD'} {what}: max|d|={err:.3e} (ref max {ref:.3e})")
+    assert ok, what
+
+
+# --------------------------------------------------------------------------------------------- M-B
+def make_mb():
+    print("== M-B (avenue_training_script2.py) ==")
+    s2 = import_ref("avenue_training_script2")
+    ck = torch.load("/root/reference/best_improved_model.pth", map_location="cpu", weights_only=False)
+    torch.save(ck, os.path.join(GOLD, "best_improved_model.pth"))
+    P = ck["model_state_dict"]
+    out = {"eval": [], "known_answers": {
+        "scores_T8": [0.13723799586296082, 0.13770483434200287, 0.13747946918010712, 0.13792464137077332],
+        "scores_T16": [0.12867575883865356, 0.12878333032131195, 0.1282607465982437, 0.12863218784332275]}}
+
+    model = s2.CausalAnomalyDetector()
+    model.load_state_dict(P, strict=True)
+    model.eval()
+    for (B, T, H, W, seed, bright) in [(4, 8, 64, 64, 1234, False), (4, 16, 64, 64, 1234, False), (3, 12, 48, 48, 7, True),
+                                       (1, 8, 64, 64, 9, False), (2, 64, 64, 64, 21, True), (5, 9, 40, 56, 33, True)]:
+        x = synth.mb_clips_bright(B, T, H, W, seed) if bright else synth.mb_clips(B, T, H, W, seed)
+        with torch.no_grad():
+            s, a, f = model(x)
+            so, ao, fo = o_mb.mb_forward(P, x)
+        print(f" eval B{B} T{T} {H}x{W}")
+        close(so, s, 1e-6, "oracle scores"); close(ao, a, 1e-6, "oracle adj"); close(fo, f, 1e-6, "oracle feat")
+        out["eval"].append({"B": B, "T": T, "H": H, "W": W, "seed": seed, "bright": bright,
+                            "scores": s.clone(), "adj": a.clone(), "feat": f.clone()})
+    close(out["eval"][0]["scores"].flatten(), out["known_answers"]["scores_T8"], 1e-5, "SURVEY known answers T8")
+    close(out["eval"][1]["scores"].flatten(), out["known_answers"]["scores_T16"], 1e-5, "SURVEY known answers T16")
+
+    # ---- one training forward/loss/backward with injected noise (s2:221-236)
+    def train_case(B, T, seed, n_anom):
+        x = synth.mb_clips_bright(B, T, 64, 64, seed)
+        kf = synth.keep_mask((B, 16), 0.3, seed + 1)
+        kg = synth.keep_mask((B, 128), 0.3, seed + 2)
+        u = torch.rand(B, generator=synth.gen(seed + 3)) * 0.9
+        u[:n_anom] = 0.99                      # rand_like(targets) > 0.95 -> pseudo label 1
+        pseudo = (u > 0.95).float()
+        trainer = s2.ImprovedMiniCausalVAD(device="cpu")
+        trainer.model.load_state_dict(P, strict=True)
+        trainer.model.train()
+        with NoiseInjector() as inj:
+            inj.dropout[id(trainer.model.feature_extractor.dropout)] = [kf]
+            inj.dropout[id(trainer.model.graph_encoder[2])] = [kg]
+            inj.rand = [u]
+            trainer.optimizer.zero_grad()
+            s, a, f = trainer.model(x)
+            loss, comps = trainer.compute_improved_loss(s, a, torch.zeros(B), f)
+            loss.backward()
+        grads = {k: p.grad.clone() for k, p in trainer.model.named_parameters()}
+        # oracle
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        so, ao, fo = o_mb.mb_forward(Pg, x, True, kf, kg)
+        lo, co = o_mb.mb_loss(so, ao, pseudo)
+        lo.backward()
+        print(f" train B{B} T{T}")
+        close(lo, loss, 1e-6, "oracle loss")
+        for k in comps:
+            close(co[k], comps[k], 1e-5, f"oracle comp {k}")
+        for k in grads:
+            close(Pg[k].grad, grads[k], 2e-5, f"oracle grad {k}")
+        return {"B": B, "T": T, "seed": seed, "keep_feat": kf, "keep_graph": kg, "pseudo": pseudo, "u": u,
+                "loss": loss.detach().clone(), "comps": comps, "scores": s.detach().clone(), "adj": a.detach().clone(),
+                "feat": f.detach().clone(),
+                "grads": {k: (g if g.numel() <= 8192 else None) for k, g in grads.items()},
+                "grad_summary": {k: synth.summarize(g) for k, g in grads.items()}}
+
+    out["train"] = [train_case(8, 8, 11, 1), train_case(4, 8, 12, 0), train_case(6, 16, 13, 2)]
+
+    # ---- loss-only case at B=32 (K11 parity incl. d/dscores, d/dadj)
+    g = synth.gen(77)
+    sc = (torch.rand(32, 1, generator=g) * 0.5 + 0.05).requires_grad_(True)
+    ad = (torch.rand(32, 16, 16, generator=g) * (1 - torch.eye(16))).requires_grad_(True)
+    u = torch.rand(32, generator=g)
+    u[3] = 0.97; u[17] = 0.999
+    trainer = s2.ImprovedMiniCausalVAD(device="cpu")
+    with NoiseInjector() as inj:
+        inj.rand = [u]
+        loss, comps = trainer.compute_improved_loss(sc, ad, torch.zeros(32), None)
+        loss.backward()
+    lo, co = o_mb.mb_loss(sc.detach(), ad.detach(), (u > 0.95).float())
+    close(lo, loss, 1e-6, "oracle loss B32")
+    out["loss32"] = {"scores": sc.detach().clone(), "adj": ad.detach().clone(), "u": u, "pseudo": (u > 0.95).float(),
+                     "loss": loss.detach().clone(), "comps": comps, "dscores": sc.grad.clone(), "dadj": ad.grad.clone()}
+
+    # ---- 3-step trajectory from the shipped checkpoint incl. AdamW state (s2:221-238)
+    trainer = s2.ImprovedMiniCausalVAD(device="cpu")
+    trainer.model.load_state_dict(P, strict=True)
+    trainer.optimizer.load_state_dict(copy.deepcopy(ck["optimizer_state_dict"]))
+    trainer.model.train()
+    traj = {"B": 8, "T": 8, "seeds": [101, 102, 103], "losses": [], "steps": []}
+    for sd in traj["seeds"]:
+        x = synth.mb_clips_bright(8, 8, 64, 64, sd)
+        kf = synth.keep_mask((8, 16), 0.3, sd + 1); kg = synth.keep_mask((8, 128), 0.3, sd + 2)
+        u = torch.rand(8, generator=synth.gen(sd + 3))
+        with NoiseInjector() as inj:
+            inj.dropout[id(trainer.model.feature_extractor.dropout)] = [kf]
+            inj.dropout[id(trainer.model.graph_encoder[2])] = [kg]
+            inj.rand = [u]
+            trainer.optimizer.zero_grad()
+            s, a, f = trainer.model(x)
+            loss, comps = trainer.compute_improved_loss(s, a, torch.zeros(8), f)
+            loss.backward()
+            norm = torch.nn.utils.clip_grad_norm_(trainer.model.parameters(), max_norm=0.5)
+            trainer.optimizer.step()
+        traj["losses"].append(float(loss)); traj["steps"].append({"comps": comps, "grad_norm": float(norm), "u": u})
+    traj["final_summary"] = {k: synth.summarize(v) for k, v in trainer.model.state_dict().items()}
+    traj["final_small"] = {k: v.clone() for k, v in trainer.model.state_dict().items() if v.numel() <= 8192}
+    traj["final_opt_step"] = float(trainer.optimizer.state_dict()["state"][0]["step"])
+    out["trajectory"] = traj
+    print(" trajectory losses", traj["losses"])
+    torch.save(out, os.path.join(GOLD, "mb.pt"))
+
+
+# --------------------------------------------------------------------------------------------- M-C
+def make_mc():
+    print("== M-C (minicausal_vad_complete3.py) ==")
+    mc3 = import_ref("minicausal_vad_complete3")
+    torch.manual_seed(0)
+    model = mc3.SimpleVideoAnomalyDetector()
+    out = {"init_state": {k: v.clone() for k, v in model.state_dict().items()}, "eval": [], "train": []}
+    # "trained-like" weights: reproducible, non-degenerate (the stock init gives a constant 0.5)
+    P = synth.synth_fill(model.state_dict(), seed=5)
+    for k in P:
+        if k.startswith("classifier") and k.endswith("weight"):
+            P[k] = P[k] * 3.0
+    out["state_seed"] = 5
+    model.load_state_dict(P, strict=True)
+    for name, st in (("init", out["init_state"]), ("synth", P)):
+        model.load_state_dict(st, strict=True)
+        model.eval()
+        for (B, T, H, W, seed) in [(4, 16, 64, 64, 1234), (2, 64, 64, 64, 3), (2, 10, 36, 44, 8), (1, 4, 64, 64, 2)]:
+            x = synth.mc_clips(B, T, H, W, seed)
+            with torch.no_grad():
+                s = model(x)
+                so = o_mc.mc_forward(st, x)
+            print(f" eval[{name}] B{B} T{T} {H}x{W}  scores {s.flatten()[:3].tolist()}")
+            close(so, s, 1e-6, "oracle scores")
+            out["eval"].append({"weights": name, "B": B, "T": T, "H": H, "W": W, "seed": seed, "scores": s.clone()})
+    # training step: forward (batch-stat BN) + BCE + backward
+    for (B, T, seed) in [(4, 8, 41), (6, 16, 42)]:
+        model.load_state_dict(P, strict=True)
+        model.train()
+        x = synth.mc_clips(B, T, 64, 64, seed)
+        y = (torch.rand(B, generator=synth.gen(seed + 5)) > 0.5).float()
+        k0 = synth.keep_mask((B, 32), 0.5, seed + 1); k1 = synth.keep_mask((B, 16), 0.3, seed + 2)
+        with NoiseInjector() as inj:
+            inj.dropout[id(model.classifier[0])] = [k0]
+            inj.dropout[id(model.classifier[3])] = [k1]
+            model.zero_grad()
+            s = model(x)
+            loss = torch.nn.BCELoss()(s.squeeze(), y)
+            loss.backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+        new_state = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+        ns = {}
+        so = o_mc.mc_forward(Pg, x, True, k0, k1, ns)
+        lo = o_mc.bce(so, y)
+        lo.backward()
+        print(f" train B{B} T{T} loss {float(loss):.6f}")
+        close(lo, loss, 1e-6, "oracle loss")
+        gscale = max(float(g.abs().max()) for g in grads.values())
+        for k in grads:
+            close(Pg[k].grad, grads[k], 5e-5, f"oracle grad {k}", floor=gscale)
+        for k in new_state:
+            close(ns[k], new_state[k], 1e-5, f"oracle stat {k}")
+        out["train"].append({"B": B, "T": T, "seed": seed, "y": y, "keep0": k0, "keep1": k1, "loss": loss.detach().clone(),
+                             "scores": s.detach().clone(), "grads": grads, "new_stats": new_state})
+    # 3-step Adam trajectory following mc3:269-311 (clip only when norm > 10)
+    model.load_state_dict(P, strict=True)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5, eps=1e-8)
+    traj = {"B": 4, "T": 8, "seeds": [51, 52, 53], "losses": []}
+    for sd in traj["seeds"]:
+        x = synth.mc_clips(4, 8, 64, 64, sd)
+        y = (torch.rand(4, generator=synth.gen(sd + 5)) > 0.5).float()
+        k0 = synth.keep_mask((4, 32), 0.5, sd + 1); k1 = synth.keep_mask((4, 16), 0.3, sd + 2)
+        with NoiseInjector() as inj:
+            inj.dropout[id(model.classifier[0])] = [k0]
+            inj.dropout[id(model.classifier[3])] = [k1]
+            opt.zero_grad()
+            s = model(x).squeeze()
+            loss = torch.nn.BCELoss()(s, y)
+            loss.backward()
+            gn = sum(p.grad.data.norm(2).item() ** 2 for p in model.parameters()) ** 0.5
+            if gn > 10.0:
+                torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+        traj["losses"].append(float(loss))
+    traj["final"] = {k: v.clone() for k, v in model.state_dict().items()}
+    out["trajectory"] = traj
+    print(" trajectory losses", traj["losses"])
+    torch.save(out, os.path.join(GOLD, "mc.pt"))
+
+
+# --------------------------------------------------------------------------------------------- M-A
+def ma_state(cad, seed, live_detector):
+    torch.manual_seed(0)
+    model = cad.CausalAnomalyDetector()
+    P = synth.synth_fill(model.state_dict(), seed=seed, skip=("detector.detector_net.10.bias",))
+    if live_detector:
+        # un-saturate the detector so 0..5 boxes per frame pass the validity window (cad:217-218)
+        P["detector.detector_net.10.bias"] = torch.tensor(
+            [0.0, 0.0, -0.5, -0.5, 0.3, -0.2, 0.0, 0.2, -3.5, 0.1, 0.0, 0.0, 0.4, 3.5, 0.0, 0.0, 0.1, -0.1, 4.5, 0.0])
+        P["detector.detector_net.10.weight"] = P["detector.detector_net.10.weight"] * 24.0
+    return model, P
+
+
+def ref_ma_run(cad, model, P, x, labels, eps, ntr, train, keep):
+    """Run the reference model + its 4-term loss (cad:671-688, the non-AMP branch) with injected noise."""
+    model.load_state_dict(P, strict=True)
+    cad.apply_memory_efficient_training.__globals__["print"] = lambda *a, **k: None
+    cad.apply_memory_efficient_training(model)
+    model.train(train)
+    B = x.shape[0]
+    with NoiseInjector() as inj:
+        inj.randn = [eps[b, : int(ntr[b])].clone() for b in range(B)]
+        if train:
+            inj.dropout[id(model.detector.detector_net[2])] = [keep["det0"]]
+            inj.dropout[id(model.detector.detector_net[5])] = [keep["det1"]]
+            inj.dropout[id(model.anomaly_scorer.causal_scorer[2])] = [keep["scorer0"][b:b + 1] for b in range(B)]
+            inj.dropout[id(model.direct_classifier[2])] = [keep["cls0"]]
+            inj.dropout[id(model.direct_classifier[5])] = [keep["cls1"]]
+        model.zero_grad()
+        ctx = torch.enable_grad() if train else torch.no_grad()
+        with ctx:
+            outputs = model(x)
+            ce = torch.nn.CrossEntropyLoss()(outputs["direct_predictions"], labels)
+            an = torch.nn.MSELoss()(outputs["anomaly_scores"], labels.float())
+            kls = outputs["kl_losses"]
+            kl = sum(k for k in kls if torch.isfinite(k)) / len(kls)
+            cs = torch.nn.MSELoss()(outputs["causal_anomaly_scores"], labels.float())
+            total = 0.4 * ce + 0.3 * an + 0.2 * cs + 0.1 * kl
+        if train:
+            total.backward()
+    return outputs, total, {"classification": float(ce), "anomaly": float(an), "causal": float(cs), "kl": float(kl)}
+
+
+def make_ma():
+    print("== M-A (causal_anomaly_detection.py) ==")
+    cad = import_ref("causal_anomaly_detection")
+    out = {"cases": []}
+    cases = [
+        dict(name="sat_eval", seed=3, live=False, B=2, T=4, H=240, W=360, wide=True, train=False, xseed=1234),
+        dict(name="sat_train", seed=3, live=False, B=2, T=4, H=240, W=360, wide=True, train=True, xseed=1235),
+        dict(name="live_eval", seed=4, live=True, B=3, T=3, H=120, W=180, wide=False, train=False, xseed=77),
+        dict(name="live_train", seed=4, live=True, B=3, T=3, H=120, W=180, wide=False, train=True, xseed=78),
+    ]
+    for c in cases:
+        model, P = ma_state(cad, c["seed"], c["live"])
+        B, T = c["B"], c["T"]
+        x = synth.ma_clips(B, T, c["H"], c["W"], c["xseed"], c["wide"])
+        labels = (torch.rand(B, generator=synth.gen(c["xseed"] + 9)) < 0.5).long()
+        eps = torch.randn(B, 5, 6, generator=synth.gen(c["xseed"] + 1))
+        keep = {"det0": synth.keep_mask((B, T, 512), 0.3, c["xseed"] + 2), "det1": synth.keep_mask((B, T, 256), 0.2, c["xseed"] + 3),
+                "scorer0": synth.keep_mask((B, 64), 0.2, c["xseed"] + 4), "cls0": synth.keep_mask((B, 512), 0.3, c["xseed"] + 5),
+                "cls1": synth.keep_mask((B, 256), 0.2, c["xseed"] + 6)}
+        # oracle first (gives the per-clip track counts needed to size the injected eps)
+        Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+        ns = {}
+        oo = o_ma.ma_forward(Pg, x, eps, c["train"], keep, ns)
+        lo, co = o_ma.ma_loss(oo, labels)
+        if c["train"]:
+            lo.backward()
+        ro, rl, rc = ref_ma_run(cad, model, P, x, labels, eps, oo["n_tracks"], c["train"], keep)
+        print(f" case {c['name']}: tracks/clip {oo['n_tracks'].tolist()} det counts {oo['det_counts'].flatten().tolist()}")
+        close(oo["anomaly_scores"], ro["anomaly_scores"], 1e-5, "anomaly_scores")
+        close(oo["causal_anomaly_scores"], ro["causal_anomaly_scores"], 1e-5, "causal_anomaly_scores")
+        close(oo["direct_predictions"], ro["direct_predictions"], 1e-5, "direct_predictions")
+        close(oo["kl_losses"], torch.stack(ro["kl_losses"]), 1e-5, "kl_losses")
+        close(oo["adjacency_matrices"], torch.stack(ro["adjacency_matrices"]), 1e-5, "adjacency")
+        for b in range(B):
+            n = int(oo["n_tracks"][b])
+            assert ro["causal_factors"][b].shape[0] == n
+            close(oo["causal_factors"][b, :n], ro["causal_factors"][b], 1e-5, f"causal_factors[{b}]")
+            for t in range(T):
+                m = int(oo["det_counts"][b, t])
+                assert ro["detections"][b][t].shape[0] == m, (ro["detections"][b][t].shape, m)
+                close(oo["detections"][b, t, :m], ro["detections"][b][t], 1e-5, f"detections[{b}][{t}]") if (b + t) == 0 else None
+        close(lo, rl, 1e-5, "total loss")
+        rec = {**c, "labels": labels, "loss": rl.detach().clone(), "comps": rc,
+               "anomaly_scores": ro["anomaly_scores"].detach().clone(),
+               "causal_anomaly_scores": ro["causal_anomaly_scores"].detach().clone(),
+               "direct_predictions": ro["direct_predictions"].detach().clone(),
+               "kl_losses": torch.stack(ro["kl_losses"]).detach().clone(),
+               "adjacency": torch.stack(ro["adjacency_matrices"]).detach().clone(),
+               "causal_factors": oo["causal_factors"].detach().clone(), "n_tracks": oo["n_tracks"].clone(),
+               "detections": oo["detections"].detach().clone(), "det_counts": oo["det_counts"].clone(),
+               "features_summary": synth.summarize(oo["features"])}
+        if c["train"]:
+            gs, has = {}, {}
+            gnorm = max(float(p.grad.norm()) for p in model.parameters() if p.grad is not None)
+            for k, p in model.named_parameters():
+                has[k] = p.grad is not None
+                if p.grad is not None:
+                    og = Pg[k].grad
+                    if float(p.grad.norm()) > 1e-5 * gnorm:   # conv biases feeding BN: analytically zero, roundoff only
+                        rel = float((og - p.grad).double().norm() / p.grad.double().norm())
+                        print(f"   {'ok ' if rel < 5e-3 else 'BAD'} grad {k}: rel-L2 {rel:.2e} |g| {float(p.grad.norm()):.3e}")
+                        assert rel < 5e-3, k
+                    gs[k] = synth.summarize(p.grad)
+                    if p.grad.numel() <= 4096:
+                        gs[k]["full"] = p.grad.clone()
+                elif "backbone.conv1" in k or "backbone.bn1" in k:
+                    pass                       # frozen by apply_memory_efficient_training (cad:596-598)
+                else:
+                    og = Pg[k].grad
+                    assert og is None or float(og.abs().max()) == 0.0, f"oracle grad for {k} should be none/zero"
+            rec["grad_summary"] = gs
+            rec["has_grad"] = has
+            rec["new_stats"] = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+            for k, v in rec["new_stats"].items():
+                close(ns[k], v, 1e-5, f"stat {k}") if "conv" not in k else None
+        out["cases"].append(rec)
+    torch.save(out, os.path.join(GOLD, "ma.pt"))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["mb", "mc", "ma"]
+    os.makedirs(GOLD, exist_ok=True)
+    if "mb" in which:
+        make_mb()
+    if "mc" in which:
+        make_mc()
+    if "ma" in which:
+        make_ma()
+    print("golden fixtures written to", GOLD)
