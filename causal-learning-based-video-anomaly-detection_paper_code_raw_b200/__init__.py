@@ -1,0 +1,19 @@
+"""cvad_b200 -- B200-native (sm_100a) hot path of the causal video-anomaly-detection reference.
+
+The directory name follows the project convention and is not a valid Python identifier; import it through the
+root-level ``cvad_b200`` alias module (``import cvad_b200``).
+
+Public surface (mirrors the reference's Python seam):
+  mb.CausalAnomalyDetector / mb.ImprovedMiniCausalVAD / mb.MiniCausalVAD      avenue_training_script2.py, script1.py
+  mc.SimpleVideoAnomalyDetector / mc.StableTrainer                           minicausal_vad_complete3.py
+  ma.CausalAnomalyDetector / ma.train_model / ma.test_model                  causal_anomaly_detection.py
+  ops (autograd glue over include/cvad_b200.h), arena.FusedAdam, parallel.DataParallel
+There is no CPU fallback: importing the package loads libcvad_b200.so and raises if it is missing.
+"""
+from . import _lib
+
+_lib.lib()   # fail loudly when the CUDA extension has not been built
+
+from . import arena, mb, mc, noise, ops  # noqa: E402,F401
+
+__all__ = ["arena", "mb", "mc", "noise", "ops"]

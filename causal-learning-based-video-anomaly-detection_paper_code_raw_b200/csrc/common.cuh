@@ -1,0 +1,89 @@
+// Shared device helpers for the cvad_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define CVAD_API extern "C" __attribute__((visibility("default")))
+
+// Every entry point returns 0 on success or the cudaError_t of the failed launch.
+#define CVAD_LAUNCH_CHECK()                         \
+  do {                                              \
+    cudaError_t e__ = cudaGetLastError();           \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+
+enum CvadAct { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY01 = 2, ACT_SIGMOID = 3, ACT_TANH = 4 };
+
+__device__ __forceinline__ float cvad_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LEAKY01: return v > 0.f ? v : 0.1f * v;
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// derivative of the activation expressed through its OUTPUT y
+__device__ __forceinline__ float cvad_act_grad_from_out(float y, int act) {
+  switch (act) {
+    case ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY01: return y > 0.f ? 1.f : 0.1f;
+    case ACT_SIGMOID: return y * (1.f - y);
+    case ACT_TANH: return 1.f - y * y;
+    default: return 1.f;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum (blockDim.x <= 1024, multiple of 32); result valid in every thread
+__device__ __forceinline__ float block_sum(float v, float* sh /* >=32 floats */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  float r = (lane < nw) ? sh[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ double block_sum_d(double v, double* sh /* >=32 doubles */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = (lane < nw) ? sh[lane] : 0.0;
+  r = warp_sum_d(r);
+  return r;
+}
+
+static inline int cvad_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline int cvad_num_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}

@@ -1,0 +1,505 @@
+"""torch.autograd glue over the C ABI (include/cvad_b200.h).  PyTorch owns memory, streams and the autograd graph;
+every FLOP on the hot path runs in the hand-written sm_100a kernels of libcvad_b200.so.  No CPU path exists: CPU
+tensors raise.
+
+Gradient convention: parameter gradients are ACCUMULATED IN PLACE into ``param.grad`` by the weight-gradient kernels
+(``param.grad`` is normally a view into the flat gradient arena of ``arena.FlatArena`` so that the gradient all-reduce
+and the fused optimizer see one contiguous buffer); the autograd Functions return ``None`` for parameters.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+ACT_NONE, ACT_RELU, ACT_LEAKY01, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+
+LAUNCHES = [0]   # number of cvad kernels-launching ABI calls issued (bench.py reports it as gpu_launches evidence)
+
+
+def L():
+    return _lib.lib()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cvad_b200 ops run only on CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _call(name, *args):
+    LAUNCHES[0] += 1
+    check(getattr(L(), name)(*args), name)
+
+
+def grad_buffer(p: torch.Tensor) -> torch.Tensor:
+    """The fp32 buffer wgrad kernels accumulate into (the arena view when the parameter is arena-managed)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+def _wants_grad(p) -> bool:
+    return p is not None and p.requires_grad
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def _conv_desc(x5, w5, y5, stride, padding) -> ConvDesc:
+    d = ConvDesc()
+    d.N, d.Cin, d.Din, d.Hin, d.Win = x5.shape
+    d.Cout, d.Dout, d.Hout, d.Wout = y5.shape[1:]
+    d.kD, d.kH, d.kW = w5.shape[2:]
+    d.sD, d.sH, d.sW = stride
+    d.pD, d.pH, d.pW = padding
+    for i in range(5):
+        d.xs[i] = x5.stride(i)
+        d.ys[i] = y5.stride(i)
+    return d
+
+
+def _triple(v, nd):
+    if isinstance(v, int):
+        v = (v,) * nd
+    v = tuple(v)
+    return (1,) * (3 - nd) + v if nd < 3 else v
+
+
+def _pad3(v, nd):
+    if isinstance(v, int):
+        v = (v,) * nd
+    v = tuple(v)
+    return (0,) * (3 - nd) + v if nd < 3 else v
+
+
+class _ConvAct(torch.autograd.Function):
+    """act(conv(x, w) + b) for 2-D (N,C,H,W) or 3-D (N,C,D,H,W) inputs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, act):
+        _cuda(x, weight, bias)
+        nd = x.dim() - 2
+        x = x if x.dtype == torch.float32 else x.float()
+        x5 = x if nd == 3 else x.unsqueeze(2)
+        w5 = weight if nd == 3 else weight.unsqueeze(2)
+        s3, p3 = _triple(stride, nd), _pad3(padding, nd)
+        N, _, Di, Hi, Wi = x5.shape
+        Co, _, kD, kH, kW = w5.shape
+        Do = (Di + 2 * p3[0] - kD) // s3[0] + 1
+        Ho = (Hi + 2 * p3[1] - kH) // s3[1] + 1
+        Wo = (Wi + 2 * p3[2] - kW) // s3[2] + 1
+        y5 = torch.empty((N, Co, Do, Ho, Wo), device=x.device, dtype=torch.float32)
+        d = _conv_desc(x5, w5, y5, s3, p3)
+        _call("cvad_conv_fwd_f32", ctypes.byref(d), _ptr(x5), _ptr(weight), _ptr(bias), _ptr(y5), act, _st())
+        ctx.geom = (s3, p3, act, nd)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.save_for_backward(x5, y5 if act != ACT_NONE else None)
+        return y5 if nd == 3 else y5.squeeze(2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x5, y5 = ctx.saved_tensors
+        s3, p3, act, nd = ctx.geom
+        weight, bias = ctx.weight, ctx.bias
+        dy5 = _f32c(dy if nd == 3 else dy.unsqueeze(2))
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy5)
+            _call("cvad_act_mask_bwd_f32", _ptr(dy5), _ptr(y5), None, 1.0, act, _ptr(dz), dy5.numel(), _st())
+            dy5 = dz
+        w5 = weight if nd == 3 else weight.unsqueeze(2)
+        d = _conv_desc(x5, w5, dy5, s3, p3)
+        if _wants_grad(weight):
+            _call("cvad_conv_wgrad_f32", ctypes.byref(d), _ptr(x5), _ptr(dy5), _ptr(grad_buffer(weight)), _st())
+        if _wants_grad(bias):
+            N, Co = dy5.shape[:2]
+            _call("cvad_channel_sum_add_f32", _ptr(dy5), N, Co, dy5[0, 0].numel(), _ptr(grad_buffer(bias)), _st())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx5 = torch.empty(x5.shape, device=x5.device, dtype=torch.float32)
+            dd = _conv_desc(dx5, w5, dy5, s3, p3)
+            _call("cvad_conv_dgrad_f32", ctypes.byref(dd), _ptr(dy5), _ptr(weight), _ptr(dx5), 0, _st())
+            dx = dx5 if nd == 3 else dx5.squeeze(2)
+        return dx, None, None, None, None, None
+
+
+def conv_act(x, weight, bias, stride=1, padding=0, act=ACT_NONE):
+    return _ConvAct.apply(x, weight, bias, stride, padding, act)
+
+
+# ------------------------------------------------------------------------------------------------ linear
+def _sgemm(M, N, K, A, lda, a_k, B, ldb, b_k, C, ldc, bias=None, act=ACT_NONE, mask=None, mask_scale=1.0, accumulate=0, splits=1):
+    _call("cvad_sgemm_f32", M, N, K, _ptr(A), lda, int(a_k), _ptr(B), ldb, int(b_k), _ptr(C), ldc, _ptr(bias), act, _ptr(mask),
+          float(mask_scale), int(accumulate), int(splits), _st())
+
+
+def _splits_for(M, N, K):
+    tiles = ((M + 63) // 64) * ((N + 63) // 64)
+    if tiles >= 64 or K < 1024:
+        return 1
+    return max(1, min(K // 256, 148 // tiles))
+
+
+class _LinearAct(torch.autograd.Function):
+    """act(x @ W^T + b) * keep_mask / (1-p) over the last axis of x."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, mask, mask_scale):
+        _cuda(x, weight, bias, mask)
+        shp = x.shape
+        x2 = _f32c(x).reshape(-1, shp[-1])
+        M, K = x2.shape
+        O = weight.shape[0]
+        splits = _splits_for(M, O, K)
+        if mask is not None:
+            mask = _f32c(mask).reshape(M, O)
+        if splits > 1:
+            y = torch.zeros((M, O), device=x.device, dtype=torch.float32)
+            _sgemm(M, O, K, x2, K, True, weight, K, True, y, O, splits=splits)
+            if bias is not None or act != ACT_NONE or mask is not None:
+                _call("cvad_bias_act_mask_f32", _ptr(y), M, O, _ptr(bias), act, _ptr(mask), float(mask_scale), _st())
+        else:
+            y = torch.empty((M, O), device=x.device, dtype=torch.float32)
+            _sgemm(M, O, K, x2, K, True, weight, K, True, y, O, bias, act, mask, mask_scale)
+        ctx.meta = (act, mask_scale, shp)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.save_for_backward(x2, y if act != ACT_NONE else None, mask)
+        return y.reshape(*shp[:-1], O)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, y, mask = ctx.saved_tensors
+        act, mask_scale, shp = ctx.meta
+        weight, bias = ctx.weight, ctx.bias
+        M, K = x2.shape
+        O = weight.shape[0]
+        dz = _f32c(dy).reshape(M, O)
+        if act != ACT_NONE or mask is not None:
+            out = torch.empty_like(dz)
+            _call("cvad_act_mask_bwd_f32", _ptr(dz), _ptr(y), _ptr(mask), float(mask_scale), act, _ptr(out), dz.numel(), _st())
+            dz = out
+        if _wants_grad(weight):      # dW[o][i] += sum_m dz[m][o] x[m][i]
+            _sgemm(O, K, M, dz, O, False, x2, K, False, grad_buffer(weight), K, accumulate=1)
+        if _wants_grad(bias):
+            _call("cvad_colsum_f32", _ptr(dz), M, O, O, _ptr(grad_buffer(bias)), 1, _st())
+        dx = None
+        if ctx.needs_input_grad[0]:  # dx[m][i] = sum_o dz[m][o] W[o][i]
+            dx = torch.empty((M, K), device=dz.device, dtype=torch.float32)
+            _sgemm(M, K, O, dz, O, True, weight, K, False, dx, K)
+            dx = dx.reshape(shp)
+        return dx, None, None, None, None, None
+
+
+def linear_act(x, weight, bias, act=ACT_NONE, mask=None, p_drop=0.0):
+    scale = 1.0 / (1.0 - p_drop) if mask is not None else 1.0
+    return _LinearAct.apply(x, weight, bias, act, mask, scale)
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+class _BatchNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, ws, training, act, eps, momentum):
+        _cuda(x, gamma, beta)
+        x = _f32c(x)
+        N, C = x.shape[:2]
+        S = x[0, 0].numel()
+        mean = torch.empty(C, device=x.device, dtype=torch.float32)
+        invstd = torch.empty_like(mean)
+        if training:
+            _call("cvad_bn_train_stats_f32", _ptr(x), N, C, S, _ptr(ws), float(eps), float(momentum), _ptr(mean), _ptr(invstd),
+                  _ptr(running_mean), _ptr(running_var), _ptr(nbt), _st())
+        else:
+            _call("cvad_bn_eval_prepare_f32", C, float(eps), _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(invstd), _st())
+        y = torch.empty_like(x)
+        _call("cvad_bn_apply_f32", _ptr(x), _ptr(y), N, C, S, _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), act, _st())
+        ctx.meta = (training, act)
+        ctx.gamma, ctx.beta, ctx.ws = gamma, beta, ws
+        ctx.save_for_backward(x, mean, invstd)
+        ctx.mark_non_differentiable(*[t for t in () if t is not None])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd = ctx.saved_tensors
+        training, act = ctx.meta
+        gamma, beta, ws = ctx.gamma, ctx.beta, ctx.ws
+        dy = _f32c(dy)
+        N, C = x.shape[:2]
+        S = x[0, 0].numel()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dg = grad_buffer(gamma) if _wants_grad(gamma) else None
+        db = grad_buffer(beta) if _wants_grad(beta) else None
+        if dx is None and dg is None and db is None:
+            return (None,) * 11
+        _call("cvad_bn_bwd_f32", _ptr(dy), _ptr(x), _ptr(dx), N, C, S, _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), act,
+              int(training), _ptr(ws), _ptr(dg), _ptr(db), _st())
+        return (dx,) + (None,) * 10
+
+
+def batchnorm_act(x, gamma, beta, running_mean, running_var, nbt, ws, training, act=ACT_NONE, eps=1e-5, momentum=0.1):
+    return _BatchNormAct.apply(x, gamma, beta, running_mean, running_var, nbt, ws, training, act, eps, momentum)
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, stride, padding):
+        _cuda(x)
+        nd = x.dim() - 2
+        x = _f32c(x)
+        k3, s3, p3 = _triple(kernel, nd), _triple(stride, nd), _pad3(padding, nd)
+        x5 = x if nd == 3 else x.unsqueeze(2)
+        N, C, D, H, W = x5.shape
+        OD = (D + 2 * p3[0] - k3[0]) // s3[0] + 1
+        OH = (H + 2 * p3[1] - k3[1]) // s3[1] + 1
+        OW = (W + 2 * p3[2] - k3[2]) // s3[2] + 1
+        y = torch.empty((N, C, OD, OH, OW), device=x.device, dtype=torch.float32)
+        need_idx = ctx.needs_input_grad[0]
+        idx = torch.empty((N, C, OD, OH, OW), device=x.device, dtype=torch.int32) if need_idx else None
+        _call("cvad_maxpool_fwd_f32", _ptr(x5), _ptr(y), _ptr(idx), N * C, D, H, W, OD, OH, OW, *k3, *s3, *p3, _st())
+        ctx.meta = (x5.shape, nd)
+        ctx.save_for_backward(idx)
+        return y if nd == 3 else y.squeeze(2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        shape5, nd = ctx.meta
+        dy = _f32c(dy)
+        N, C, D, H, W = shape5
+        dx = torch.zeros(shape5, device=dy.device, dtype=torch.float32)
+        _call("cvad_maxpool_bwd_f32", _ptr(dy), _ptr(idx), _ptr(dx), N * C, D * H * W, idx[0, 0].numel(), _st())
+        return (dx if nd == 3 else dx.squeeze(2)), None, None, None
+
+
+def maxpool(x, kernel, stride=None, padding=0):
+    return _MaxPool.apply(x, kernel, stride if stride is not None else kernel, padding)
+
+
+class _AdaptiveAvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_size):
+        _cuda(x)
+        nd = x.dim() - 2
+        x = _f32c(x)
+        x5 = x if nd == 3 else x.unsqueeze(2)
+        o3 = _triple(out_size, nd)
+        N, C, D, H, W = x5.shape
+        y = torch.empty((N, C) + tuple(o3), device=x.device, dtype=torch.float32)
+        _call("cvad_adaptive_avgpool_fwd_f32", _ptr(x5), _ptr(y), N * C, D, H, W, *o3, _st())
+        ctx.meta = (x5.shape, o3, nd)
+        return y if nd == 3 else y.squeeze(2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape5, o3, nd = ctx.meta
+        dy = _f32c(dy)
+        N, C, D, H, W = shape5
+        dx = torch.empty(shape5, device=dy.device, dtype=torch.float32)
+        _call("cvad_adaptive_avgpool_bwd_f32", _ptr(dy), _ptr(dx), N * C, D, H, W, *o3, _st())
+        return (dx if nd == 3 else dx.squeeze(2)), None
+
+
+def adaptive_avgpool(x, out_size):
+    return _AdaptiveAvgPool.apply(x, out_size)
+
+
+class _MeanMid(torch.autograd.Function):
+    """(A,T,F) -> (A,F) mean over T."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _cuda(x)
+        x = _f32c(x)
+        A, T, F = x.shape
+        y = torch.empty((A, F), device=x.device, dtype=torch.float32)
+        _call("cvad_mean_mid_fwd_f32", _ptr(x), _ptr(y), A, T, F, _st())
+        ctx.meta = (A, T, F)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, T, F = ctx.meta
+        dy = _f32c(dy)
+        dx = torch.empty((A, T, F), device=dy.device, dtype=torch.float32)
+        _call("cvad_mean_mid_bwd_f32", _ptr(dy), _ptr(dx), A, T, F, 0, _st())
+        return dx
+
+
+def mean_mid(x):
+    return _MeanMid.apply(x)
+
+
+# ------------------------------------------------------------------------------------------------ losses
+class _MbLoss(torch.autograd.Function):
+    """s2:135-205.  Returns (total, components[8]); gradients w.r.t. scores and adj come from the same kernel pass."""
+
+    @staticmethod
+    def forward(ctx, scores, adj, pseudo, weights, flag):
+        _cuda(scores, adj, pseudo)
+        B = adj.shape[0]
+        s = _f32c(scores).reshape(B)
+        a = _f32c(adj).reshape(B, 256)
+        ps = _f32c(pseudo).reshape(B)
+        ws = torch.empty(int(L().cvad_mb_loss_ws_floats(B)), device=a.device, dtype=torch.float32)
+        out = torch.empty(8, device=a.device, dtype=torch.float32)
+        ds = torch.empty(B, device=a.device, dtype=torch.float32)
+        da = torch.empty((B, 256), device=a.device, dtype=torch.float32)
+        _call("cvad_mb_loss_f32", _ptr(s), _ptr(a), _ptr(ps), B, *[float(w) for w in weights], _ptr(ws), _ptr(out), _ptr(ds), _ptr(da),
+              _ptr(flag), _st())
+        ctx.save_for_backward(ds, da)
+        ctx.shapes = (scores.shape, adj.shape)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_out):
+        ds, da = ctx.saved_tensors
+        ss, sa = ctx.shapes
+        # g_total is 1 for loss.backward(); scaling by a device scalar keeps general callers correct
+        return (ds * g_total).reshape(ss), (da * g_total).reshape(sa), None, None, None
+
+
+def mb_loss(scores, adj, pseudo, weights=(1.0, 0.01, 0.001, 0.01), flag=None):
+    return _MbLoss.apply(scores, adj, pseudo, tuple(weights), flag)
+
+
+class _BceLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, targets, flag):
+        _cuda(scores, targets)
+        s = _f32c(scores).reshape(-1)
+        y = _f32c(targets).reshape(-1)
+        out = torch.empty(1, device=s.device, dtype=torch.float32)
+        ds = torch.empty_like(s)
+        _call("cvad_bce_loss_f32", _ptr(s), _ptr(y), s.numel(), _ptr(out), _ptr(ds), _ptr(flag), _st())
+        ctx.save_for_backward(ds)
+        ctx.shape = scores.shape
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (ds,) = ctx.saved_tensors
+        return (ds * g).reshape(ctx.shape), None, None
+
+
+def bce_loss(scores, targets, flag=None):
+    return _BceLoss.apply(scores, targets, flag)
+
+
+class _MaLoss(torch.autograd.Function):
+    """cad:649-662 on (direct_predictions (B,2), anomaly_scores (B,), causal_anomaly_scores (B,), kl (B,), labels (B,))."""
+
+    @staticmethod
+    def forward(ctx, probs, final, causal, kl, labels, flag):
+        _cuda(probs, final, causal, kl, labels)
+        B = probs.shape[0]
+        p, f, c, k = _f32c(probs), _f32c(final), _f32c(causal), _f32c(kl)
+        lab = labels.to(torch.int64).contiguous()
+        out = torch.empty(5, device=p.device, dtype=torch.float32)
+        dp, df, dc, dk = torch.empty_like(p), torch.empty_like(f), torch.empty_like(c), torch.empty_like(k)
+        _call("cvad_ma_loss_f32", _ptr(p), _ptr(f), _ptr(c), _ptr(k), _ptr(lab), B, _ptr(out), _ptr(dp), _ptr(df), _ptr(dc), _ptr(dk),
+              _ptr(flag), _st())
+        ctx.save_for_backward(dp, df, dc, dk)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, g, _g2):
+        dp, df, dc, dk = ctx.saved_tensors
+        return dp * g, df * g, dc * g, dk * g, None, None
+
+
+def ma_loss(probs, final, causal, kl, labels, flag=None):
+    return _MaLoss.apply(probs, final, causal, kl, labels, flag)
+
+
+class _LinComb2(torch.autograd.Function):
+    """out = a*x + b*y[:, col]  (cad:574)."""
+
+    @staticmethod
+    def forward(ctx, x, a, y, col, b):
+        _cuda(x, y)
+        x = _f32c(x)
+        y = _f32c(y)
+        n = x.numel()
+        out = torch.empty_like(x)
+        ys = y.shape[1] if y.dim() == 2 else 1
+        yv = y[:, col] if y.dim() == 2 else y
+        _call("cvad_lincomb2_f32", _ptr(out), _ptr(x), 1, float(a), yv.data_ptr(), ys, float(b), n, _st())
+        ctx.meta = (a, b, col, y.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, col, yshape = ctx.meta
+        g = _f32c(g)
+        dx = torch.empty_like(g)
+        _call("cvad_lincomb2_f32", _ptr(dx), _ptr(g), 1, float(a), _ptr(g), 1, 0.0, g.numel(), _st())
+        dy = torch.zeros(yshape, device=g.device, dtype=torch.float32)
+        tgt = dy[:, col] if len(yshape) == 2 else dy
+        tmp = torch.empty_like(g)
+        _call("cvad_lincomb2_f32", _ptr(tmp), _ptr(g), 1, float(b), _ptr(g), 1, 0.0, g.numel(), _st())
+        tgt.copy_(tmp)
+        return dx, None, dy, None, None
+
+
+def lincomb2(x, a, y, col, b):
+    return _LinComb2.apply(x, a, y, col, b)
+
+
+# ------------------------------------------------------------------------------------------------ dropout / helpers
+class _MaskScale(torch.autograd.Function):
+    """y = x * keep_mask / (1-p): a Dropout that is not preceded by one of our GEMMs (mc3:61)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, scale):
+        _cuda(x, mask)
+        y = _f32c(x).clone()
+        mask = _f32c(mask)
+        rows = y.numel() // y.shape[-1]
+        _call("cvad_bias_act_mask_f32", _ptr(y), rows, y.shape[-1], None, ACT_NONE, _ptr(mask), float(scale), _st())
+        ctx.save_for_backward(mask)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = torch.empty_like(dy)
+        _call("cvad_act_mask_bwd_f32", _ptr(dy), None, _ptr(mask), float(ctx.scale), ACT_NONE, _ptr(dx), dy.numel(), _st())
+        return dx, None, None
+
+
+def mask_scale(x, mask, p_drop):
+    return _MaskScale.apply(x, mask, 1.0 / (1.0 - p_drop))
+
+
+_BN_WS = {}
+
+
+def bn_workspace(device, C):
+    """2*C zeroed fp64 accumulators shared by all BN layers of that width on a device (calls are stream-ordered and each
+    call re-zeroes the buffer before returning)."""
+    key = (str(device), int(C))
+    ws = _BN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(2 * C, device=device, dtype=torch.float64)
+        _BN_WS[key] = ws
+    return ws

@@ -1,0 +1,126 @@
+/*
+ * cvad_b200.h -- C ABI of libcvad_b200.so: the B200 (sm_100a) kernels behind the causal video-anomaly hot path.
+ *
+ * The reference (pvvkishore/Causal-Learning-Based-Video-Anomaly-Detection_Paper_Code_Raw) is pure Python/PyTorch and has
+ * no FFI of its own; its seam is the nn.Module / trainer interface.  Each entry point below therefore
+ * names the reference arithmetic (file:line) it replaces; the Python mirror of that interface
+ * (causal-learning-based-video-anomaly-detection_paper_code_raw_b200/) binds these symbols with ctypes.
+ *
+ * Conventions: plain pointers to DEVICE memory and sizes, no torch types; every function is asynchronous on `stream`
+ * (a cudaStream_t passed as void*), allocates nothing, keeps no global state besides a cached SM count, and returns
+ * 0 or the cudaError_t of the failed launch.  All tensors are fp32 unless a name says bf16.
+ */
+#ifndef CVAD_B200_H
+#define CVAD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* activation codes shared by conv / linear / batch-norm epilogues */
+#define CVAD_ACT_NONE 0
+#define CVAD_ACT_RELU 1
+#define CVAD_ACT_LEAKY01 2 /* LeakyReLU(0.1), cad1:133 */
+#define CVAD_ACT_SIGMOID 3
+#define CVAD_ACT_TANH 4
+
+/* Convolution geometry.  xs / ys are ELEMENT strides of the input / output tensors in (n, c, d, h, w) order, so
+ * NCDHW-contiguous torch tensors and channels-last views are both addressable; 2-D convolutions use D = kD = 1. */
+typedef struct cvad_conv_desc {
+  int N, Cin, Din, Hin, Win;
+  int Cout, Dout, Hout, Wout;
+  int kD, kH, kW, sD, sH, sW, pD, pH, pW;
+  long long xs[5];
+  long long ys[5];
+} cvad_conv_desc;
+
+/* Device-resident optimizer bookkeeping (one per flat parameter arena). */
+typedef struct cvad_opt_state {
+  double gradsq;         /* running sum of squared gradients (zeroed by cvad_adam_flat_f32)              */
+  double nonfinite;      /* > 0 when a NaN/Inf gradient was seen this step                                */
+  double last_gradnorm;  /* total gradient norm of the last step (what clip_grad_norm_ returns)            */
+  long long step[8];     /* Adam step count per activity slot; slot 0 = tensors that always receive grads */
+  long long skipped;     /* steps skipped because of a non-finite loss / gradient                         */
+} cvad_opt_state;
+
+/* ---- convolution, fp32 implicit GEMM (conv_f32.cu) -------------------------------------------------------------
+ * nn.Conv3d / nn.Conv2d forward with fused bias + activation: s2:19-21,28-30; mc3:38,44,50; cad:115,130,135; cad1:131-146.
+ * w is torch's OIDHW layout (Cout, Cin, kD, kH, kW), contiguous. */
+int cvad_conv_fwd_f32(const cvad_conv_desc* d, const float* x, const float* w, const float* bias, float* y, int act, void* stream);
+/* input gradient (autograd of the above; also nn.ConvTranspose2d forward, cad1:162-177).  accumulate != 0 adds into dx. */
+int cvad_conv_dgrad_f32(const cvad_conv_desc* d, const float* dy, const float* w, float* dx, int accumulate, void* stream);
+/* weight gradient, ADDED atomically onto dw (OIDHW) -- dw is a slice of the flat gradient arena. */
+int cvad_conv_wgrad_f32(const cvad_conv_desc* d, const float* x, const float* dy, float* dw, void* stream);
+
+/* ---- fully connected layers (linear_f32.cu) ---------------------------------------------------------------------
+ * C[i][j] (+)= sum_k A(i,k) B(k,j);  A(i,k)=A[i*lda+k] if a_kmajor else A[k*lda+i];  B(k,j)=B[j*ldb+k] if b_kmajor else B[k*ldb+j].
+ * Epilogue: +bias[j], activation, *mask[i][j]*mask_scale (dropout keep-mask).  splits>1: split-K with atomic adds onto a
+ * pre-zeroed C and no epilogue.  nn.Linear stacks: s2:24,43-48,77-89; mc3:60-69; cad:167-179,240-246,318-326,361-367,407-413,435-461,525-538. */
+int cvad_sgemm_f32(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor, float* C,
+                   long long ldc, const float* bias, int act, const float* mask, float mask_scale, int accumulate, int splits,
+                   void* stream);
+int cvad_bias_act_mask_f32(float* y, long long rows, int cols, const float* bias, int act, const float* mask, float mask_scale,
+                           void* stream);
+/* dz = dy * mask*mask_scale * act'(y)  (y is the stored, post-mask output; NULL for ACT_NONE) */
+int cvad_act_mask_bwd_f32(const float* dy, const float* y, const float* mask, float mask_scale, int act, float* dz, long long n,
+                          void* stream);
+/* out[j] (+)= sum_i x[i*ld + j]   (bias gradients) */
+int cvad_colsum_f32(const float* x, long long rows, int cols, long long ld, float* out, int accumulate, void* stream);
+
+/* ---- batch norm / pooling (norm_pool_f32.cu); tensors are N,C,(D,)H,W contiguous with S = D*H*W -------------------
+ * nn.BatchNorm2d/3d in train mode: cad:116,131,136; mc3:39,45,51; cad1:132-147.  ws = 2*C zero-initialised doubles
+ * (re-zeroed by the call).  Writes batch mean / invstd and updates running stats (momentum, unbiased variance). */
+int cvad_bn_train_stats_f32(const float* x, int N, int C, long long S, double* ws, float eps, float momentum, float* mean, float* invstd,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+int cvad_bn_eval_prepare_f32(int C, float eps, const float* running_mean, const float* running_var, float* mean, float* invstd,
+                             void* stream);
+/* y = act((x-mean)*invstd*gamma+beta) */
+int cvad_bn_apply_f32(const float* x, float* y, int N, int C, long long S, const float* mean, const float* invstd, const float* gamma,
+                      const float* beta, int act, void* stream);
+/* backward of bn_apply (+activation): dx (may be NULL), dgamma/dbeta ADDED (may be NULL).  training=0 -> frozen statistics. */
+int cvad_bn_bwd_f32(const float* dy, const float* x, float* dx, int N, int C, long long S, const float* mean, const float* invstd,
+                    const float* gamma, const float* beta, int act, int training, double* ws, float* dgamma, float* dbeta, void* stream);
+/* out[c] += sum_{n,s} x[n][c][s]  -- bias gradient of a convolution (autograd of s2:19-21 etc.) */
+int cvad_channel_sum_add_f32(const float* x, int N, int C, long long S, float* out, void* stream);
+/* nn.MaxPool2d/3d: cad:118 (3,2,1); mc3:41,47,53.  idx (int32, may be NULL) = arg-max offset inside each (n,c) plane. */
+int cvad_maxpool_fwd_f32(const float* x, float* y, int* idx, long long planes, int D, int H, int W, int OD, int OH, int OW, int kD, int kH,
+                         int kW, int sD, int sH, int sW, int pD, int pH, int pW, void* stream);
+int cvad_maxpool_bwd_f32(const float* dy, const int* idx, float* dx, long long planes, long long in_size, long long out_size,
+                         void* stream); /* dx pre-zeroed */
+/* nn.AdaptiveAvgPool2d/3d: s2:23 (4,4,4); cad:126 (4,6); mc3:56 (1,1,1) */
+int cvad_adaptive_avgpool_fwd_f32(const float* x, float* y, long long planes, int D, int H, int W, int OD, int OH, int OW, void* stream);
+int cvad_adaptive_avgpool_bwd_f32(const float* dy, float* dx, long long planes, int D, int H, int W, int OD, int OH, int OW, void* stream);
+/* mean over the middle axis of (A,T,F): cad:568 features.mean(dim=1) */
+int cvad_mean_mid_fwd_f32(const float* x, float* y, long long A, int T, long long F, void* stream);
+int cvad_mean_mid_bwd_f32(const float* dy, float* dx, long long A, int T, long long F, int accumulate, void* stream);
+
+/* ---- losses (loss_optim.cu) ---------------------------------------------------------------------------------------
+ * ImprovedMiniCausalVAD.compute_improved_loss, s2:135-205.  pseudo (B) in {0,1} = (rand > 0.95) drawn by the caller.
+ * out8 = {total, anomaly, acyclicity, sparsity, consistency, structure, edge_count, sparsity_ratio}; dscores (B), dadj (B,256).
+ * ws: cvad_mb_loss_ws_floats(B) floats.  nonfinite_flag (may be NULL) is set to 1 when the loss is NaN/Inf (s2:230). */
+long long cvad_mb_loss_ws_floats(int B);
+int cvad_mb_loss_f32(const float* scores, const float* adj, const float* pseudo, int B, float w_anom, float w_causal, float w_sparse,
+                     float w_cons, float* ws, float* out8, float* dscores, float* dadj, float* nonfinite_flag, void* stream);
+/* nn.BCELoss (mean) + gradient, mc3:240,287 (+ the NaN/Inf guards of mc3:282-292 as a device flag) */
+int cvad_bce_loss_f32(const float* scores, const float* targets, int B, float* out1, float* dscores, float* nonfinite_flag, void* stream);
+/* cad:649-662: out5 = {total, CE(on softmax probs), MSE(final), MSE(causal), KL}; gradients may be NULL (all or none) */
+int cvad_ma_loss_f32(const float* probs, const float* final_scores, const float* causal_scores, const float* kl, const long long* labels,
+                     int B, float* out5, float* dprobs, float* dfinal, float* dcausal, float* dkl, float* nonfinite_flag, void* stream);
+
+/* ---- optimizer over a flat arena (loss_optim.cu) ---------------------------------------------------------------------
+ * Arena layout: block 0 (1024 floats) is a header -- header[0] = non-finite-loss flag, header[1..7] = per-slot "this group
+ * received a gradient" flags; every tensor starts on a 1024-float boundary.  block_slot[b] = -1 (header/padding), 0 (always
+ * stepped) or 1..7 (stepped only when header[slot] > 0; torch skips tensors whose grad is None: cad:615-617 + SURVEY fact 6).
+ * clip_grad_norm_ + AdamW: s2:236-238, cad:665-667; Adam with L2 decay and clip-if-norm>threshold: mc3:298-311. */
+int cvad_sumsq_f32(const float* g, long long n, float scale, cvad_opt_state* state, void* stream);
+int cvad_adam_flat_f32(float* p, const float* g, float* m, float* v, long long n, const int* block_slot, cvad_opt_state* state,
+                       float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled, int clip_mode,
+                       float max_norm, float clip_threshold, int nan_mode, void* stream);
+int cvad_fill_f32(float* x, long long n, float value, void* stream);
+/* out[i] = a*x[i*xs] + b*y[i*ys]   (score fusion 0.6*causal + 0.4*direct[:,1], cad:574) */
+int cvad_lincomb2_f32(float* out, const float* x, long long xs, float a, const float* y, long long ys, float b, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVAD_B200_H */

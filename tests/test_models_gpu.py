@@ -1,0 +1,207 @@
+"""Model-level parity on the B200 against the golden fixtures produced by the reference (tests/golden) and the oracle."""
+import copy
+import os
+
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b, floor=1e-3):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+# --------------------------------------------------------------------------------------------------------- M-B
+def test_mb_eval_parity_fp32(dev, gold):
+    """a1-a3: scores / adjacency / features within 1e-5 relative (north-star fp32 tolerance), identical ranking."""
+    from cvad_b200.mb import CausalAnomalyDetector
+    g = gold("mb.pt")
+    m = CausalAnomalyDetector().to(dev)
+    m.load_state_dict(gold("best_improved_model.pth")["model_state_dict"], strict=True)
+    m.eval()
+    for c in g["eval"]:
+        x = (synth.mb_clips_bright if c["bright"] else synth.mb_clips)(c["B"], c["T"], c["H"], c["W"], c["seed"])
+        with torch.no_grad():
+            s, a, f = m(x.to(dev))
+        assert s.shape == (c["B"], 1) and a.shape == (c["B"], 16, 16) and f.shape == (c["B"], 16)
+        assert rel(s, c["scores"]) < 1e-5, (c, rel(s, c["scores"]))
+        assert rel(a, c["adj"]) < 1e-5
+        assert rel(f, c["feat"]) < 1e-5
+        assert torch.equal(((a.cpu() > 0.1).sum((1, 2))), (c["adj"] > 0.1).sum((1, 2)))
+    ka = g["known_answers"]["scores_T8"]
+    x = synth.mb_clips(4, 8, 64, 64, 1234)
+    with torch.no_grad():
+        s, _, _ = m(x.to(dev))
+    assert rel(s.flatten(), torch.tensor(ka)) < 1e-5
+
+
+def test_mb_train_step_parity(dev, gold):
+    """a4-a5: loss, the 7 components and every parameter gradient of one training forward/backward."""
+    from cvad_b200.mb import COMPONENT_KEYS, ImprovedMiniCausalVAD
+    from cvad_b200.noise import FixedNoise
+    g = gold("mb.pt")
+    ck = gold("best_improved_model.pth")
+    for c in g["train"]:
+        tr = ImprovedMiniCausalVAD(device=dev, verbose=False)
+        tr.model.load_state_dict(ck["model_state_dict"], strict=True)
+        tr.model.train()
+        tr.model.noise = FixedNoise({"feat": c["keep_feat"], "graph": c["keep_graph"]})
+        x = synth.mb_clips_bright(c["B"], c["T"], 64, 64, c["seed"]).to(dev)
+        tr.optimizer.zero_grad()
+        s, a, f = tr.model(x)
+        loss, comp = tr.loss_on_device(s, a, torch.zeros(c["B"], device=dev), c["pseudo"].to(dev))
+        loss.backward()
+        assert rel(loss, c["loss"]) < 1e-5
+        for i, k in enumerate(COMPONENT_KEYS):
+            assert abs(float(comp[i + 1]) - c["comps"][k]) <= 1e-5 * max(1.0, abs(c["comps"][k])), k
+        assert rel(s, c["scores"]) < 1e-5 and rel(a, c["adj"]) < 1e-5
+        for k, p in tr.model.named_parameters():
+            sm = c["grad_summary"][k]
+            assert abs(float(p.grad.double().norm()) - sm["norm"]) <= 2e-4 * max(sm["norm"], 1e-7), k
+            assert rel(p.grad.flatten()[:16], sm["head"], floor=sm["absmax"] + 1e-12) < 2e-4, k
+            if c["grads"][k] is not None:
+                assert rel(p.grad, c["grads"][k], floor=sm["absmax"] + 1e-12) < 2e-4, k
+
+
+def test_mb_trajectory_from_shipped_checkpoint(dev, gold):
+    """3 optimizer steps from best_improved_model.pth incl. its AdamW state == the reference's trajectory (s2:221-238)."""
+    from cvad_b200.mb import ImprovedMiniCausalVAD
+    from cvad_b200.noise import FixedNoise
+    g = gold("mb.pt")["trajectory"]
+    ck = gold("best_improved_model.pth")
+    tr = ImprovedMiniCausalVAD(device=dev, verbose=False)
+    tr.model.load_state_dict(ck["model_state_dict"], strict=True)
+    tr.optimizer.load_state_dict(copy.deepcopy(ck["optimizer_state_dict"]))
+    tr.model.train()
+    for it, sd in enumerate(g["seeds"]):
+        x = synth.mb_clips_bright(8, 8, 64, 64, sd).to(dev)
+        tr.model.noise = FixedNoise({"feat": synth.keep_mask((8, 16), 0.3, sd + 1), "graph": synth.keep_mask((8, 128), 0.3, sd + 2)})
+        pseudo = (g["steps"][it]["u"] > 0.95).float().to(dev)
+        comp = tr.train_step(x, torch.zeros(8, device=dev), pseudo)
+        assert abs(float(comp[0]) - g["losses"][it]) < 2e-5 * max(1, abs(g["losses"][it])), it
+        assert abs(tr.optimizer.last_grad_norm() - g["steps"][it]["grad_norm"]) < 2e-4 * g["steps"][it]["grad_norm"]
+    sd = tr.model.state_dict()
+    for k, v in g["final_small"].items():
+        assert rel(sd[k], v) < 2e-5, k
+    for k, sm in g["final_summary"].items():
+        assert abs(float(sd[k].double().norm()) - sm["norm"]) < 1e-5 * max(sm["norm"], 1e-6), k
+    osd = tr.optimizer.state_dict()
+    assert float(osd["state"][0]["step"]) == g["final_opt_step"]
+    # checkpoint round trip through stock torch (s2:437-443 layout)
+    path = "/tmp/cvad_roundtrip.pth"
+    torch.save({"model_state_dict": tr.model.state_dict(), "optimizer_state_dict": osd, "epoch": 0, "eval_metrics": {}}, path)
+    back = torch.load(path, map_location="cpu", weights_only=False)
+    ref_opt_keys = set(ck["optimizer_state_dict"]["param_groups"][0].keys())
+    assert set(back["optimizer_state_dict"]["param_groups"][0].keys()) == ref_opt_keys
+    stock = torch.optim.AdamW([torch.nn.Parameter(v.clone()) for v in back["model_state_dict"].values()], lr=5e-4, weight_decay=1e-3)
+    stock.load_state_dict(back["optimizer_state_dict"])
+
+
+def test_mb_epoch_api_and_nan_skip(dev, gold):
+    from cvad_b200.mb import ImprovedMiniCausalVAD, MiniCausalVAD
+    tr = ImprovedMiniCausalVAD(device=dev, verbose=False)
+    tr.model.load_state_dict(gold("best_improved_model.pth")["model_state_dict"], strict=True)
+    loader = [(synth.mb_clips_bright(4, 8, 64, 64, 200 + i), torch.zeros(4)) for i in range(3)]
+    avg, comps = tr.train_epoch_improved(loader)
+    assert set(comps) == {"anomaly_loss", "acyclicity_loss", "sparsity_loss", "consistency_loss", "structure_loss", "edge_count",
+                          "sparsity_ratio"}
+    assert avg == avg and avg > 0
+    preds, graphs, metrics = tr.evaluate_improved(loader)
+    assert preds.shape == (12,) and graphs.shape == (12, 16, 16) and len(metrics) == 8
+    before = {k: v.clone() for k, v in tr.model.state_dict().items()}
+    bad = loader[0][0].clone()
+    bad[0, 0, 0, 0, 0] = float("nan")
+    tr.model.train()
+    tr.train_step(bad.to(dev), torch.zeros(4, device=dev))
+    assert tr.optimizer.skipped_steps() == 1
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(v, before[k]), k
+    m = MiniCausalVAD(device=dev)
+    loss, c4 = m.train_epoch(loader)
+    assert set(c4) == {"anomaly_loss", "acyclicity_loss", "sparsity_loss", "consistency_loss"}
+    p, _, gr = m.evaluate(loader)
+    assert p.shape == (12,) and gr.shape == (12, 16, 16)
+    m.save_model("/tmp/cvad_mini.pth")
+    m.load_model("/tmp/cvad_mini.pth")
+    for pg in m.optimizer.param_groups:
+        pg["lr"] = 1e-4          # s1:104-106
+
+
+# --------------------------------------------------------------------------------------------------------- M-C
+def _mc_synth(g):
+    st = synth.synth_fill(g["init_state"], seed=g["state_seed"])
+    for k in st:
+        if k.startswith("classifier") and k.endswith("weight"):
+            st[k] = st[k] * 3.0
+    return st
+
+
+def test_mc_eval_parity(dev, gold):
+    from cvad_b200.mc import SimpleVideoAnomalyDetector
+    g = gold("mc.pt")
+    m = SimpleVideoAnomalyDetector().to(dev)
+    for c in g["eval"]:
+        m.load_state_dict(g["init_state"] if c["weights"] == "init" else _mc_synth(g), strict=True)
+        m.eval()
+        x = synth.mc_clips(c["B"], c["T"], c["H"], c["W"], c["seed"]).to(dev)
+        with torch.no_grad():
+            s = m(x)
+        assert s.shape == (c["B"], 1)
+        assert rel(s, c["scores"]) < 1e-5, c
+
+
+def test_mc_train_step_parity(dev, gold):
+    from cvad_b200 import ops
+    from cvad_b200.mc import SimpleVideoAnomalyDetector
+    from cvad_b200.noise import FixedNoise
+    g = gold("mc.pt")
+    for c in g["train"]:
+        m = SimpleVideoAnomalyDetector().to(dev)
+        m.load_state_dict(_mc_synth(g), strict=True)
+        m.train()
+        m.noise = FixedNoise({"cls0": c["keep0"], "cls1": c["keep1"]})
+        x = synth.mc_clips(c["B"], c["T"], 64, 64, c["seed"]).to(dev)
+        s = m(x)
+        loss = ops.bce_loss(s.reshape(-1), c["y"].to(dev))
+        loss.backward()
+        assert rel(loss, c["loss"]) < 1e-5
+        assert rel(s, c["scores"]) < 1e-5
+        gscale = max(float(v.abs().max()) for v in c["grads"].values())
+        for k, p in m.named_parameters():
+            assert rel(p.grad, c["grads"][k], floor=gscale) < 2e-4, k
+        sd = m.state_dict()
+        for k, v in c["new_stats"].items():
+            assert rel(sd[k].float(), v.float()) < 1e-5, k
+
+
+def test_mc_trajectory_and_trainer(dev, gold):
+    from cvad_b200.mc import SimpleVideoAnomalyDetector, StableTrainer, roc_auc
+    from cvad_b200.noise import FixedNoise
+    g = gold("mc.pt")
+    tj = g["trajectory"]
+    m = SimpleVideoAnomalyDetector()
+    m.load_state_dict(_mc_synth(g), strict=True)
+    tr = StableTrainer(m, [], [], dev, lr=1e-3)
+    tr.model.train()
+    for it, sd in enumerate(tj["seeds"]):
+        x = synth.mc_clips(4, 8, 64, 64, sd).to(dev)
+        y = (torch.rand(4, generator=synth.gen(sd + 5)) > 0.5).float().to(dev)
+        tr.model.noise = FixedNoise({"cls0": synth.keep_mask((4, 32), 0.5, sd + 1), "cls1": synth.keep_mask((4, 16), 0.3, sd + 2)})
+        loss, _ = tr.train_step(x, y)
+        assert abs(float(loss) - tj["losses"][it]) < 1e-4 * max(1, abs(tj["losses"][it])), it
+    sd = tr.model.state_dict()
+    for k, v in tj["final"].items():
+        assert rel(sd[k].float(), v.float()) < 1e-4, k
+    import numpy as np
+    t = np.array([0, 1, 1, 0, 1, 0]); s = np.array([0.1, 0.8, 0.4, 0.4, 0.9, 0.2])
+    assert abs(roc_auc(t, s) - (8.5 / 9)) < 1e-12
+    loader = [(synth.mc_clips(4, 8, 64, 64, 300 + i), (torch.arange(4) % 2).float()) for i in range(2)]
+    tr2 = StableTrainer(SimpleVideoAnomalyDetector(), loader, loader, dev)
+    l, a = tr2.train_epoch()
+    tl, auc, acc = tr2.evaluate()
+    assert l > 0 and 0 <= a <= 1 and 0 <= auc <= 1

@@ -1,0 +1,204 @@
+"""The oracle restatement (oracle/) against the committed golden fixtures produced by the reference itself
+(tools/make_golden.py).  Runs on CPU; pins the oracle without needing /root/reference."""
+import os
+
+import pytest
+import torch
+
+import synth
+from oracle import ma as o_ma
+from oracle import mb as o_mb
+from oracle import mc as o_mc
+from oracle import optim as o_opt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b, floor=1e-3):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+def test_mb_eval_matches_reference(gold):
+    g = gold("mb.pt")
+    P = gold("best_improved_model.pth")["model_state_dict"]
+    for c in g["eval"]:
+        x = (synth.mb_clips_bright if c["bright"] else synth.mb_clips)(c["B"], c["T"], c["H"], c["W"], c["seed"])
+        with torch.no_grad():
+            s, a, f = o_mb.mb_forward(P, x)
+        assert rel(s, c["scores"]) < 1e-5 and rel(a, c["adj"]) < 1e-5 and rel(f, c["feat"]) < 1e-5
+    assert rel(g["eval"][0]["scores"].flatten(), g["known_answers"]["scores_T8"]) < 1e-5
+
+
+def test_mb_train_loss_and_grads_match_reference(gold):
+    g = gold("mb.pt")
+    P0 = gold("best_improved_model.pth")["model_state_dict"]
+    for c in g["train"]:
+        P = {k: v.clone().requires_grad_(True) for k, v in P0.items()}
+        x = synth.mb_clips_bright(c["B"], c["T"], 64, 64, c["seed"])
+        s, a, f = o_mb.mb_forward(P, x, True, c["keep_feat"], c["keep_graph"])
+        loss, comps = o_mb.mb_loss(s, a, c["pseudo"])
+        loss.backward()
+        assert rel(loss, c["loss"]) < 1e-5
+        for k, v in c["comps"].items():
+            assert abs(comps[k] - v) <= 1e-5 * max(1.0, abs(v)), k
+        for k, sm in c["grad_summary"].items():
+            assert abs(float(P[k].grad.double().norm()) - sm["norm"]) <= 1e-4 * max(sm["norm"], 1e-6), k
+
+
+def test_mb_loss32_and_input_grads(gold):
+    c = gold("mb.pt")["loss32"]
+    sc = c["scores"].clone().requires_grad_(True)
+    ad = c["adj"].clone().requires_grad_(True)
+    loss, comps = o_mb.mb_loss(sc, ad, c["pseudo"])
+    loss.backward()
+    assert rel(loss, c["loss"]) < 1e-6
+    assert rel(sc.grad, c["dscores"]) < 1e-5 and rel(ad.grad, c["dadj"]) < 1e-5
+
+
+def test_mb_trajectory_with_oracle_optimizer(gold):
+    """3 AdamW steps from the shipped checkpoint incl. its optimizer state (s2:221-238)."""
+    g = gold("mb.pt")["trajectory"]
+    ck = gold("best_improved_model.pth")
+    names = list(ck["model_state_dict"].keys())
+    P = {k: v.clone() for k, v in ck["model_state_dict"].items()}
+    st = ck["optimizer_state_dict"]["state"]
+    M = {k: st[i]["exp_avg"].clone() for i, k in enumerate(names)}
+    V = {k: st[i]["exp_avg_sq"].clone() for i, k in enumerate(names)}
+    step = int(st[0]["step"])
+    for it, sd in enumerate(g["seeds"]):
+        Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        x = synth.mb_clips_bright(8, 8, 64, 64, sd)
+        kf, kg = synth.keep_mask((8, 16), 0.3, sd + 1), synth.keep_mask((8, 128), 0.3, sd + 2)
+        pseudo = (g["steps"][it]["u"] > 0.95).float()
+        s, a, f = o_mb.mb_forward(Pg, x, True, kf, kg)
+        loss, _ = o_mb.mb_loss(s, a, pseudo)
+        loss.backward()
+        assert abs(float(loss) - g["losses"][it]) < 1e-5 * max(1, abs(g["losses"][it]))
+        norm, grads = o_opt.clip_grad_norm([Pg[k].grad for k in names], 0.5)
+        assert abs(float(norm) - g["steps"][it]["grad_norm"]) < 1e-4 * g["steps"][it]["grad_norm"]
+        step += 1
+        for k, gr in zip(names, grads):
+            P[k], M[k], V[k] = o_opt.adamw_step(P[k], gr, M[k], V[k], step, 5e-4, weight_decay=1e-3)
+    for k, v in g["final_small"].items():
+        assert rel(P[k], v) < 1e-5, k
+    assert step == g["final_opt_step"]
+
+
+def test_mc_matches_reference(gold):
+    g = gold("mc.pt")
+    synth_state = synth.synth_fill(g["init_state"], seed=g["state_seed"])
+    for k in synth_state:
+        if k.startswith("classifier") and k.endswith("weight"):
+            synth_state[k] = synth_state[k] * 3.0
+    for c in g["eval"]:
+        st = g["init_state"] if c["weights"] == "init" else synth_state
+        x = synth.mc_clips(c["B"], c["T"], c["H"], c["W"], c["seed"])
+        with torch.no_grad():
+            s = o_mc.mc_forward(st, x)
+        assert rel(s, c["scores"]) < 1e-5
+    for c in g["train"]:
+        P = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+             for k, v in synth_state.items()}
+        x = synth.mc_clips(c["B"], c["T"], 64, 64, c["seed"])
+        ns = {}
+        s = o_mc.mc_forward(P, x, True, c["keep0"], c["keep1"], ns)
+        loss = o_mc.bce(s, c["y"])
+        loss.backward()
+        assert rel(loss, c["loss"]) < 1e-5
+        gscale = max(float(v.abs().max()) for v in c["grads"].values())
+        for k, v in c["grads"].items():
+            assert rel(P[k].grad, v, floor=gscale) < 1e-4, k
+        for k, v in c["new_stats"].items():
+            assert rel(ns[k].float(), v.float()) < 1e-5, k
+
+
+def test_ma_matches_reference(gold):
+    from oracle.ma import ma_forward, ma_loss
+    g = gold("ma.pt")
+    import torch.nn as nn
+    for c in g["cases"]:
+        P = ma_synth_state(c["seed"], c["live"])
+        x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"])
+        eps, keep = ma_noise(c)
+        with torch.no_grad():
+            out = ma_forward(P, x, eps, c["train"], keep)
+            loss, comps = ma_loss(out, c["labels"])
+        assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 1e-4
+        assert rel(out["direct_predictions"], c["direct_predictions"]) < 1e-4
+        assert rel(out["kl_losses"], c["kl_losses"]) < 1e-4
+        assert torch.equal(out["det_counts"], c["det_counts"])
+        assert rel(loss, c["loss"]) < 1e-4
+
+
+# ---- shared helpers for M-A fixtures (also used by the GPU tests) -------------------------------------------------
+def ma_reference_shapes():
+    """state_dict skeleton of causal_anomaly_detection.CausalAnomalyDetector (cad:508-538), built without the reference."""
+    import collections
+    sd = collections.OrderedDict()
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = torch.zeros(co, ci, k, k)
+        sd[name + ".bias"] = torch.zeros(co)
+
+    def bn(name, c):
+        sd[name + ".weight"] = torch.ones(c); sd[name + ".bias"] = torch.zeros(c)
+        sd[name + ".running_mean"] = torch.zeros(c); sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0)
+
+    def lin(name, o, i):
+        sd[name + ".weight"] = torch.zeros(o, i)
+        sd[name + ".bias"] = torch.zeros(o)
+
+    conv("backbone.conv1", 32, 1, 7); bn("backbone.bn1", 32)
+    cin = 32
+    for li, co in zip((1, 2, 3, 4), (32, 64, 128, 256)):
+        conv(f"backbone.layer{li}.0", co, cin, 3); bn(f"backbone.layer{li}.1", co)
+        conv(f"backbone.layer{li}.3", co, co, 3); bn(f"backbone.layer{li}.4", co)
+        cin = co
+    for idx, (o, i) in zip((0, 3, 6, 8, 10), ((512, 6144), (256, 512), (128, 256), (64, 128), (20, 64))):
+        lin(f"detector.detector_net.{idx}", o, i)
+    for idx, (o, i) in zip((0, 2, 4), ((32, 4), (64, 32), (64, 64))):
+        lin(f"tracker.reid_net.{idx}", o, i)
+    sd["traj_encoder.gru.weight_ih_l0"] = torch.zeros(192, 68); sd["traj_encoder.gru.weight_hh_l0"] = torch.zeros(192, 64)
+    sd["traj_encoder.gru.bias_ih_l0"] = torch.zeros(192); sd["traj_encoder.gru.bias_hh_l0"] = torch.zeros(192)
+    lin("traj_encoder.encoder", 32, 64)
+    lin("causal_extractor.encoder.0", 32, 32); lin("causal_extractor.encoder.2", 32, 32)
+    lin("causal_extractor.mu_head", 6, 32); lin("causal_extractor.logvar_head", 6, 32)
+    sd["structure_learner.structure_params"] = torch.zeros(6, 6)
+    lin("structure_learner.node_encoder", 32, 6)
+    lin("structure_learner.edge_predictor.0", 32, 64); lin("structure_learner.edge_predictor.2", 1, 32)
+    for idx, (o, i) in zip((0, 2, 4), ((32, 6), (32, 32), (6, 32))):
+        lin(f"dynamics_predictor.dynamics_net.{idx}", o, i)
+    for idx, (o, i) in zip((0, 3, 5), ((64, 18), (32, 64), (1, 32))):
+        lin(f"anomaly_scorer.causal_scorer.{idx}", o, i)
+    for idx, (o, i) in zip((0, 2, 4), ((32, 12), (16, 32), (1, 16))):
+        lin(f"anomaly_scorer.motion_scorer.{idx}", o, i)
+    for idx, (o, i) in zip((0, 2, 4), ((32, 6), (16, 32), (1, 16))):
+        lin(f"anomaly_scorer.temporal_scorer.{idx}", o, i)
+    for idx, (o, i) in zip((0, 3, 6, 8, 10), ((512, 6144), (256, 512), (128, 256), (64, 128), (2, 64))):
+        lin(f"direct_classifier.{idx}", o, i)
+    return sd
+
+
+DET_BIAS_SAT = [180, 120, 25, 50, 150, 100, 20, 45, 210, 140, 30, 55, 120, 80, 22, 48, 240, 160, 28, 52]     # cad:186-192
+DET_BIAS_LIVE = [0.0, 0.0, -0.5, -0.5, 0.3, -0.2, 0.0, 0.2, -3.5, 0.1, 0.0, 0.0, 0.4, 3.5, 0.0, 0.0, 0.1, -0.1, 4.5, 0.0]
+
+
+def ma_synth_state(seed, live):
+    sd = ma_reference_shapes()
+    sd["detector.detector_net.10.bias"] = torch.tensor(DET_BIAS_SAT, dtype=torch.float32)
+    P = synth.synth_fill(sd, seed=seed, skip=("detector.detector_net.10.bias",))
+    if live:
+        P["detector.detector_net.10.bias"] = torch.tensor(DET_BIAS_LIVE)
+        P["detector.detector_net.10.weight"] = P["detector.detector_net.10.weight"] * 24.0
+    return P
+
+
+def ma_noise(c):
+    B, T, xs = c["B"], c["T"], c["xseed"]
+    eps = torch.randn(B, 5, 6, generator=synth.gen(xs + 1))
+    keep = {"det0": synth.keep_mask((B, T, 512), 0.3, xs + 2), "det1": synth.keep_mask((B, T, 256), 0.2, xs + 3),
+            "scorer0": synth.keep_mask((B, 64), 0.2, xs + 4), "cls0": synth.keep_mask((B, 512), 0.3, xs + 5),
+            "cls1": synth.keep_mask((B, 256), 0.2, xs + 6)}
+    return eps, keep
