@@ -120,6 +120,48 @@ int cvad_fill_f32(float* x, long long n, float value, void* stream);
 /* out[i] = a*x[i*xs] + b*y[i*ys]   (score fusion 0.6*causal + 0.4*direct[:,1], cad:574) */
 int cvad_lincomb2_f32(float* out, const float* x, long long xs, float a, const float* y, long long ys, float b, long long n, void* stream);
 
+/* ---- M-A causal branch, dense masked batched form (ma_tail.cu) -------------------------------------------------------
+ * Every clip carries 5 padded track slots (the detector emits <= 5 boxes per frame, cad:178,198) and a per-clip track
+ * count; rows = B*T frames.  Replaces the ragged Python-list loops of cad:206-228, 251-272, 290-307, 337-350, 375-396,
+ * 418-424, 466-500 (thousands of batch-1 launches and host syncs per forward). */
+/* cad:198-228: box = sigmoid(raw)*scale+offset, validity window, in-order compaction, fallback box when none valid.
+ * box (rows,5,4), cnt (rows) int32 >= 1, src (rows,5) int32 = original detection index of each kept slot or -1.
+ * active_flag (may be NULL) is set to 1 when any real detection was kept (the detector then receives gradients). */
+int cvad_det_decode_f32(const float* raw, long long rows, float* box, int* cnt, int* src, float* active_flag, void* stream);
+int cvad_det_decode_bwd_f32(const float* raw, const float* dbox, const int* src, long long rows, float* draw, void* stream);
+/* cad:251-269: traj (B,5,T,4+reid_dim) = [box | reid] per kept slot, zero rows for padding; ntr[b] = max_t cnt[b,t];
+ * multi_flag (may be NULL) is set to 1 when some clip has >= 2 tracks (only then does the edge MLP get gradients). */
+int cvad_traj_assemble_f32(const float* box, const float* reid, const int* cnt, int B, int T, int reid_dim, float* traj, int* ntr,
+                           float* multi_flag, void* stream);
+int cvad_traj_assemble_bwd_f32(const float* dtraj, const int* cnt, int B, int T, int reid_dim, float* dbox, float* dreid, void* stream);
+/* cad:284,298-299: nn.GRU(68->64) recurrence over T for the B*5 track slots (gi = x W_ih^T + b_ih precomputed, (B*5,T,192));
+ * hT (B*5,64) last hidden state (zeros for slots >= ntr[b]); saved (B*5,T,5,64) = r,z,n,gh_n,h_prev for the backward. */
+int cvad_gru_fwd_f32(const float* gi, const float* w_hh, const float* b_hh, const int* ntr, int B, int T, float* hT, float* saved,
+                     void* stream);
+int cvad_gru_bwd_f32(const float* dhT, const float* saved, const float* w_hh, const int* ntr, int B, int T, float* dgi, float* dw_hh,
+                     float* db_hh, void* stream); /* dw_hh / db_hh are ADDED */
+/* cad:328-347: z = mu + eps*exp(logvar/2) (B,5,6), kl (B) = mean over the clip's tracks of -0.5*sum(1+lv-mu^2-e^lv) */
+int cvad_reparam_kl_f32(const float* mu, const float* logvar, const float* eps, const int* ntr, int B, float* z, float* kl, void* stream);
+int cvad_reparam_kl_bwd_f32(const float* mu, const float* logvar, const float* eps, const int* ntr, int B, const float* dz,
+                            const float* dkl, float* dmu, float* dlogvar, void* stream);
+/* cad:385: pair (B,5,5,2*node_dim) = [node_i | node_j] */
+int cvad_pair_concat_f32(const float* node, int B, int node_dim, float* pair, void* stream);
+int cvad_pair_concat_bwd_f32(const float* dpair, int B, int node_dim, float* dnode, void* stream);
+/* cad:380-390: adj (B,6,6) from edge probabilities e (B,5,5): i != j and i,j < ntr[b]; backward=1 maps dadj -> de */
+int cvad_adj_assemble_f32(const float* src, const int* ntr, int B, float* dst, int backward, void* stream);
+/* cad:420: structured[b,k,:] = adj[b] @ z[b,k,:] */
+int cvad_structured_f32(const float* adj, const float* z, int B, float* out, void* stream);
+int cvad_structured_bwd_f32(const float* adj, const float* z, const float* dout, int B, float* dadj, float* dz, void* stream);
+/* cad:469-494: masked track means cur/prd, cin (B,18) = [cur|prd||cur-prd|], min (B,12) = [cur|prd], tin (B,6) = cur */
+int cvad_scorer_inputs_f32(const float* z, const float* pred, const int* ntr, int B, float* cin, float* min_, float* tin, void* stream);
+int cvad_scorer_inputs_bwd_f32(const float* cin, const int* ntr, int B, const float* dcin, const float* dmin, const float* dtin, float* dz,
+                               float* dpred, void* stream);
+/* cad:497: 0.5*causal + 0.3*motion + 0.2*temporal */
+int cvad_lincomb3_f32(float* out, const float* x, float a, const float* y, float b, const float* z, float c, long long n, void* stream);
+/* cad:537: nn.Softmax(dim=-1) over rows of C (small) entries */
+int cvad_softmax_rows_f32(const float* x, long long rows, int C, float* y, void* stream);
+int cvad_softmax_rows_bwd_f32(const float* y, const float* dy, long long rows, int C, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

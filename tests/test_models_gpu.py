@@ -196,6 +196,11 @@ def test_mc_trajectory_and_trainer(dev, gold):
         assert abs(float(loss) - tj["losses"][it]) < 1e-4 * max(1, abs(tj["losses"][it])), it
     sd = tr.model.state_dict()
     for k, v in tj["final"].items():
+        if k in ("features.0.bias", "features.4.bias", "features.8.bias"):
+            # conv biases feeding BatchNorm have an analytically zero gradient: Adam normalises pure round-off noise into
+            # +-lr steps, so these follow a noise-driven walk in the reference too; bound it by the 3 steps taken.
+            assert float((sd[k].cpu() - v).abs().max()) <= 2 * 3 * 1e-3 + 1e-6, k
+            continue
         assert rel(sd[k].float(), v.float()) < 1e-4, k
     import numpy as np
     t = np.array([0, 1, 1, 0, 1, 0]); s = np.array([0.1, 0.8, 0.4, 0.4, 0.9, 0.2])
@@ -205,3 +210,89 @@ def test_mc_trajectory_and_trainer(dev, gold):
     l, a = tr2.train_epoch()
     tl, auc, acc = tr2.evaluate()
     assert l > 0 and 0 <= a <= 1 and 0 <= auc <= 1
+
+
+# --------------------------------------------------------------------------------------------------------- M-A
+def _ma_model(dev, c):
+    from test_oracle_golden import ma_noise, ma_synth_state
+    from cvad_b200.ma import CausalAnomalyDetector
+    from cvad_b200.noise import FixedNoise
+    m = CausalAnomalyDetector()
+    m.load_state_dict(ma_synth_state(c["seed"], c["live"]), strict=True)
+    eps, keep = ma_noise(c)
+    noise = FixedNoise({"eps": eps, **keep})
+    return m, noise
+
+
+@pytest.mark.parametrize("idx", [0, 2])
+def test_ma_eval_parity_fp32(dev, gold, idx):
+    """a7-a15 forward in eval mode (fp32 path): scores, probabilities, KL, adjacency, detections vs the reference."""
+    c = gold("ma.pt")["cases"][idx]
+    assert not c["train"]
+    m, noise = _ma_model(dev, c)
+    m = m.to(dev).eval()
+    m.noise = noise
+    x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"]).to(dev)
+    with torch.no_grad():
+        out = m(x)
+    assert set(out) >= {"anomaly_scores", "causal_factors", "adjacency_matrices", "kl_losses", "detections", "direct_predictions",
+                        "causal_anomaly_scores"}
+    assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 2e-5
+    assert rel(out["causal_anomaly_scores"], c["causal_anomaly_scores"]) < 2e-5
+    assert rel(out["direct_predictions"], c["direct_predictions"]) < 2e-5
+    d = out["dense"]
+    assert rel(d["kl_losses"], c["kl_losses"]) < 2e-5
+    assert rel(d["adjacency_matrices"], c["adjacency"]) < 2e-5
+    assert torch.equal(d["det_counts"].cpu().long(), c["det_counts"])
+    assert torch.equal(d["n_tracks"].cpu().long(), c["n_tracks"])
+    assert rel(d["detections"], c["detections"]) < 2e-5
+    assert abs(float(d["features"].double().norm()) - c["features_summary"]["norm"]) < 1e-5 * c["features_summary"]["norm"]
+    # ragged views of the reference's output dict
+    n = c["n_tracks"].tolist()
+    assert len(out["causal_factors"]) == c["B"] and out["causal_factors"][0].shape == (n[0], 6)
+    assert len(out["detections"][0]) == c["T"] and out["detections"][0][0].shape == (int(c["det_counts"][0, 0]), 4)
+    assert len(out["kl_losses"]) == c["B"] and out["adjacency_matrices"][0].shape == (6, 6)
+
+
+@pytest.mark.parametrize("idx", [1, 3])
+def test_ma_train_step_parity_fp32(dev, gold, idx):
+    """a16: 4-term loss, gradients of every parameter, BN running statistics, and the grad-is-None groups."""
+    from cvad_b200.ma import MATrainer
+    c = gold("ma.pt")["cases"][idx]
+    assert c["train"]
+    m, noise = _ma_model(dev, c)
+    tr = MATrainer(m, dev, precision="fp32")
+    tr.model.train()
+    tr.model.noise = noise
+    x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"]).to(dev)
+    labels = c["labels"].to(dev)
+    tr.optimizer.zero_grad()
+    out = tr.model(x)
+    loss, comp = tr.loss_on_device(out, labels)
+    loss.backward()
+    assert rel(loss, c["loss"]) < 5e-5
+    for i, k in enumerate(("classification", "anomaly", "causal", "kl")):
+        assert abs(float(comp[i + 1]) - c["comps"][k]) < 5e-5 * max(1.0, abs(c["comps"][k])), k
+    assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 5e-5
+    gnorm = max(v["norm"] for v in c["grad_summary"].values())
+    for k, p in tr.model.named_parameters():
+        if k not in c["grad_summary"]:
+            continue
+        sm = c["grad_summary"][k]
+        if sm["norm"] < 1e-5 * gnorm:
+            continue
+        got = float(p.grad.double().norm())
+        assert abs(got - sm["norm"]) <= 5e-3 * sm["norm"], (k, got, sm["norm"])
+        if "full" in sm:
+            assert float((p.grad.cpu() - sm["full"]).double().norm()) <= 5e-3 * sm["norm"], k
+    sd = tr.model.state_dict()
+    for k, v in c["new_stats"].items():
+        assert rel(sd[k].float(), v.float()) < 2e-5, k
+    # groups whose gradient is None in the reference must not be stepped (no weight decay either)
+    before = {k: p.detach().clone() for k, p in tr.model.named_parameters()}
+    tr.optimizer.step()
+    for k, p in tr.model.named_parameters():
+        if not p.requires_grad:
+            continue
+        moved = not torch.equal(before[k], p.detach())
+        assert moved == c["has_grad"][k], (k, moved, c["has_grad"][k])
