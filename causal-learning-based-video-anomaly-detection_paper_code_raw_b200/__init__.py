@@ -14,6 +14,6 @@ from . import _lib
 
 _lib.lib()   # fail loudly when the CUDA extension has not been built
 
-from . import arena, ma, ma_ops, mb, mc, noise, ops  # noqa: E402,F401
+from . import arena, ma, ma_ops, mb, mc, noise, ops, parallel  # noqa: E402,F401
 
-__all__ = ["arena", "ma", "ma_ops", "mb", "mc", "noise", "ops"]
+__all__ = ["arena", "ma", "ma_ops", "mb", "mc", "noise", "ops", "parallel"]

@@ -1,0 +1,70 @@
+"""Data parallelism over the 8 GPUs of one box: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+
+Clips are independent units: inference shards clips with no communication; training has exactly one
+exchange step per iteration -- the sum all-reduce of the flat gradient arena (M-B 0.76 MB, M-C 73 KB, M-A 18 MB fp32).
+The arena is contiguous, so there is no pack/unpack; its 16-float header rides along, which all-reduces the
+"non-finite loss" flag and the group-activity flags so every rank takes the same skip decisions.  The 1/world scaling
+is folded into the fused clip+Adam kernel (``grad_scale``).  BatchNorm statistics and M-B's batch-coupled loss terms
+are rank-local (DDP semantics): an 8x4 run is not numerically a 1x32 run.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel:
+    def __init__(self, group=None, buckets: int = 1):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.buckets = max(1, int(buckets))
+
+    def attach(self, optimizer):
+        optimizer.pre_step_hook = self.all_reduce_grads
+        optimizer.grad_scale = 1.0 / self.world
+        return optimizer
+
+    def all_reduce_grads(self, arena):
+        if self.world == 1:
+            return
+        g = arena.g
+        if self.buckets == 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        n = g.numel()
+        step = (n + self.buckets - 1) // self.buckets
+        works = [dist.all_reduce(g[i:i + step], op=dist.ReduceOp.SUM, group=self.group, async_op=True) for i in range(0, n, step)]
+        for w in works:
+            w.wait()
+
+    def broadcast_parameters(self, arena, src: int = 0):
+        dist.broadcast(arena.p, src=src, group=self.group)
+        dist.broadcast(arena.m, src=src, group=self.group)
+        dist.broadcast(arena.v, src=src, group=self.group)
+
+    def shard(self, n_items: int):
+        """Contiguous shard [lo, hi) of n_items for this rank (inference: disjoint clip shards, no communication)."""
+        per = (n_items + self.world - 1) // self.world
+        lo = min(self.rank * per, n_items)
+        return lo, min(lo + per, n_items)
+
+
+def init_from_env(backend: str | None = None):
+    """Initialise torch.distributed from torchrun's environment (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_*)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local, world

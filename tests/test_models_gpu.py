@@ -196,9 +196,11 @@ def test_mc_trajectory_and_trainer(dev, gold):
         assert abs(float(loss) - tj["losses"][it]) < 1e-4 * max(1, abs(tj["losses"][it])), it
     sd = tr.model.state_dict()
     for k, v in tj["final"].items():
-        if k in ("features.0.bias", "features.4.bias", "features.8.bias"):
+        if k in ("features.0.bias", "features.4.bias", "features.8.bias", "features.1.running_mean", "features.5.running_mean",
+                 "features.9.running_mean"):
             # conv biases feeding BatchNorm have an analytically zero gradient: Adam normalises pure round-off noise into
-            # +-lr steps, so these follow a noise-driven walk in the reference too; bound it by the 3 steps taken.
+            # +-lr steps, so these (and the BN running means that absorb them) follow a noise-driven walk in the reference
+            # too; bound it by the 3 steps taken.
             assert float((sd[k].cpu() - v).abs().max()) <= 2 * 3 * 1e-3 + 1e-6, k
             continue
         assert rel(sd[k].float(), v.float()) < 1e-4, k
