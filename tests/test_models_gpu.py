@@ -298,3 +298,38 @@ def test_ma_train_step_parity_fp32(dev, gold, idx):
             continue
         moved = not torch.equal(before[k], p.detach())
         assert moved == c["has_grad"][k], (k, moved, c["has_grad"][k])
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_ma_bf16_tensor_core_path(dev, gold, idx):
+    """bf16 operands / fp32 accumulation (tcgen05) backbone: scores and loss within 1e-3 relative of the fp32 reference
+    (north-star tolerance), identical thresholded labels; gradients within bf16 noise."""
+    from cvad_b200.ma import MATrainer
+    c = gold("ma.pt")["cases"][idx]
+    m, noise = _ma_model(dev, c)
+    tr = MATrainer(m, dev, precision="bf16")
+    tr.model.train(c["train"])
+    tr.model.noise = noise
+    x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"]).to(dev)
+    labels = c["labels"].to(dev)
+    tr.optimizer.zero_grad()
+    with torch.set_grad_enabled(c["train"]):
+        out = tr.model(x)
+        loss, comp = tr.loss_on_device(out, labels)
+    e_s = rel(out["anomaly_scores"], c["anomaly_scores"], floor=1e-6)
+    e_l = rel(loss, c["loss"], floor=1e-6)
+    print(f"[bf16] case {c['name']}: score rel err {e_s:.2e}, loss rel err {e_l:.2e}")
+    assert e_s < 1e-3 and e_l < 1e-3
+    assert torch.equal(out["anomaly_scores"].cpu() > 0.5, c["anomaly_scores"] > 0.5)
+    assert torch.equal(out["dense"]["det_counts"].cpu().long(), c["det_counts"])
+    if c["train"]:
+        loss.backward()
+        gnorm = max(v["norm"] for v in c["grad_summary"].values())
+        worst = 0.0
+        for k, p in tr.model.named_parameters():
+            sm = c["grad_summary"].get(k)
+            if sm is None or sm["norm"] < 1e-3 * gnorm or k.endswith(".bias") and "backbone" in k:
+                continue
+            worst = max(worst, abs(float(p.grad.double().norm()) - sm["norm"]) / sm["norm"])
+        print(f"[bf16] case {c['name']}: worst grad-norm rel err {worst:.2e}")
+        assert worst < 5e-2
