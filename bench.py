@@ -1,0 +1,242 @@
+#!/usr/bin/env python
+"""Headline benchmark: M-A (causal_anomaly_detection.py) training step on synthetic Avenue-shaped clips.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ma_train|mb_train|mc_infer]
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch: zero_grad -> forward ->
+4-term loss -> backward -> (gradient all-reduce when N > 1) -> fused clip + AdamW.
+  value     clips/s with inputs resident in HBM (the 177 MB fp32 batch exceeds the 126 MB L2, so every step streams it)
+  e2e       the same through the public trainer API with the batch in PINNED HOST memory: H2D copy of the step's inputs and
+            a D2H read of the loss inside the timed region
+  roofline  the dominant kernel family (the tcgen05 implicit-GEMM convolutions) timed with CUDA events inside the timed
+            region against the measured dense bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port of the reference step on the box's host cores, bounded sample (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+T, H, W = 16, 240, 360
+PER_GPU_BATCH = 32
+# algorithmic FLOPs (2*MAC) per frame of the eight 3x3 convolutions: forward, and forward+dgrad+wgrad
+CONV_FWD_MFLOP = [99.53, 99.53, 49.77, 99.53, 50.87, 101.74, 56.62, 113.25]
+CONV_TRAIN_MFLOP = sum(CONV_FWD_MFLOP) * 3 - CONV_FWD_MFLOP[0]      # layer1.0 needs no data-gradient (frozen stem below it)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1341.2), d.get("hbm_gbs", 6499.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples if len(s) > 2 + i)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons}
+
+
+def synth_batch(B, seed):
+    import synth
+    x = synth.ma_clips(B, T, H, W, seed, wide=True)
+    y = (torch.rand(B, generator=synth.gen(seed + 9)) < 0.3).long()
+    return x, y
+
+
+def cpu_reference_step_rate(sample_clips=2, steps=2, warm=1):
+    """Oracle port of the reference train step on the host cores: clips/s on a bounded sample."""
+    from oracle import train as o_train
+    from test_oracle_golden import ma_synth_state
+    import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = ma_synth_state(3, False)
+    opt = o_train.OracleAdam(o_train.ma_trainable(P), 3e-4, 1e-5, True, 1.0)
+    x, y = synth_batch(sample_clips, 1234)
+    eps = torch.randn(sample_clips, 5, 6, generator=synth.gen(1))
+    keep = {"det0": synth.keep_mask((sample_clips, T, 512), 0.3, 2), "det1": synth.keep_mask((sample_clips, T, 256), 0.2, 3),
+            "scorer0": synth.keep_mask((sample_clips, 64), 0.2, 4), "cls0": synth.keep_mask((sample_clips, 512), 0.3, 5),
+            "cls1": synth.keep_mask((sample_clips, 256), 0.2, 6)}
+    for _ in range(warm):
+        o_train.ma_train_step(P, opt, x, y, eps, keep)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o_train.ma_train_step(P, opt, x, y, eps, keep)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_clips / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 2
+    rate, dt, cores = cpu_reference_step_rate(sample, max(1, min(args.steps, 3)), max(1, min(args.warmup, 1)))
+    line = {
+        "impl": "reference", "metric": "train clips/sec", "value": rate, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "M-A (causal_anomaly_detection.py) train step, synthetic Avenue clips (B,16,1,240,360)",
+                   "per_step_sample_clips": sample},
+        "cpu_baseline": {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} clips/step (fwd + 4-term loss + bwd + clip + AdamW), oracle port of cad:637-690 on CPU"},
+        "e2e": {"value": rate, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import cvad_b200
+    from cvad_b200 import ops
+    from cvad_b200.ma import CausalAnomalyDetector, MATrainer
+    from cvad_b200.parallel import DataParallel, init_from_env
+
+    rank, local, world = init_from_env()
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    torch.manual_seed(1234 + rank)
+    B = PER_GPU_BATCH
+    dp = DataParallel() if world > 1 else None
+    tr = MATrainer(CausalAnomalyDetector(), dev, precision=args.precision, dp=dp)
+    if dp is not None:
+        dp.broadcast_parameters(tr.optimizer.arena)
+    tr.model.train()
+    x_host, y_host = synth_batch(B, 1234 + rank)
+    x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tr.train_step(x_dev, y_dev)
+    barrier()
+    conv_names = {"cvad_conv3x3_fwd_bf16", "cvad_conv3x3_dgrad_bf16", "cvad_conv3x3_wgrad_bf16"} if args.precision == "bf16" else \
+        {"cvad_conv_fwd_f32", "cvad_conv_dgrad_f32", "cvad_conv_wgrad_f32"}
+    ops.TIMED.clear()
+    ops.TIMED_NAMES.update(conv_names)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        comp, _ = tr.train_step(x_dev, y_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCHES[0] - n0
+    ops.TIMED_NAMES.clear()
+    conv_ms = {k: sum(s.elapsed_time(e) for s, e in v) / args.steps for k, v in ops.TIMED.items()}
+    conv_launches = sum(len(v) for v in ops.TIMED.values()) // max(args.steps, 1)
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H loss
+    for _ in range(2):
+        xd = x_pin.to(dev, non_blocking=True); yd = y_pin.to(dev, non_blocking=True)
+        c, _ = tr.train_step(xd, yd); float(c[0])
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        xd = x_pin.to(dev, non_blocking=True); yd = y_pin.to(dev, non_blocking=True)
+        c, _ = tr.train_step(xd, yd)
+        loss_host = float(c[0])
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    sampler.stop_flag = True
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    tf_peak, hbm_peak, src = peaks()
+    ms_step = ms / args.steps
+    value = world * B / (ms_step / 1e3)
+    e2e_value = world * B / (ms_e2e / args.steps / 1e3)
+    conv_total_ms = sum(conv_ms.values())
+    flops_step = CONV_TRAIN_MFLOP * 1e6 * B * T
+    achieved = flops_step / (conv_total_ms / 1e3) / 1e12 if conv_total_ms > 0 else 0.0
+    line = {
+        "metric": "train clips/sec", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": "M-A (causal_anomaly_detection.py) train step, synthetic Avenue clips (32,16,1,240,360) per GPU",
+                   "per_gpu_batch": B, "frames_per_clip": T, "frame": [H, W], "parallelism": f"dp{world}",
+                   "l2": "inputs (177 MB fp32 per step) larger than the 126 MB L2", "precision": "bf16 operands, fp32 accumulate (tcgen05), "
+                   "fp32 stem/tail" if args.precision == "bf16" else "fp32"},
+        "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 8, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                     "kernel": "conv3x3 tcgen05 implicit GEMM (fwd+dgrad+wgrad)" if args.precision == "bf16" else "conv_gemm_kernel fp32",
+                     "peak_source": src, "launches_per_step": conv_launches, "ms_per_step": conv_total_ms,
+                     "share_of_step": conv_total_ms / ms_step, "per_kernel_ms": conv_ms,
+                     "algorithmic_gflop_per_step": flops_step / 1e9},
+        "clocks": sampler.summary(),
+        "loss": loss_host,
+    }
+    if world == 1 and not args.no_cpu:
+        rate, dt, cores = cpu_reference_step_rate(2, 2, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "clips/s", "cores": cores, "kind": "port",
+                                "sample": "2 clips/step x 2 steps of the same workload (oracle port of cad:637-690, fp32, all host threads)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

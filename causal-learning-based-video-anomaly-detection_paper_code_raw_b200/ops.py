@@ -38,8 +38,20 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+TIMED = {}        # bench.py: ABI name -> list of (start_event, end_event); set TIMED_NAMES to enable
+TIMED_NAMES = set()
+
+
 def _call(name, *args):
     LAUNCHES[0] += 1
+    if name in TIMED_NAMES:
+        s = torch.cuda.Event(enable_timing=True)
+        e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        check(getattr(L(), name)(*args), name)
+        e.record()
+        TIMED.setdefault(name, []).append((s, e))
+        return
     check(getattr(L(), name)(*args), name)
 
 
