@@ -1,0 +1,634 @@
+// "Flat" tensor-core 3x3 convolution for the M-A backbone (cad:128-139, 150-153): forward and data-gradient as
+// TMA-fed tcgen05.mma GEMMs over a zero-bordered NHWC layout.
+//
+// Layout in HBM.  An activation with logical shape (N,H,W,C) is stored as (N, H+2, W+2, C) bf16 with a zero border
+// ("padded-flat").  With q the flat pixel index of that buffer, a stride-1 3x3 convolution is a sum of nine row-shifted
+// GEMMs over the SAME index space for input and output:
+//        out[q][:] = sum_{kh,kw} in[q + (kh-1)*(W+2) + (kw-1)][:] * W[kh][kw]
+// (border positions produce junk that nobody reads).  A stride-2 convolution reads its input from four "phase planes"
+// P_ab[n][i][j] = in_padded(2(i-1)+a, 2(j-1)+b) stored in the OUTPUT's padded geometry, which makes it the same kind of
+// sum: tap (kh,kw) reads plane (kh&1, kw&1) shifted by (kh>>1)*(Wo+2) + (kw>>1).  The data-gradients are the transposed
+// sums (negative shifts; one launch per phase plane for stride 2).
+//
+// Kernel.  Persistent, warp-specialised, one CTA per SM:
+//   warp 0 (one lane)  TMA producer: per K-unit (a 32/64-channel slab of one source plane) one activation segment of
+//                      128*SUB + halo rows, hardware-swizzled (SWIZZLE_64B / SWIZZLE_128B), double buffered; per tap one
+//                      [N x slab] weight tile through a 4-deep ring;
+//   warp 1 (one lane)  tcgen05.mma issuer: every tap is a ROW-SHIFTED VIEW of the resident segment (descriptor start
+//                      address + delta*row_bytes; the swizzle is a function of the absolute smem address, see
+//                      profiles/r01_umma_descriptor_probe.md), M=128 x N x K=16 MMAs into a ring of TMEM accumulators;
+//   warp 2             TMEM allocator;
+//   warps 4-7          epilogue: tcgen05.ld -> +bias -> bf16 -> global, overlapped with the next tile's MMAs.
+// So an activation element is fetched from L2/HBM ~1.1-1.4x (halo) instead of 9x, and no thread computes an address.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "cvad_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace cvad_tc;
+
+constexpr int FC_MAX_UNITS = 16;
+constexpr int FC_WST = 4;        // weight-tile ring depth
+constexpr int FC_BOXR = 64;      // rows per activation TMA box
+
+struct FcUnit {
+  int row_off;          // first segment row relative to the tile's first output row (may be negative)
+  int col;              // first channel of the slab
+  int ntaps;
+  int tap_delta[9];     // row shift of the tap inside the segment (>= 0)
+  int tap_wrow[9];      // first row of the tap's weight block in the packed weight matrix
+};
+
+struct FcParams {
+  long long rows;        // output rows (flat pixels)
+  long long out_row_base;
+  int n_units, seg_rows, sub, n_blocks, ld_out;
+  FcUnit units[FC_MAX_UNITS];
+};
+
+template <int ROWB, int N>
+__global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
+                                                          const FcParams p, const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ out) {
+  constexpr int NSLOT = (512 / N) > 8 ? 8 : (512 / N);
+  constexpr uint32_t TMEM_COLS = NSLOT * N;
+  constexpr int W_BYTES = N * ROWB;
+  constexpr int K16 = ROWB / 32;
+  constexpr uint32_t SBO = ROWB * 8;
+  constexpr int LAYOUT = ROWB == 128 ? UMMA_SW128 : UMMA_SW64;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_src_full[2], bar_src_empty[2], bar_w_full[FC_WST], bar_w_empty[FC_WST], bar_acc_full[8], bar_acc_empty[8];
+  __shared__ uint32_t tmem_base_sh;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t seg_bytes = (uint32_t)p.seg_rows * ROWB;
+  const uint32_t s_src = smem_base;
+  const uint32_t s_w = smem_base + 2 * seg_bytes;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = 128 * p.sub;
+  const long long n_tiles = (p.rows + MT - 1) / MT;
+  const long long total = n_tiles * p.n_blocks;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
+    for (int i = 0; i < FC_WST; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+    fence_barrier_init();
+    prefetch_tmap(&map_src);
+    prefetch_tmap(&map_w);
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_sh);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t src_cnt = 0, w_cnt = 0;
+    auto load_src = [&](long long q0, const FcUnit& u) {
+      const int st = src_cnt & 1;
+      mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
+      mbar_expect_tx(&bar_src_full[st], seg_bytes);
+      const int r0 = (int)(q0 + u.row_off);
+      for (int r = 0; r < p.seg_rows; r += FC_BOXR) tma_load_2d(s_src + st * seg_bytes + r * ROWB, &map_src, u.col, r0 + r, &bar_src_full[st]);
+      ++src_cnt;
+    };
+    if ((long long)blockIdx.x < total) load_src((blockIdx.x / p.n_blocks) * (long long)MT, p.units[0]);
+    for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
+      const long long q0 = (wi / p.n_blocks) * MT;
+      const int nb = (int)(wi % p.n_blocks);
+      for (int u = 0; u < p.n_units; ++u) {
+        if (u + 1 < p.n_units) load_src(q0, p.units[u + 1]);
+        else if (wi + gridDim.x < total) load_src(((wi + gridDim.x) / p.n_blocks) * MT, p.units[0]);
+        const FcUnit& un = p.units[u];
+        for (int t = 0; t < un.ntaps; ++t) {
+          const int st = w_cnt % FC_WST;
+          mbar_wait(&bar_w_empty[st], ((w_cnt / FC_WST) & 1) ^ 1);
+          mbar_expect_tx(&bar_w_full[st], W_BYTES);
+          tma_load_2d(s_w + st * W_BYTES, &map_w, un.col, un.tap_wrow[t] + nb * N, &bar_w_full[st]);
+          ++w_cnt;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    uint32_t src_cnt = 0, w_cnt = 0, acc_cnt = 0;
+    for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
+      for (int u = 0; u < p.n_units; ++u) {
+        const FcUnit& un = p.units[u];
+        const int st = src_cnt & 1;
+        mbar_wait(&bar_src_full[st], (src_cnt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_seg = s_src + st * seg_bytes;
+        for (int t = 0; t < un.ntaps; ++t) {
+          const int ws = w_cnt % FC_WST;
+          mbar_wait(&bar_w_full[ws], (w_cnt / FC_WST) & 1);
+          tc_fence_after();
+          const uint32_t b_base = s_w + ws * W_BYTES;
+          const bool first = (u == 0 && t == 0);
+          const bool last = (u == p.n_units - 1 && t == un.ntaps - 1);
+          for (int s = 0; s < p.sub; ++s) {
+            const uint32_t use = acc_cnt + s;
+            const int slot = use % NSLOT;
+            if (first) {
+              mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
+              tc_fence_after();
+            }
+            const uint32_t a_base = a_seg + (uint32_t)(un.tap_delta[t] + s * 128) * ROWB;
+#pragma unroll
+            for (int k = 0; k < K16; ++k) {
+              const uint64_t da = make_smem_desc(a_base + k * 32, 16, SBO, LAYOUT);
+              const uint64_t db = make_smem_desc(b_base + k * 32, 16, SBO, LAYOUT);
+              tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+            }
+            if (last) tc_commit(&bar_acc_full[slot]);
+          }
+          tc_commit(&bar_w_empty[ws]);
+          ++w_cnt;
+        }
+        tc_commit(&bar_src_empty[st]);
+        ++src_cnt;
+      }
+      acc_cnt += p.sub;
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
+    const int ew = warp - 4;
+    uint32_t acc_cnt = 0;
+    for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
+      const long long q0 = (wi / p.n_blocks) * MT;
+      const int nb = (int)(wi % p.n_blocks);
+      for (int s = 0; s < p.sub; ++s) {
+        const uint32_t use = acc_cnt + s;
+        const int slot = use % NSLOT;
+        mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
+        tc_fence_after();
+        const long long q = q0 + s * 128 + ew * 32 + lane;
+        const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
+        __nv_bfloat16* orow = out + (p.out_row_base + q) * (long long)p.ld_out + nb * N;
+#pragma unroll
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (q < p.rows) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+              if (bias) { a += __ldg(bias + nb * N + c0 + 2 * i); b += __ldg(bias + nb * N + c0 + 2 * i + 1); }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bar_acc_empty[slot]);
+      }
+      acc_cnt += p.sub;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+template <int ROWB, int N>
+int launch_flatconv(const CUtensorMap& ms, const CUtensorMap& mw, const FcParams& p, const float* bias, __nv_bfloat16* out, cudaStream_t st) {
+  const size_t smem = 2 * (size_t)p.seg_rows * ROWB + (size_t)FC_WST * N * ROWB + 1024;
+  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(flatconv_kernel<ROWB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  const long long MT = 128LL * p.sub;
+  const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
+  const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
+  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mw, p, bias, out);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+int dispatch_flatconv(int rowb, int n, const CUtensorMap& ms, const CUtensorMap& mw, const FcParams& p, const float* bias, __nv_bfloat16* out,
+                      cudaStream_t st) {
+  if (rowb == 64) {
+    if (n == 32) return launch_flatconv<64, 32>(ms, mw, p, bias, out, st);
+    if (n == 64) return launch_flatconv<64, 64>(ms, mw, p, bias, out, st);
+    if (n == 128) return launch_flatconv<64, 128>(ms, mw, p, bias, out, st);
+  } else {
+    if (n == 32) return launch_flatconv<128, 32>(ms, mw, p, bias, out, st);
+    if (n == 64) return launch_flatconv<128, 64>(ms, mw, p, bias, out, st);
+    if (n == 128) return launch_flatconv<128, 128>(ms, mw, p, bias, out, st);
+  }
+  return (int)cudaErrorInvalidValue;
+}
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Common driver: `K` reduction channels (the gathered tensor's channel count), `Nout` output channels.
+// src_rows: rows of the gathered buffer (all planes); w_rows: rows of the packed weight matrix (9 * Nout).
+int run_flat(const void* src, long long src_rows, int K, const void* wpk, int Nout, const float* bias, void* out, FcParams& p,
+             cudaStream_t st) {
+  if (K % 32 || Nout % 32) return (int)cudaErrorInvalidValue;
+  const int rowb = K >= 64 ? 128 : 64;
+  if (K >= 64 && K % 64) return (int)cudaErrorInvalidValue;
+  const int n = Nout % 128 == 0 ? 128 : (Nout % 64 == 0 ? 64 : 32);
+  p.n_blocks = Nout / n;
+  p.ld_out = Nout;
+  // fewer sub-tiles per work item when the problem would not fill the machine
+  p.sub = 4;
+  while (p.sub > 1 && ((p.rows + 128LL * p.sub - 1) / (128LL * p.sub)) * p.n_blocks < 2LL * cvad_num_sms()) p.sub >>= 1;
+  int max_delta = 0;
+  for (int u = 0; u < p.n_units; ++u)
+    for (int t = 0; t < p.units[u].ntaps; ++t) max_delta = p.units[u].tap_delta[t] > max_delta ? p.units[u].tap_delta[t] : max_delta;
+  p.seg_rows = round_up(128 * p.sub + max_delta, FC_BOXR);
+  CUtensorMap ms, mw;
+  int e = make_tmap_2d(&ms, src, src_rows, K, FC_BOXR, rowb / 2, rowb);
+  if (e) return e;
+  e = make_tmap_2d(&mw, wpk, 9LL * Nout, K, n, rowb / 2, rowb);
+  if (e) return e;
+  return dispatch_flatconv(rowb, n, ms, mw, p, bias, (__nv_bfloat16*)out, st);
+}
+
+// OIHW fp32 (Co, Ci, 3, 3) -> fwd [tap][Co][Ci] bf16 and dgrad [tap][Ci][Co] bf16
+__global__ void pack_w3x3_flat_kernel(const float* __restrict__ w, int Co, int Ci, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const int total = Co * Ci * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (wf) wf[((long long)tap * Co + co) * Ci + ci] = v;
+    if (wd) wd[((long long)tap * Ci + ci) * Co + co] = v;
+  }
+}
+
+}  // namespace
+
+CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, void* w_fwd, void* w_dgrad, void* stream) {
+  int total = Cout * Cin * 9;
+  pack_w3x3_flat_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                                        int stride, void* stream) {
+  if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
+  const int slab = Cin >= 64 ? 64 : 32;
+  const int nslab = Cin / slab;
+  FcParams p;
+  memset(&p, 0, sizeof(p));
+  p.out_row_base = 0;
+  long long src_rows;
+  if (stride == 1) {
+    const int Wp = W + 2;
+    p.rows = (long long)N * (H + 2) * Wp;
+    src_rows = p.rows;
+    if (nslab > FC_MAX_UNITS) return (int)cudaErrorInvalidValue;
+    p.n_units = nslab;
+    for (int s = 0; s < nslab; ++s) {
+      FcUnit& u = p.units[s];
+      u.row_off = -(Wp + 1);
+      u.col = s * slab;
+      u.ntaps = 9;
+      for (int t = 0; t < 9; ++t) { u.tap_delta[t] = (t / 3) * Wp + (t % 3); u.tap_wrow[t] = t * Cout; }
+    }
+  } else {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
+    p.rows = (long long)N * (Ho + 2) * Wq;
+    src_rows = 4 * p.rows;
+    if (4 * nslab > FC_MAX_UNITS) return (int)cudaErrorInvalidValue;
+    p.n_units = 4 * nslab;
+    for (int pl = 0; pl < 4; ++pl)
+      for (int s = 0; s < nslab; ++s) {
+        FcUnit& u = p.units[pl * nslab + s];
+        const int a = pl >> 1, b = pl & 1;
+        u.row_off = 0;                      // plane offset does not fit an int: folded into tap_delta-free base below
+        u.col = s * slab;
+        u.ntaps = 0;
+        for (int t = 0; t < 9; ++t) {
+          const int kh = t / 3, kw = t % 3;
+          if ((kh & 1) != a || (kw & 1) != b) continue;
+          u.tap_delta[u.ntaps] = (kh >> 1) * Wq + (kw >> 1);
+          u.tap_wrow[u.ntaps] = t * Cout;
+          ++u.ntaps;
+        }
+        if (pl * p.rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
+        u.row_off = (int)(pl * p.rows);
+      }
+  }
+  return run_flat(x, src_rows, Cin, w_fwd, Cout, bias, y, p, (cudaStream_t)stream);
+}
+
+CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                                          void* stream) {
+  // (N,H,W,Cin) is the convolution INPUT geometry.  stride 1: dy, dx padded-flat (N,H+2,W+2,.).  stride 2: dy padded-flat
+  // (N,Ho+2,Wo+2,Cout), dx = four phase planes in that same geometry.
+  if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
+  const int slab = Cout >= 64 ? 64 : 32;
+  const int nslab = Cout / slab;
+  if (nslab > FC_MAX_UNITS) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1) {
+    const int Wp = W + 2;
+    FcParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = (long long)N * (H + 2) * Wp;
+    p.n_units = nslab;
+    for (int s = 0; s < nslab; ++s) {
+      FcUnit& u = p.units[s];
+      u.row_off = -(Wp + 1);
+      u.col = s * slab;
+      u.ntaps = 9;
+      for (int t = 0; t < 9; ++t) { u.tap_delta[t] = (2 - t / 3) * Wp + (2 - t % 3); u.tap_wrow[t] = t * Cin; }
+    }
+    return run_flat(dy, p.rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
+  }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
+  const long long rows = (long long)N * (Ho + 2) * Wq;
+  for (int pl = 0; pl < 4; ++pl) {
+    const int a = pl >> 1, b = pl & 1;
+    FcParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows;
+    p.out_row_base = pl * rows;
+    p.n_units = nslab;
+    for (int s = 0; s < nslab; ++s) {
+      FcUnit& u = p.units[s];
+      u.row_off = -(Wq + 1);
+      u.col = s * slab;
+      u.ntaps = 0;
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t % 3;
+        if ((kh & 1) != a || (kw & 1) != b) continue;
+        u.tap_delta[u.ntaps] = (Wq + 1) - ((kh >> 1) * Wq + (kw >> 1));
+        u.tap_wrow[u.ntaps] = t * Cin;
+        ++u.ntaps;
+      }
+    }
+    int e = run_flat(dy, rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
+    if (e) return e;
+  }
+  return 0;
+}
+
+// ================================================================================================ weight gradient
+// dW[tap][ci][co] += sum_q  src[q + off_tap][ci] * dy[q][co]   over the flat pixel index q (dy has a ZERO border, so the
+// junk positions contribute nothing).  Both operands are MN-major views of TMA-swizzled [pixel][channel] tiles (K = pixels):
+//   A (M = 128): the activation segment, row-shifted per tap.  With 32 (64) input channels the four (two) 32- (64-) channel
+//                atoms of the M dimension are consecutive PIXEL SHIFTS of the same tile (LBO = one pixel row), so one MMA
+//                covers up to four (two) taps of a kernel row; with >= 128 channels the atoms are two channel slabs.
+//   B (N = NB):  the dy tile.
+// One accumulator [128 x NB] per tap group lives in TMEM for the CTA's whole pixel range; the epilogue adds it atomically
+// into the OIHW fp32 gradient (a slice of the flat gradient arena).
+namespace {
+
+constexpr int WG_BOXR_A = 32;
+constexpr int WG_BOXR_B = 64;
+constexpr int WG_MAX_STAGES = 4;
+
+struct WgGroup {
+  int seg, delta;
+  int tap[4];            // tap index of each M atom (pixel shift j), -1 = unused lanes
+};
+struct WgParams {
+  long long rows;        // flat pixels
+  long long pix_per_cta; // multiple of qs
+  int n_seg, n_groups, seg_rows, qs, n_stages;
+  int Cin, Cout, ci_blocks, co_blocks;
+  int seg_row_off[4];
+  WgGroup groups[9];
+};
+
+template <int ROWB_A, int ROWB_B, int NB, int A_SLABS>
+__global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                           const WgParams p, float* __restrict__ dw) {
+  constexpr int B_SLABS = (NB * 2 + ROWB_B - 1) / ROWB_B;
+  constexpr int LAY_A = ROWB_A == 128 ? UMMA_SW128 : UMMA_SW64;
+  constexpr int LAY_B = ROWB_B == 128 ? UMMA_SW128 : UMMA_SW64;
+  constexpr int AW = A_SLABS == 2 ? 128 : ROWB_A / 2;      // channels per M atom group that share a tap
+  constexpr int CI_BLK = A_SLABS == 2 ? 128 : ROWB_A / 2;  // input channels handled by one CTA
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[WG_MAX_STAGES], bar_empty[WG_MAX_STAGES], bar_done;
+  __shared__ uint32_t tmem_base_sh;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t seg1 = (uint32_t)p.seg_rows * ROWB_A;            // one slab of one segment
+  const uint32_t a_bytes = (uint32_t)p.n_seg * A_SLABS * seg1;
+  const uint32_t b1 = (uint32_t)p.qs * ROWB_B;
+  const uint32_t stage_bytes = a_bytes + B_SLABS * b1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cib = blockIdx.y / p.co_blocks, cob = blockIdx.y % p.co_blocks;
+  const long long p_begin = (long long)blockIdx.x * p.pix_per_cta;
+  long long p_end = p_begin + p.pix_per_cta;
+  if (p_end > p.rows) p_end = p.rows;
+  const int n_iter = p_begin < p_end ? (int)((p_end - p_begin + p.qs - 1) / p.qs) : 0;
+
+  if (tid == 0) {
+    for (int i = 0; i < WG_MAX_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    mbar_init(&bar_done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_b);
+  }
+  if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0 && lane == 0) {
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it % p.n_stages;
+      mbar_wait(&bar_empty[st], ((it / p.n_stages) & 1) ^ 1);
+      mbar_expect_tx(&bar_full[st], stage_bytes);
+      const long long q = p_begin + (long long)it * p.qs;
+      const uint32_t base = smem_base + st * stage_bytes;
+      for (int sg = 0; sg < p.n_seg; ++sg)
+        for (int sl = 0; sl < A_SLABS; ++sl) {
+          const uint32_t dst = base + (sg * A_SLABS + sl) * seg1;
+          const int r0 = (int)(q + p.seg_row_off[sg]);
+          for (int r = 0; r < p.seg_rows; r += WG_BOXR_A) tma_load_2d(dst + r * ROWB_A, &map_a, cib * CI_BLK + sl * 64, r0 + r, &bar_full[st]);
+        }
+      for (int sl = 0; sl < B_SLABS; ++sl) {
+        const uint32_t dst = base + a_bytes + sl * b1;
+        for (int r = 0; r < p.qs; r += WG_BOXR_B) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);
+    const uint32_t lbo_a = A_SLABS == 2 ? seg1 : ROWB_A;
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it % p.n_stages;
+      mbar_wait(&bar_full[st], (it / p.n_stages) & 1);
+      tc_fence_after();
+      const uint32_t base = smem_base + st * stage_bytes;
+      const int ksteps = p.qs / 16;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t db = make_smem_desc(base + a_bytes + k * 16 * ROWB_B, b1, 8 * ROWB_B, LAY_B);
+        for (int g = 0; g < p.n_groups; ++g) {
+          const uint32_t a_start = base + p.groups[g].seg * A_SLABS * seg1 + (uint32_t)(p.groups[g].delta + k * 16) * ROWB_A;
+          const uint64_t da = make_smem_desc(a_start, lbo_a, 8 * ROWB_A, LAY_A);
+          tc_mma_bf16(tmem_base + g * NB, da, db, idesc, (it | k) != 0);
+        }
+      }
+      tc_commit(&bar_empty[st]);
+    }
+    tc_commit(&bar_done);
+  }
+  __syncwarp();
+  if (n_iter > 0) {
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int lq = warp & 3, half = warp >> 2;
+    const int m = lq * 32 + lane;
+    const int j = m / AW;
+    const int ci = cib * CI_BLK + (m % AW);
+    const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
+    for (int g = 0; g < p.n_groups; ++g) {
+      const int tap = p.groups[g].tap[j];
+#pragma unroll
+      for (int c0 = 0; c0 < NB; c0 += 16) {
+        if ((((c0 >> 4) + g) & 1) != half) continue;
+        uint32_t v[16];
+        tmem_ld16(tlane + g * NB + c0, v);
+        tmem_ld_wait();
+        if (tap >= 0 && ci < p.Cin) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int co = cob * NB + c0 + i;
+            atomicAdd(dw + ((long long)co * p.Cin + ci) * 9 + tap, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <int ROWB_A, int ROWB_B, int NB, int A_SLABS>
+int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& p, float* dw, cudaStream_t st) {
+  constexpr int B_SLABS = (NB * 2 + ROWB_B - 1) / ROWB_B;
+  constexpr int CI_BLK = A_SLABS == 2 ? 128 : ROWB_A / 2;
+  p.ci_blocks = (p.Cin + CI_BLK - 1) / CI_BLK;
+  p.co_blocks = p.Cout / NB;
+  int max_delta = 0;
+  for (int g = 0; g < p.n_groups; ++g) max_delta = p.groups[g].delta > max_delta ? p.groups[g].delta : max_delta;
+  const int shifts = A_SLABS == 2 ? 0 : (128 / CI_BLK - 1);   // extra rows touched by the pixel-shift atoms
+  // stage size: largest qs in {512, 256, 128, 64} that leaves room for >= 2 stages
+  int qs = 512;
+  size_t stage = 0;
+  for (;; qs >>= 1) {
+    p.seg_rows = round_up(qs + max_delta + shifts, WG_BOXR_A);
+    stage = (size_t)p.n_seg * A_SLABS * p.seg_rows * ROWB_A + (size_t)B_SLABS * qs * ROWB_B;
+    if (2 * stage + 1024 <= 227 * 1024 || qs == 64) break;
+  }
+  if (2 * stage + 1024 > 227 * 1024) return (int)cudaErrorInvalidValue;
+  p.qs = qs;
+  p.n_stages = (int)((227 * 1024 - 1024) / stage);
+  if (p.n_stages > WG_MAX_STAGES) p.n_stages = WG_MAX_STAGES;
+  const size_t smem = p.n_stages * stage + 1024;
+  const int yblocks = p.ci_blocks * p.co_blocks;
+  long long chunks = (2LL * cvad_num_sms() + yblocks - 1) / yblocks;
+  const long long max_chunks = (p.rows + qs - 1) / qs;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  p.pix_per_cta = ((p.rows + chunks - 1) / chunks + qs - 1) / qs * qs;
+  chunks = (p.rows + p.pix_per_cta - 1) / p.pix_per_cta;
+  CUtensorMap ma, mb;
+  int e = make_tmap_2d(&ma, src, src_rows, p.Cin, WG_BOXR_A, ROWB_A / 2, ROWB_A);
+  if (e) return e;
+  e = make_tmap_2d(&mb, dy, p.rows, p.Cout, WG_BOXR_B, ROWB_B / 2, ROWB_B);
+  if (e) return e;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t ce = cudaFuncSetAttribute(flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
+    configured = smem;
+  }
+  flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS><<<dim3((unsigned)chunks, yblocks), 256, smem, st>>>(ma, mb, p, dw);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+int dispatch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& p, float* dw, cudaStream_t st) {
+  if (p.Cin == 32 && p.Cout == 32) return launch_wgrad<64, 64, 32, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin == 32 && p.Cout % 64 == 0) return launch_wgrad<64, 128, 64, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin == 64 && p.Cout % 64 == 0) return launch_wgrad<128, 128, 64, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin % 128 == 0 && p.Cout % 128 == 0) return launch_wgrad<128, 128, 128, 2>(src, src_rows, dy, p, dw, st);
+  return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+CVAD_API int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride,
+                                          void* stream) {
+  if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int apm = Cin == 32 ? 4 : (Cin == 64 ? 2 : 1);     // taps one MMA can cover through pixel-shift atoms
+  WgParams p;
+  if (stride == 1) {
+    const int Wp = W + 2;
+    const long long rows = (long long)N * (H + 2) * Wp;
+    // big layers: one launch per kernel row keeps 3 accumulators of 128 columns in TMEM; small layers: all nine taps at once
+    const int launches = apm == 1 ? 3 : 1;
+    for (int l = 0; l < launches; ++l) {
+      memset(&p, 0, sizeof(p));
+      p.rows = rows; p.Cin = Cin; p.Cout = Cout;
+      p.n_seg = 1;
+      const int kh0 = apm == 1 ? l : 0, kh1 = apm == 1 ? l + 1 : 3;
+      p.seg_row_off[0] = (kh0 - 1) * Wp - 1;
+      for (int kh = kh0; kh < kh1; ++kh)
+        for (int kw = 0; kw < 3; kw += apm) {
+          WgGroup& g = p.groups[p.n_groups++];
+          g.seg = 0;
+          g.delta = (kh - kh0) * Wp + kw;
+          for (int j = 0; j < 4; ++j) g.tap[j] = (j < apm && kw + j < 3) ? kh * 3 + kw + j : -1;
+        }
+      int e = dispatch_wgrad(x, rows, dy, p, dw, st);
+      if (e) return e;
+    }
+    return 0;
+  }
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
+  const long long rows = (long long)N * (Ho + 2) * Wq;
+  if (3 * rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
+  // per phase plane (a,b): taps with (kh&1, kw&1) = (a,b), shift (kh>>1)*Wq + (kw>>1)
+  const int launches = apm == 1 ? 4 : 1;
+  for (int l = 0; l < launches; ++l) {
+    memset(&p, 0, sizeof(p));
+    p.rows = rows; p.Cin = Cin; p.Cout = Cout;
+    for (int pl = 0; pl < 4; ++pl) {
+      if (apm == 1 && pl != l) continue;
+      const int a = pl >> 1, b = pl & 1;
+      const int sg = p.n_seg++;
+      p.seg_row_off[sg] = (int)(pl * rows);
+      for (int kh = a; kh < 3; kh += 2)
+        for (int kw = b; kw < 3; kw += 2 * (apm > 1 ? 2 : 1)) {
+          WgGroup& g = p.groups[p.n_groups++];
+          g.seg = sg;
+          g.delta = (kh >> 1) * Wq + (kw >> 1);
+          for (int j = 0; j < 4; ++j) g.tap[j] = -1;
+          g.tap[0] = kh * 3 + kw;
+          if (apm > 1 && kw + 2 < 3) g.tap[1] = kh * 3 + kw + 2;      // the next same-parity tap is one plane pixel further
+        }
+    }
+    int e = dispatch_wgrad(x, 4 * rows, dy, p, dw, st);
+    if (e) return e;
+  }
+  return 0;
+}

@@ -234,6 +234,255 @@ inline int blocks_for(long long n, int per = 256) {
   return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+
+// ================================================================================================ padded-flat layout
+// Activations of the flat tensor-core path (flatconv_tc.cu): (N, H+2, W+2, C) bf16 with a zero border, or -- for the
+// input of a stride-2 convolution -- four phase planes P_ab[n][i][j] = padded(2(i-1)+a, 2(j-1)+b) in the geometry
+// (N, Ho+2, Wo+2) of that convolution's output.  Convolution outputs (raw) and data-gradients (dact) carry junk in their
+// border; every kernel below reads interiors only and writes complete buffers (zero borders where a consumer needs them).
+struct PadGeo {
+  int N, H, W, C;       // interior geometry of the raw / plain tensor
+  int Hq, Wq;           // phase-plane geometry (Ho+2, Wo+2) when a phase layout is involved
+  int lg;               // log2(C/8)
+};
+
+__device__ __forceinline__ long long plain_row(const PadGeo& g, int n, int hp, int wp) { return ((long long)n * (g.H + 2) + hp) * (g.W + 2) + wp; }
+__device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, int wp) {
+  const int pl = ((hp & 1) << 1) | (wp & 1);
+  return (((long long)pl * g.N + n) * g.Hq + (hp >> 1) + 1) * g.Wq + (wp >> 1) + 1;
+}
+
+// relu(bn(raw)) -> act.  PHASE=0: plain padded act, zero border.  PHASE=1: four phase planes (zeros where no pixel maps).
+template <int PHASE>
+__global__ void pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ act, PadGeo g,
+                                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta) {
+  const int groups = 1 << g.lg;
+  const int cg = threadIdx.x & (groups - 1);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    sc[i] = invstd[c] * gamma[c];
+    sh[i] = beta[c] - mean[c] * sc[i];
+  }
+  const int Hp = g.H + 2, Wp = g.W + 2;
+  const int rows = PHASE ? 4 * g.N * g.Hq : g.N * Hp;
+  const int rowlen = (PHASE ? g.Wq : Wp) << g.lg;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    int n, hp, a = 0, b = 0;
+    if (PHASE) {
+      const int i = r % g.Hq;
+      const int t = r / g.Hq;
+      n = t % g.N;
+      const int pl = t / g.N;
+      a = pl >> 1; b = pl & 1;
+      hp = 2 * (i - 1) + a;
+    } else {
+      hp = r % Hp;
+      n = r / Hp;
+    }
+    const bool row_ok = hp >= 1 && hp <= g.H;
+    uint4* dst = reinterpret_cast<uint4*>(act) + (long long)r * rowlen;
+    for (int v = threadIdx.x; v < rowlen; v += blockDim.x) {
+      const int j = v >> g.lg;
+      const int wp = PHASE ? 2 * (j - 1) + b : j;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (row_ok && wp >= 1 && wp <= g.W) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + ((plain_row(g, n, hp, wp) << g.lg) + cg)), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
+        o = pack8(f);
+      }
+      dst[v] = o;
+    }
+  }
+}
+
+// per-channel reductions over the INTERIOR of raw.  !BWD: sum x, sum x^2.  BWD: g = dact*(pre>0): sum g, sum g*xhat.
+// dact is plain (PHASE=0) or phase planes (PHASE=1).
+template <bool BWD, int PHASE>
+__global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact, PadGeo g,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, double* __restrict__ ws) {
+  extern __shared__ float red[];             // [blockDim][16]
+  const int groups = 1 << g.lg;
+  const int cg = threadIdx.x & (groups - 1), slot = threadIdx.x >> g.lg, slots = blockDim.x >> g.lg;
+  const int C = g.C;
+  float s[8], q[8], mu[8], is[8], ga[8], be[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s[i] = 0.f; q[i] = 0.f;
+    if (BWD) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; ga[i] = gamma[cg * 8 + i]; be[i] = beta[cg * 8 + i]; }
+  }
+  const int rows = g.N * g.H;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int h = r % g.H, n = r / g.H;
+    const long long base = plain_row(g, n, h + 1, 1);
+    for (int w = slot; w < g.W; w += slots) {
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + (((base + w) << g.lg) + cg)), f);
+      if (!BWD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+      } else {
+        const long long drow = PHASE ? phase_row(g, n, h + 1, w + 1) : base + w;
+        float d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dact) + ((drow << g.lg) + cg)), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mu[i]) * is[i];
+          const float gg = fmaf(xh, ga[i], be[i]) > 0.f ? d[i] : 0.f;
+          s[i] += gg;
+          q[i] = fmaf(gg, xh, q[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    const int c = j % C, which = j / C;
+    const int g2 = c >> 3, i = c & 7;
+    double acc = 0.0;
+    for (int r = 0; r < slots; ++r) acc += (double)red[(r * groups + g2) * 16 + which * 8 + i];
+    atomicAdd(ws + which * C + c, acc);
+  }
+}
+
+// ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)
+template <int PHASE>
+__global__ void pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
+                                             __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
+                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, const double* __restrict__ ws, double count, int training) {
+  const int groups = 1 << g.lg;
+  const int cg = threadIdx.x & (groups - 1);
+  float mu[8], is[8], ga[8], be[8], mg[8], mgx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = cg * 8 + i;
+    mu[i] = mean[c]; is[i] = invstd[c]; ga[i] = gamma[c]; be[i] = beta[c];
+    mg[i] = training ? (float)(ws[c] / count) : 0.f;
+    mgx[i] = training ? (float)(ws[g.C + c] / count) : 0.f;
+  }
+  const int Hp = g.H + 2, Wp = g.W + 2;
+  const int rows = g.N * Hp, rowlen = Wp << g.lg;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int hp = r % Hp, n = r / Hp;
+    const bool row_ok = hp >= 1 && hp <= g.H;
+    const long long vbase = (long long)r * rowlen;
+    for (int v = threadIdx.x; v < rowlen; v += blockDim.x) {
+      const int wp = v >> g.lg;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (row_ok && wp >= 1 && wp <= g.W) {
+        float f[8], d[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + vbase + v), f);
+        const long long dv = PHASE ? ((phase_row(g, n, hp, wp) << g.lg) + cg) : vbase + v;
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dact) + dv), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (f[i] - mu[i]) * is[i];
+          const float gg = fmaf(xh, ga[i], be[i]) > 0.f ? d[i] : 0.f;
+          f[i] = ga[i] * is[i] * (gg - mg[i] - xh * mgx[i]);
+        }
+        o = pack8(f);
+      }
+      reinterpret_cast<uint4*>(draw)[vbase + v] = o;
+    }
+  }
+}
+
+// stem: y (N,C,H,W) fp32 NCHW -> relu(bn) -> maxpool(3,2,1) -> padded-flat (N,PH+2,PW+2,C) bf16 with zero border
+__global__ void stem_bn_relu_maxpool_pad_kernel(const float* __restrict__ y, int C, int H, int W, int PH, int PW, const float* __restrict__ mean,
+                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __nv_bfloat16 tile[];   // [PW+2][C]
+  const int php = blockIdx.x % (PH + 2), n = blockIdx.x / (PH + 2);
+  const int rowlen = (PW + 2) * C;
+  uint4* o4 = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * rowlen);
+  if (php == 0 || php == PH + 1) {
+    for (int i = threadIdx.x; i < rowlen / 8; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const int ph = php - 1;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tile[(i < C ? 0 : (PW + 1) * C) + (i % C)] = __float2bfloat16(0.f);
+  for (int i = threadIdx.x; i < C * PW; i += blockDim.x) {
+    const int pw = i % PW, c = i / PW;
+    const float sc = invstd[c] * gamma[c];
+    const float sh = beta[c] - mean[c] * sc;
+    const float* yp = y + ((long long)n * C + c) * H * W;
+    float best = 0.f;
+    for (int a = 0; a < 3; ++a) {
+      const int h = ph * 2 - 1 + a;
+      if ((unsigned)h >= (unsigned)H) continue;
+      for (int b = 0; b < 3; ++b) {
+        const int w = pw * 2 - 1 + b;
+        if ((unsigned)w >= (unsigned)W) continue;
+        best = fmaxf(best, fmaf(__ldg(yp + (long long)h * W + w), sc, sh));
+      }
+    }
+    tile[(pw + 1) * C + c] = __float2bfloat16(best);
+  }
+  __syncthreads();
+  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
+  for (int i = threadIdx.x; i < rowlen / 8; i += blockDim.x) o4[i] = t4[i];
+}
+
+// AdaptiveAvgPool2d on a padded-flat input; out (N, C, OH, OW) fp32
+__global__ void avgpool_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int OH, int OW, float* __restrict__ out) {
+  const long long total = (long long)N * OH * OW * C;
+  const int Wp = W + 2, Hp = H + 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    long long r = t / C;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH), w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
+    float s = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) s += __bfloat162float(x[(((long long)n * Hp + h + 1) * Wp + w + 1) * C + c]);
+    out[(((long long)n * C + c) * OH + oh) * OW + ow] = s / (float)((h1 - h0) * (w1 - w0));
+  }
+}
+// dout (N,C,OH,OW) fp32 -> dx padded-flat bf16 (interior only; the border is never read)
+__global__ void avgpool_pad_bwd_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
+                                       __nv_bfloat16* __restrict__ dx) {
+  const long long total = (long long)N * H * W * C;
+  const int Wp = W + 2, Hp = H + 2;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(t % C);
+    long long r = t / C;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    float s = 0.f;
+    for (int oh = 0; oh < OH; ++oh) {
+      const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH);
+      if (h < h0 || h >= h1) continue;
+      for (int ow = 0; ow < OW; ++ow) {
+        const int w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
+        if (w < w0 || w >= w1) continue;
+        s += __ldg(dout + (((long long)n * C + c) * OH + oh) * OW + ow) / (float)((h1 - h0) * (w1 - w0));
+      }
+    }
+    dx[(((long long)n * Hp + h + 1) * Wp + w + 1) * C + c] = __float2bfloat16(s);
+  }
+}
+
+inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
+  if (C % 8 || C > 256 || (C / 8) & (C / 8 - 1)) return 1;
+  g.N = N; g.H = H; g.W = W; g.C = C;
+  g.Hq = phase ? (H - 1) / 2 + 3 : 0;
+  g.Wq = phase ? (W - 1) / 2 + 3 : 0;
+  g.lg = 0;
+  while ((8 << g.lg) < C) ++g.lg;
+  return 0;
+}
+
 }  // namespace
 
 CVAD_API int cvad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd,
@@ -306,6 +555,93 @@ CVAD_API int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, 
   long long total = (long long)N * H * W * C;
   if (total <= 0) return 0;
   avgpool_nhwc_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- padded-flat entry points
+CVAD_API int cvad_pad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd,
+                                                const float* gamma, const float* beta, void* out, void* stream) {
+  const int PH = (H + 2 - 3) / 2 + 1, PW = (W + 2 - 3) / 2 + 1;
+  if (C % 8) return (int)cudaErrorInvalidValue;
+  size_t smem = (size_t)(PW + 2) * C * 2;
+  stem_bn_relu_maxpool_pad_kernel<<<N * (PH + 2), 256, smem, (cudaStream_t)stream>>>(y, C, H, W, PH, PW, mean, invstd, gamma, beta,
+                                                                                     (__nv_bfloat16*)out);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean,
+                                    float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
+  PadGeo g;
+  if (make_geo(g, N, H, W, C, 0)) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
+  pad_reduce_kernel<false, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)raw, nullptr, g, nullptr, nullptr, nullptr,
+                                                                              nullptr, ws);
+  CVAD_LAUNCH_CHECK();
+  bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, (double)N * H * W, eps, momentum, mean, invstd, running_mean, running_var,
+                                                           num_batches_tracked);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int H, int W, int C, int phase_out, const float* mean,
+                                         const float* invstd, const float* gamma, const float* beta, void* stream) {
+  PadGeo g;
+  if (make_geo(g, N, H, W, C, phase_out)) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rows = phase_out ? 4 * N * g.Hq : N * (H + 2);
+  const int blocks = rows < 16 * cvad_num_sms() ? rows : 16 * cvad_num_sms();
+  if (phase_out)
+    pad_bn_apply_relu_kernel<1><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
+  else
+    pad_bn_apply_relu_kernel<0><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in,
+                                       const float* mean, const float* invstd, const float* gamma, const float* beta, int training, double* ws,
+                                       float* dgamma, float* dbeta, void* stream) {
+  PadGeo g;
+  if (make_geo(g, N, H, W, C, phase_in)) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
+  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
+  if (phase_in)
+    pad_reduce_kernel<true, 1><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
+  else
+    pad_reduce_kernel<true, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
+  CVAD_LAUNCH_CHECK();
+  if (draw) {
+    const int rows = N * (H + 2);
+    const int ab = rows < 16 * cvad_num_sms() ? rows : 16 * cvad_num_sms();
+    if (phase_in)
+      pad_bn_relu_bwd_apply_kernel<1><<<ab, 128, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
+                                                          training);
+    else
+      pad_bn_relu_bwd_apply_kernel<0><<<ab, 128, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
+                                                          training);
+    CVAD_LAUNCH_CHECK();
+  }
+  bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream) {
+  long long total = (long long)N * OH * OW * C;
+  if (total <= 0) return 0;
+  avgpool_pad_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream) {
+  long long total = (long long)N * H * W * C;
+  if (total <= 0) return 0;
+  avgpool_pad_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

@@ -1,19 +1,20 @@
 """bf16 tensor-core execution of the M-A backbone (cad:141-158): one autograd node for the whole conv/BN/ReLU stack.
 
-Data flow per step (activations NHWC bf16 in HBM, statistics / gradients of parameters fp32):
+Data flow per step.  Activations live in HBM as zero-bordered NHWC bf16 ("padded-flat", (N, H+2, W+2, C)); the input of a
+stride-2 convolution is written by its producer as four phase planes instead (see csrc/flatconv_tc.cu), so every one of
+the eight 3x3 convolutions -- forward, data-gradient and weight-gradient -- is a sum of row-shifted GEMMs that TMA feeds
+straight into tcgen05.mma.  Statistics and parameter gradients are fp32.
 
   x fp32 (B*T,1,240,360) --conv 7x7 s2 (fp32 FFMA, frozen stem)--> y1 fp32 NCHW
-      --bn1 batch stats--> fused BN+ReLU+MaxPool(3,2,1) --> a0 bf16 NHWC (.,60,90,32)
-  for the 8 layers: raw_i = conv3x3_tcgen05(a_{i-1}) ; (mean, invstd) = stats(raw_i) ; a_i = relu(bn(raw_i))
+      --bn1 batch stats--> fused BN+ReLU+MaxPool(3,2,1) --> a0 bf16 padded-flat (.,62,92,32)
+  for the 8 layers: raw_i = flatconv(a_{i-1}) ; (mean, invstd) = stats(raw_i) ; a_i = relu(bn(raw_i)) [plain | phase planes]
   features = AdaptiveAvgPool(4,6)(a_8) -> fp32 (B*T, 6144) in the reference's (c,h,w) order
 
-Backward walks the same list in reverse: fused ReLU+BN backward (bf16), tcgen05 weight-gradient (fp32 atomics into the
-gradient arena) and tcgen05 data-gradient.  Convolution biases that feed a BatchNorm have an analytically zero gradient
-(the reference only accumulates round-off there); they receive exactly zero here.
+Backward walks the same list in reverse: fused ReLU+BN backward (two passes), tcgen05 weight-gradient (fp32 atomics into
+the gradient arena) and tcgen05 data-gradient.  Convolution biases that feed a BatchNorm have an analytically zero
+gradient (the reference only accumulates round-off there); they receive exactly zero here.
 """
 from __future__ import annotations
-
-import ctypes
 
 import torch
 
@@ -31,13 +32,24 @@ def _layers(bb):
     return out
 
 
+def out_hw(h, w, stride):
+    return (h - 1) // stride + 1, (w - 1) // stride + 1
+
+
+def act_shape(N, h, w, c, phase):
+    """Buffer shape of an activation with interior (h, w): padded-flat, or the 4 phase planes of the stride-2 conv reading it."""
+    if not phase:
+        return (N, h + 2, w + 2, c)
+    ho, wo = out_hw(h, w, 2)
+    return (4, N, ho + 2, wo + 2, c)
+
+
 class _BackboneBF16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, bb, *params):
         dev = x.device
         N, _, H, W = x.shape
         st = _st()
-        training = bb.training
         # ---- stem (frozen in the reference's training recipe, cad:596-598): fp32 conv + bn1 statistics
         y1 = ops.conv_act(x, bb.conv1.weight.detach(), bb.conv1.bias.detach(), 2, 3, ops.ACT_NONE)
         C1 = y1.shape[1]
@@ -50,36 +62,41 @@ class _BackboneBF16(torch.autograd.Function):
                   _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
         else:
             _call("cvad_bn_eval_prepare_f32", C1, float(bn1.eps), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(mean), _ptr(invstd), st)
-        PH, PW = (H1 - 1) // 2 + 1, (W1 - 1) // 2 + 1
-        a = torch.empty((N, PH, PW, C1), device=dev, dtype=BF16)
-        _call("cvad_stem_bn_relu_maxpool_bf16", _ptr(y1), N, C1, H1, W1, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias), _ptr(a), st)
+        h, w = out_hw(H1, W1, 2)
+        layers = _layers(bb)
+        strides = [conv.stride[0] for conv, _ in layers]
+        a = torch.empty(act_shape(N, h, w, C1, strides[0] == 2), device=dev, dtype=BF16)
+        if strides[0] == 2:
+            raise RuntimeError("the first 3x3 convolution after the stem is stride 1 in the reference (cad:150)")
+        _call("cvad_pad_stem_bn_relu_maxpool_bf16", _ptr(y1), N, C1, H1, W1, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias), _ptr(a), st)
         del y1
         need_bwd = any(ctx.needs_input_grad)
         saved = []
-        h, w, cin = PH, PW, C1
-        for conv, bn in _layers(bb):
-            cout, stride = conv.out_channels, conv.stride[0]
-            wf = torch.empty((cout, 9 * cin), device=dev, dtype=BF16)
-            wd = torch.empty((cin, 9 * cout), device=dev, dtype=BF16) if need_bwd else None
-            _call("cvad_pack_w3x3_bf16", _ptr(conv.weight), cout, cin, _ptr(wf), _ptr(wd), st)
-            ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-            raw = torch.empty((N, ho, wo, cout), device=dev, dtype=BF16)
-            _call("cvad_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
-            P = N * ho * wo
+        cin = C1
+        for i, (conv, bn) in enumerate(layers):
+            cout, stride = conv.out_channels, strides[i]
+            wf = torch.empty((9 * cout, cin), device=dev, dtype=BF16)
+            wd = torch.empty((9 * cin, cout), device=dev, dtype=BF16) if need_bwd and i > 0 else None
+            _call("cvad_flat_pack_w3x3_bf16", _ptr(conv.weight), cout, cin, _ptr(wf), _ptr(wd), st)
+            ho, wo = out_hw(h, w, stride)
+            raw = torch.empty((N, ho + 2, wo + 2, cout), device=dev, dtype=BF16)
+            _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
             mean = torch.empty(cout, device=dev, dtype=torch.float32)
             invstd = torch.empty_like(mean)
             if bn.training:
-                _call("cvad_bn_stats_nhwc_bf16", _ptr(raw), P, cout, _ptr(ops.bn_workspace(dev, cout)), float(bn.eps), float(bn.momentum),
+                _call("cvad_pad_bn_stats_bf16", _ptr(raw), N, ho, wo, cout, _ptr(ops.bn_workspace(dev, cout)), float(bn.eps), float(bn.momentum),
                       _ptr(mean), _ptr(invstd), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(bn.num_batches_tracked), st)
             else:
                 _call("cvad_bn_eval_prepare_f32", cout, float(bn.eps), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(mean), _ptr(invstd), st)
-            act = torch.empty_like(raw)
-            _call("cvad_bn_apply_relu_nhwc_bf16", _ptr(raw), _ptr(act), P, cout, _ptr(mean), _ptr(invstd), _ptr(bn.weight), _ptr(bn.bias), st)
+            phase_out = i + 1 < len(layers) and strides[i + 1] == 2
+            act = torch.empty(act_shape(N, ho, wo, cout, phase_out), device=dev, dtype=BF16)
+            _call("cvad_pad_bn_apply_relu_bf16", _ptr(raw), _ptr(act), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd), _ptr(bn.weight),
+                  _ptr(bn.bias), st)
             if need_bwd:
-                saved.append((a, raw, mean, invstd, wd, (h, w, cin, cout, stride, ho, wo), bn.training))
+                saved.append((a, raw, mean, invstd, wd, (h, w, cin, cout, stride, ho, wo), bn.training, phase_out))
             a, h, w, cin = act, ho, wo, cout
         feats = torch.empty((N, cin, 4, 6), device=dev, dtype=torch.float32)
-        _call("cvad_avgpool_nhwc_bf16_fwd", _ptr(a), N, h, w, cin, 4, 6, _ptr(feats), st)
+        _call("cvad_pad_avgpool_bf16_fwd", _ptr(a), N, h, w, cin, 4, 6, _ptr(feats), st)
         ctx.bb, ctx.saved, ctx.last = bb, saved, (N, h, w, cin)
         return feats.reshape(N, -1)
 
@@ -90,25 +107,24 @@ class _BackboneBF16(torch.autograd.Function):
         st = _st()
         dev = dfeat.device
         dfeat = ops._f32c(dfeat)
-        dact = torch.empty((N, h, w, c), device=dev, dtype=BF16)
-        _call("cvad_avgpool_nhwc_bf16_bwd", _ptr(dfeat), N, h, w, c, 4, 6, _ptr(dact), st)
+        dact = torch.empty((N, h + 2, w + 2, c), device=dev, dtype=BF16)
+        _call("cvad_pad_avgpool_bf16_bwd", _ptr(dfeat), N, h, w, c, 4, 6, _ptr(dact), st)
         layers = _layers(bb)
         for idx in range(len(layers) - 1, -1, -1):
             conv, bn = layers[idx]
-            a_in, raw, mean, invstd, wd, (hi, wi, cin, cout, stride, ho, wo), bn_training = saved[idx]
-            P = N * ho * wo
+            a_in, raw, mean, invstd, wd, (hi, wi, cin, cout, stride, ho, wo), bn_training, phase_out = saved[idx]
             draw = torch.empty_like(raw)
             dg = grad_buffer(bn.weight) if _wants_grad(bn.weight) else None
             db = grad_buffer(bn.bias) if _wants_grad(bn.bias) else None
-            _call("cvad_bn_relu_bwd_nhwc_bf16", _ptr(raw), _ptr(dact), _ptr(draw), P, cout, _ptr(mean), _ptr(invstd), _ptr(bn.weight),
-                  _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
+            _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
+                  _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
             if _wants_grad(conv.weight):
-                _call("cvad_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, st)
+                _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, st)
             if _wants_grad(conv.bias):
                 grad_buffer(conv.bias)          # analytically zero (BatchNorm removes the mean); keep the tensor "with grad"
             if idx > 0:
-                dact = torch.empty((N, hi, wi, cin), device=dev, dtype=BF16)
-                _call("cvad_conv3x3_dgrad_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, st)
+                dact = torch.empty(a_in.shape, device=dev, dtype=BF16)
+                _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, st)
             saved[idx] = None
         return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
@@ -118,3 +134,38 @@ def backbone_forward_bf16(bb, x):
     ops._cuda(x)
     params = [p for p in bb.parameters() if p.requires_grad]
     return _BackboneBF16.apply(x.float().contiguous(), bb, *params)
+
+
+# ---- layout helpers (host side; used by the tests and by callers that want NCHW views of the flat buffers)
+def to_padded(x_nchw):
+    """(N,C,H,W) -> padded-flat (N,H+2,W+2,C) bf16 with a zero border."""
+    N, C, H, W = x_nchw.shape
+    out = torch.zeros((N, H + 2, W + 2, C), device=x_nchw.device, dtype=BF16)
+    out[:, 1:H + 1, 1:W + 1, :] = x_nchw.permute(0, 2, 3, 1).to(BF16)
+    return out
+
+
+def from_padded(buf, H, W):
+    return buf[:, 1:H + 1, 1:W + 1, :].permute(0, 3, 1, 2).float().contiguous()
+
+
+def to_phase(x_nchw):
+    """(N,C,H,W) -> the four phase planes (4,N,Ho+2,Wo+2,C) a stride-2 flat convolution reads."""
+    N, C, H, W = x_nchw.shape
+    ho, wo = out_hw(H, W, 2)
+    xp = torch.zeros((N, 2 * (ho + 2) + 2, 2 * (wo + 2) + 2, C), device=x_nchw.device, dtype=BF16)
+    xp[:, 3:H + 3, 3:W + 3, :] = x_nchw.permute(0, 2, 3, 1).to(BF16)      # xp[r] = padded(r - 2)
+    planes = [xp[:, a:a + 2 * (ho + 2):2, b:b + 2 * (wo + 2):2, :] for a in (0, 1) for b in (0, 1)]
+    return torch.stack(planes, 0).contiguous()
+
+
+def from_phase(planes, H, W):
+    """Inverse of to_phase for the interior pixels: (4,N,Ho+2,Wo+2,C) -> (N,C,H,W) fp32."""
+    _, N, hq, wq, C = planes.shape
+    full = torch.zeros((N, 2 * hq, 2 * wq, C), device=planes.device, dtype=planes.dtype)
+    k = 0
+    for a in (0, 1):
+        for b in (0, 1):
+            full[:, a::2, b::2, :] = planes[k]
+            k += 1
+    return full[:, 3:H + 3, 3:W + 3, :].permute(0, 3, 1, 2).float().contiguous()

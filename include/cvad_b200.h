@@ -189,6 +189,37 @@ int cvad_bn_relu_bwd_nhwc_bf16(const void* x, const void* dact, void* dx, long l
 int cvad_avgpool_nhwc_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream);
 int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream);
 
+/* ---- "flat" bf16 tensor-core path of the M-A backbone (flatconv_tc.cu, nhwc_bf16.cu) -----------------------------------
+ * Same arithmetic as the block above (cad:128-139, 145-155) on a zero-bordered layout that lets TMA feed tcgen05 directly:
+ * an activation (N,H,W,C) is stored "padded-flat" as (N,H+2,W+2,C) bf16; the input of a stride-2 convolution is stored as
+ * four phase planes P_ab[n][i][j] = padded(2(i-1)+a, 2(j-1)+b), each in the geometry (N,Ho+2,Wo+2,C) of that convolution's
+ * output, plane index a*2+b outermost.  Convolution outputs / data-gradients carry junk in their border rows. */
+/* OIHW fp32 -> w_fwd [tap][Cout][Cin] bf16, w_dgrad [tap][Cin][Cout] bf16 (either may be NULL) */
+int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, void* w_fwd, void* w_dgrad, void* stream);
+/* (N,H,W,Cin) = input geometry.  stride 1: x, y padded-flat.  stride 2: x = phase planes, y padded-flat (N,Ho+2,Wo+2,Cout). */
+int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                               int stride, void* stream);
+/* stride 1: dy, dx padded-flat.  stride 2: dy padded-flat (N,Ho+2,Wo+2,Cout), dx = phase planes. */
+int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                                 void* stream);
+/* dw (OIHW fp32) += sum over pixels; x as for the forward (padded-flat or phase planes), dy padded-flat with a ZERO border */
+int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
+/* cad:145-148 -> padded-flat (N,PH+2,PW+2,C) bf16 with zero border */
+int cvad_pad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd, const float* gamma,
+                                       const float* beta, void* out, void* stream);
+/* batch statistics over the interior of a padded-flat raw tensor (N,H,W,C interior geometry) */
+int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
+                           float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+/* act = relu(bn(raw)) written padded-flat with zero border (phase_out = 0) or as the four phase planes (phase_out = 1) */
+int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int H, int W, int C, int phase_out, const float* mean, const float* invstd,
+                                const float* gamma, const float* beta, void* stream);
+/* ReLU+BN backward; dact padded-flat (phase_in = 0) or phase planes (phase_in = 1); draw padded-flat with ZERO border (may be NULL) */
+int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, int training, double* ws, float* dgamma,
+                              float* dbeta, void* stream);
+int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream);
+int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

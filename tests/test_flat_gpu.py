@@ -1,0 +1,161 @@
+"""Parity of the flat (TMA + tcgen05) backbone kernels on the B200 against plain PyTorch fp32 ops on the same bf16-rounded
+operands: convolution forward / data-gradient / weight-gradient for stride 1 and 2, and the padded-layout BN / pool /
+stem kernels in both activation layouts (padded-flat and phase planes)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def setup_module(_m):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def rel(a, b, floor=1e-6):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), floor))
+
+
+def _g(seed):
+    return torch.Generator(device="cpu").manual_seed(seed)
+
+
+# N, H, W, Cin, Cout, stride -- the reference's eight layer shapes (cad:150-153) at small / ragged frame counts, plus one
+# case large enough for several 512-row tiles per CTA
+FLAT_CASES = [(3, 12, 17, 32, 32, 1), (2, 9, 11, 64, 64, 1), (2, 8, 12, 128, 128, 1), (1, 8, 12, 256, 256, 1),
+              (2, 12, 18, 32, 64, 2), (3, 15, 23, 64, 128, 2), (2, 15, 23, 128, 256, 2), (1, 7, 9, 32, 32, 1),
+              (40, 60, 90, 32, 32, 1), (24, 30, 45, 64, 64, 1), (9, 60, 90, 32, 64, 2)]
+
+
+def _inputs(dev, N, H, W, Ci, Co, s):
+    x = torch.randn(N, Ci, H, W, generator=_g(1)).to(dev).to(torch.bfloat16).float()
+    w = (torch.randn(Co, Ci, 3, 3, generator=_g(2)) / (3.0 * Ci ** 0.5)).to(dev)
+    b = torch.randn(Co, generator=_g(3)).to(dev)
+    xr = x.clone().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, b, stride=s, padding=1)
+    dy = torch.randn(ref.shape, generator=_g(4)).to(dev).to(torch.bfloat16).float()
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dy)
+    return x, w, b, ref.detach(), dy, gx, gw
+
+
+@pytest.mark.parametrize("case", FLAT_CASES)
+def test_flat_conv3x3_fwd_dgrad_wgrad(dev, case):
+    from cvad_b200 import tc
+    from cvad_b200.ops import _call, _ptr, _st
+    N, H, W, Ci, Co, s = case
+    x, w, b, ref, dy, gx, gw = _inputs(dev, *case)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    wf = torch.empty(9 * Co, Ci, device=dev, dtype=torch.bfloat16)
+    wd = torch.empty(9 * Ci, Co, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_pack_w3x3_bf16", _ptr(w), Co, Ci, _ptr(wf), _ptr(wd), _st())
+    xin = tc.to_padded(x) if s == 1 else tc.to_phase(x)
+    # junk-filled outputs: the kernels must write every interior element themselves
+    y = torch.full((N, Ho + 2, Wo + 2, Co), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_conv3x3_fwd_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _st())
+    torch.cuda.synchronize()
+    e_f = rel(tc.from_padded(y, Ho, Wo), ref)
+    dyp = tc.to_padded(dy)
+    dx = torch.full(xin.shape, 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(dyp), _ptr(wd), _ptr(dx), N, H, W, Ci, Co, s, _st())
+    torch.cuda.synchronize()
+    dxr = tc.from_padded(dx, H, W) if s == 1 else tc.from_phase(dx, H, W)
+    e_d = rel(dxr, gx)
+    dw = torch.zeros(Co, Ci, 3, 3, device=dev)
+    _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(xin), _ptr(dyp), _ptr(dw), N, H, W, Ci, Co, s, _st())
+    torch.cuda.synchronize()
+    e_w = rel(dw, gw)
+    print(f"[flat] {case}: fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e}")
+    assert e_f < 1e-2 and e_d < 1e-2 and e_w < 2e-3
+
+
+def test_layout_helpers_roundtrip(dev):
+    from cvad_b200 import tc
+    x = torch.randn(2, 8, 15, 23, generator=_g(1)).to(dev).to(torch.bfloat16).float()
+    assert torch.equal(tc.from_padded(tc.to_padded(x), 15, 23), x)
+    assert torch.equal(tc.from_phase(tc.to_phase(x), 15, 23), x)
+    x = torch.randn(1, 8, 60, 90, generator=_g(2)).to(dev).to(torch.bfloat16).float()
+    assert torch.equal(tc.from_phase(tc.to_phase(x), 60, 90), x)
+
+
+@pytest.mark.parametrize("C,H,W,phase", [(32, 12, 18, 0), (32, 12, 18, 1), (64, 15, 23, 1), (128, 15, 23, 0), (256, 8, 12, 0), (64, 9, 7, 1)])
+@pytest.mark.parametrize("training", [True, False])
+def test_pad_bn_relu_fwd_bwd(dev, C, H, W, phase, training):
+    """stats + apply (+ phase-plane output) and the fused ReLU+BN backward (dact given in the same layout as act)."""
+    from cvad_b200 import ops, tc
+    from cvad_b200.ops import _call, _ptr, _st
+    N = 3
+    x = (torch.randn(N, C, H, W, generator=_g(1)) * 2 + 1).to(dev).to(torch.bfloat16).float()
+    raw = tc.to_padded(x)
+    raw[:, 0] = 9.0                      # convolution outputs carry junk in their border
+    raw[:, :, 0] = -9.0
+    raw[:, -1] = 5.0
+    raw[:, :, -1] = 3.0
+    xr = x.clone().requires_grad_(True)
+    gam = (torch.rand(C, generator=_g(2)) + 0.5).to(dev).requires_grad_(True)
+    bet = torch.randn(C, generator=_g(3)).to(dev).requires_grad_(True)
+    rm = (torch.randn(C, generator=_g(12)) * 0.1 + 1).to(dev)
+    rv = (torch.rand(C, generator=_g(13)) + 3.5).to(dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    ref = F.relu(F.batch_norm(xr, rm, rv, gam, bet, training, 0.1, 1e-5))
+    mean, invstd = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    nbt = torch.tensor(0, device=dev)
+    if training:
+        _call("cvad_pad_bn_stats_bf16", _ptr(raw), N, H, W, C, _ptr(ops.bn_workspace(dev, C)), 1e-5, 0.1, _ptr(mean), _ptr(invstd), _ptr(rm2),
+              _ptr(rv2), _ptr(nbt), _st())
+        assert rel(rm2, rm) < 1e-4 and rel(rv2, rv) < 1e-4 and int(nbt) == 1
+    else:
+        _call("cvad_bn_eval_prepare_f32", C, 1e-5, _ptr(rm2), _ptr(rv2), _ptr(mean), _ptr(invstd), _st())
+    act = torch.full(tc.act_shape(N, H, W, C, phase), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_pad_bn_apply_relu_bf16", _ptr(raw), _ptr(act), N, H, W, C, phase, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), _st())
+    torch.cuda.synchronize()
+    expect = tc.to_phase(ref.detach()) if phase else tc.to_padded(ref.detach())
+    assert rel(act.float(), expect.float()) < 1e-2
+    ones = torch.ones(N, C, H, W, device=dev)
+    hole = (tc.to_phase(ones) if phase else tc.to_padded(ones)) == 0
+    assert float(act[hole].float().abs().max()) == 0.0      # exact zeros wherever no pixel maps (conv padding)
+    g = torch.randn(N, C, H, W, generator=_g(5)).to(dev).to(torch.bfloat16).float()
+    dact = tc.to_phase(g) if phase else tc.to_padded(g)
+    if not phase:
+        dact[:, 0] = 11.0                # data-gradients carry junk in their border as well
+        dact[:, :, -1] = -4.0
+    gr = torch.autograd.grad(ref, (xr, gam, bet), g)
+    draw = torch.full(raw.shape, 7.0, device=dev, dtype=torch.bfloat16)
+    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, H, W, C, phase, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet),
+          int(training), _ptr(ops.bn_workspace(dev, C)), _ptr(dg), _ptr(db), _st())
+    torch.cuda.synchronize()
+    assert rel(tc.from_padded(draw, H, W), gr[0]) < 1e-2
+    border = draw.clone()
+    border[:, 1:H + 1, 1:W + 1] = 0
+    assert float(border.float().abs().max()) == 0.0
+    assert rel(dg, gr[1]) < 2e-3 and rel(db, gr[2]) < 2e-3
+
+
+def test_pad_stem_and_avgpool(dev):
+    from cvad_b200 import tc
+    from cvad_b200.ops import _call, _ptr, _st
+    y1 = torch.randn(2, 32, 21, 30, generator=_g(7)).to(dev) * 3
+    m1, i1 = torch.randn(32, generator=_g(8)).to(dev), (torch.rand(32, generator=_g(9)) + 0.5).to(dev)
+    g1, b1 = (torch.rand(32, generator=_g(10)) - 0.3).to(dev), torch.randn(32, generator=_g(11)).to(dev)
+    sref = F.max_pool2d(F.relu((y1 - m1.view(1, -1, 1, 1)) * (i1 * g1).view(1, -1, 1, 1) + b1.view(1, -1, 1, 1)), 3, 2, 1)
+    PH, PW = sref.shape[2], sref.shape[3]
+    so = torch.full((2, PH + 2, PW + 2, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_pad_stem_bn_relu_maxpool_bf16", _ptr(y1), 2, 32, 21, 30, _ptr(m1), _ptr(i1), _ptr(g1), _ptr(b1), _ptr(so), _st())
+    assert rel(so.float(), tc.to_padded(sref).float()) < 1e-2
+    N, C, H, W = 3, 64, 9, 14
+    x = torch.randn(N, C, H, W, generator=_g(1)).to(dev).to(torch.bfloat16).float()
+    xp = tc.to_padded(x)
+    xp[:, 0] = 5.0
+    feats = torch.empty(N, C, 4, 6, device=dev)
+    _call("cvad_pad_avgpool_bf16_fwd", _ptr(xp), N, H, W, C, 4, 6, _ptr(feats), _st())
+    xr = x.clone().requires_grad_(True)
+    pr = F.adaptive_avg_pool2d(xr, (4, 6))
+    assert rel(feats, pr) < 1e-5
+    go = torch.randn(N, C, 4, 6, generator=_g(6)).to(dev)
+    (gxr,) = torch.autograd.grad(pr, xr, go)
+    dxp = torch.zeros(N, H + 2, W + 2, C, device=dev, dtype=torch.bfloat16)
+    _call("cvad_pad_avgpool_bf16_bwd", _ptr(go), N, H, W, C, 4, 6, _ptr(dxp), _st())
+    assert rel(tc.from_padded(dxp, H, W), gxr) < 1e-2
