@@ -14,6 +14,6 @@ from . import _lib
 
 _lib.lib()   # fail loudly when the CUDA extension has not been built
 
-from . import arena, ma, ma_ops, mb, mc, noise, ops, parallel  # noqa: E402,F401
+from . import arena, graphs, ma, ma_ops, mb, mc, noise, ops, parallel, tc  # noqa: E402,F401
 
-__all__ = ["arena", "ma", "ma_ops", "mb", "mc", "noise", "ops", "parallel"]
+__all__ = ["arena", "graphs", "ma", "ma_ops", "mb", "mc", "noise", "ops", "parallel", "tc"]

@@ -29,7 +29,7 @@ class ConvDesc(ctypes.Structure):
 
 class OptState(ctypes.Structure):
     _fields_ = [("gradsq", ctypes.c_double), ("nonfinite", ctypes.c_double), ("last_gradnorm", ctypes.c_double),
-                ("step", ctypes.c_longlong * 8), ("skipped", ctypes.c_longlong)]
+                ("step", ctypes.c_longlong * 8), ("skipped", ctypes.c_longlong), ("lr_device", ctypes.c_double)]
 
 
 def sources():

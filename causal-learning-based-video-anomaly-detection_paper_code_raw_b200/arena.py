@@ -88,6 +88,14 @@ class FlatArena:
         buf = torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8)
         self.state.copy_(buf.to(self.device))
 
+    def set_device_lr(self, lr: float):
+        """Keep the learning rate in device memory so a captured CUDA graph follows the scheduler (0 = use the argument)."""
+        if getattr(self, "_device_lr", None) == lr:
+            return
+        off = OptState.lr_device.offset
+        self.state[off:off + 8].copy_(torch.tensor([lr], dtype=torch.float64).view(torch.uint8), non_blocking=False)
+        self._device_lr = lr
+
     def step(self, lr, betas, eps, weight_decay, decoupled, clip_mode, max_norm, clip_threshold, nan_mode, grad_scale=1.0):
         st = ops._st()
         ops._call("cvad_sumsq_f32", self.g.data_ptr() + 4 * HEADER, self.total - HEADER, float(grad_scale), self.state.data_ptr(), st)
@@ -164,6 +172,10 @@ class FusedAdam(torch.optim.Optimizer):
             for k in ("lr", "betas", "eps", "weight_decay"):
                 if k in sg:
                     g[k] = sg[k]
+
+    def sync_lr_to_device(self):
+        """Call before replaying a captured step: publishes param_groups[0]['lr'] to the device-side optimizer state."""
+        self.arena.set_device_lr(float(self.param_groups[0]["lr"]))
 
     def last_grad_norm(self) -> float:
         return float(self.arena.read_state().last_gradnorm)

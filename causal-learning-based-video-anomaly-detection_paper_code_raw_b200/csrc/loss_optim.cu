@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
   const double t = (double)(st->step[slot] + 1);
   const float bc1 = (float)(1.0 - pow((double)beta1, t));
   const float bc2s = (float)sqrt(1.0 - pow((double)beta2, t));
+  if (st->lr_device > 0.0) lr = (float)st->lr_device;
   const float step_size = lr / bc1;
   const long long base = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
   float4 pv = *reinterpret_cast<float4*>(p + base);

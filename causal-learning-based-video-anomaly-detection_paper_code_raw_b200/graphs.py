@@ -1,0 +1,59 @@
+"""CUDA-graph capture of a whole train / inference step (forward, fused loss, backward, all-reduce, fused clip+Adam).
+
+A step of the hot path is 250-300 kernel launches of a few microseconds each; issued one by one from Python the host
+is slower than the device (~17 ms of launch work for a ~10 ms step).  Every kernel of libcvad_b200.so launches on the
+caller's stream, allocates nothing and never synchronises, and all step bookkeeping (NaN flags, skip logic, Adam step
+counts) lives on the device, so the whole step can be captured once and replayed with one launch.
+
+Capturing needs a few warm-up executions on a side stream (lazy one-time initialisation: function attributes, driver
+entry points, torch's allocator).  Those executions are real steps, so every tensor a step mutates -- parameters, Adam
+moments and counters, BatchNorm running statistics -- is snapshotted before and restored after them: building the graph
+does not advance training.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class GraphedStep:
+    """``step_fn(*static_inputs) -> tuple of tensors`` captured into one CUDA graph.
+
+    ``__call__(*inputs)`` copies the inputs into the static buffers (an H2D copy when they live in pinned host memory),
+    replays the graph and returns the static output tensors (valid until the next replay)."""
+
+    def __init__(self, step_fn, example_inputs, mutated=(), warmup: int = 3, pre_replay=None):
+        self.pre_replay = pre_replay
+        self.static_inputs = [torch.empty_like(t, device=t.device if t.is_cuda else torch.cuda.current_device()) for t in example_inputs]
+        for s, t in zip(self.static_inputs, example_inputs):
+            s.copy_(t)
+        mutated = [t for t in mutated if t is not None]
+        snap = [t.detach().clone() for t in mutated]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step_fn(*self.static_inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            for t, s in zip(mutated, snap):
+                t.copy_(s)
+        del snap
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(self.graph):
+            out = step_fn(*self.static_inputs)
+        self.launches = ops.LAUNCHES[0] - n0          # cvad ABI calls inside one replay
+        self.outputs = out if isinstance(out, tuple) else (out,)
+
+    def __call__(self, *inputs):
+        for s, t in zip(self.static_inputs, inputs):
+            if t is not s:
+                s.copy_(t, non_blocking=True)
+        if self.pre_replay is not None:
+            self.pre_replay()
+        self.graph.replay()
+        ops.LAUNCHES[0] += self.launches
+        return self.outputs

@@ -332,6 +332,22 @@ class MATrainer:
         self.optimizer.step()
         return comp, outputs
 
+    def mutated_tensors(self):
+        """Everything a train step changes in place (what a CUDA-graph warm-up has to restore)."""
+        a = self.optimizer.arena
+        return [a.p, a.m, a.v, a.state] + [b for b in self.model.buffers()]
+
+    def graphed_train_step(self, videos, labels):
+        """One CUDA graph for zero_grad + forward + loss + backward (+ all-reduce) + clip/AdamW on this batch shape.
+        Returns a callable ``(videos, labels) -> (loss components (5,), anomaly_scores (B,))``."""
+        from .graphs import GraphedStep
+
+        def step(x, y):
+            comp, out = self.train_step(x, y)
+            return comp, out["anomaly_scores"]
+        self.optimizer.sync_lr_to_device()
+        return GraphedStep(step, (videos, labels), self.mutated_tensors(), pre_replay=self.optimizer.sync_lr_to_device)
+
     @torch.no_grad()
     def eval_step(self, videos, labels):
         outputs = self.model(videos)

@@ -41,6 +41,7 @@ typedef struct cvad_opt_state {
   double last_gradnorm;  /* total gradient norm of the last step (what clip_grad_norm_ returns)            */
   long long step[8];     /* Adam step count per activity slot; slot 0 = tensors that always receive grads */
   long long skipped;     /* steps skipped because of a non-finite loss / gradient                         */
+  double lr_device;      /* > 0: overrides the lr argument (lets a captured CUDA graph follow an LR scheduler) */
 } cvad_opt_state;
 
 /* ---- convolution, fp32 implicit GEMM (conv_f32.cu) -------------------------------------------------------------

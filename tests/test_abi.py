@@ -30,7 +30,7 @@ def test_header_declares_only_plain_c_types():
 def test_struct_mirrors_match_header_layout():
     from cvad_b200._lib import ConvDesc, OptState
     assert ctypes.sizeof(ConvDesc) == 18 * 4 + 10 * 8
-    assert ctypes.sizeof(OptState) == 3 * 8 + 8 * 8 + 8
+    assert ctypes.sizeof(OptState) == 3 * 8 + 8 * 8 + 8 + 8
 
 
 def test_no_cpu_fallback():

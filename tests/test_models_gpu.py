@@ -299,7 +299,11 @@ def test_ma_train_step_parity_fp32(dev, gold, idx):
         if not p.requires_grad:
             continue
         moved = not torch.equal(before[k], p.detach())
-        assert moved == c["has_grad"][k], (k, moved, c["has_grad"][k])
+        if not c["has_grad"][k]:
+            assert not moved, k
+        elif c["grad_summary"].get(k, {"norm": 0.0})["norm"] > 0:
+            # (a tensor whose gradient exists but is exactly zero only sees lr*wd = 3e-9 of decay: below fp32 resolution)
+            assert moved, k
 
 
 @pytest.mark.parametrize("idx", [0, 1, 2, 3])
