@@ -31,7 +31,7 @@ namespace {
 using namespace cvad_tc;
 
 constexpr int FC_MAX_UNITS = 16;
-constexpr int FC_WST = 4;        // weight-tile ring depth
+constexpr int FC_WST = 16;       // maximum weight-tile ring depth (the launch picks what fits)
 constexpr int FC_BOXR = 64;      // rows per activation TMA box
 
 struct FcUnit {
@@ -45,7 +45,7 @@ struct FcUnit {
 struct FcParams {
   long long rows;        // output rows (flat pixels)
   long long out_row_base;
-  int n_units, seg_rows, sub, n_blocks, ld_out;
+  int n_units, seg_rows, sub, n_blocks, ld_out, wst;
   FcUnit units[FC_MAX_UNITS];
 };
 
@@ -69,10 +69,11 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
   const uint32_t s_src = smem_base;
   const uint32_t s_w = smem_base + 2 * seg_bytes;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int MT = 128 * p.sub;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int sub = p.sub, n_units = p.n_units, n_blocks = p.n_blocks, seg_rows = p.seg_rows, wst = p.wst;
+  const int MT = 128 * sub;
   const long long n_tiles = (p.rows + MT - 1) / MT;
-  const long long total = n_tiles * p.n_blocks;
+  const long long total = n_tiles * n_blocks;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
@@ -88,84 +89,101 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    uint32_t src_cnt = 0, w_cnt = 0;
-    auto load_src = [&](long long q0, const FcUnit& u) {
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: activation segments
+    uint32_t src_cnt = 0;
+    auto load_src = [&](long long q0, int u) {
       const int st = src_cnt & 1;
       mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
-      mbar_expect_tx(&bar_src_full[st], seg_bytes);
-      const int r0 = (int)(q0 + u.row_off);
-      for (int r = 0; r < p.seg_rows; r += FC_BOXR) tma_load_2d(s_src + st * seg_bytes + r * ROWB, &map_src, u.col, r0 + r, &bar_src_full[st]);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_src_full[st], seg_bytes);
+        const int r0 = (int)(q0 + p.units[u].row_off), col = p.units[u].col;
+        const uint32_t dst = s_src + st * seg_bytes;
+        for (int r = 0; r < seg_rows; r += FC_BOXR) tma_load_2d(dst + r * ROWB, &map_src, col, r0 + r, &bar_src_full[st]);
+      }
+      __syncwarp();
       ++src_cnt;
     };
-    if ((long long)blockIdx.x < total) load_src((blockIdx.x / p.n_blocks) * (long long)MT, p.units[0]);
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const long long q0 = (wi / p.n_blocks) * MT;
-      const int nb = (int)(wi % p.n_blocks);
-      for (int u = 0; u < p.n_units; ++u) {
-        if (u + 1 < p.n_units) load_src(q0, p.units[u + 1]);
-        else if (wi + gridDim.x < total) load_src(((wi + gridDim.x) / p.n_blocks) * MT, p.units[0]);
-        const FcUnit& un = p.units[u];
-        for (int t = 0; t < un.ntaps; ++t) {
-          const int st = w_cnt % FC_WST;
-          mbar_wait(&bar_w_empty[st], ((w_cnt / FC_WST) & 1) ^ 1);
-          mbar_expect_tx(&bar_w_full[st], W_BYTES);
-          tma_load_2d(s_w + st * W_BYTES, &map_w, un.col, un.tap_wrow[t] + nb * N, &bar_w_full[st]);
+      const long long q0 = (wi / n_blocks) * MT;
+      for (int u = 0; u < n_units; ++u) load_src(q0, u);
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ TMA producer: per-tap weight tiles
+    uint32_t w_cnt = 0;
+    for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
+      const int nb = (int)(wi % n_blocks);
+      for (int u = 0; u < n_units; ++u) {
+        const int ntaps = p.units[u].ntaps, col = p.units[u].col;
+        for (int t = 0; t < ntaps; ++t) {
+          const int st = w_cnt % wst;
+          mbar_wait(&bar_w_empty[st], ((w_cnt / wst) & 1) ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&bar_w_full[st], W_BYTES);
+            tma_load_2d(s_w + st * W_BYTES, &map_w, col, p.units[u].tap_wrow[t] + nb * N, &bar_w_full[st]);
+          }
+          __syncwarp();
           ++w_cnt;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp walks the loops, one lane issues)
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint64_t desc_hi = make_smem_desc(0, 16, SBO, LAYOUT);
     uint32_t src_cnt = 0, w_cnt = 0, acc_cnt = 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      for (int u = 0; u < p.n_units; ++u) {
-        const FcUnit& un = p.units[u];
+      for (int u = 0; u < n_units; ++u) {
+        const int ntaps = p.units[u].ntaps;
         const int st = src_cnt & 1;
         mbar_wait(&bar_src_full[st], (src_cnt >> 1) & 1);
         tc_fence_after();
         const uint32_t a_seg = s_src + st * seg_bytes;
-        for (int t = 0; t < un.ntaps; ++t) {
-          const int ws = w_cnt % FC_WST;
-          mbar_wait(&bar_w_full[ws], (w_cnt / FC_WST) & 1);
+        for (int t = 0; t < ntaps; ++t) {
+          const int ws = w_cnt % wst;
+          mbar_wait(&bar_w_full[ws], (w_cnt / wst) & 1);
           tc_fence_after();
           const uint32_t b_base = s_w + ws * W_BYTES;
           const bool first = (u == 0 && t == 0);
-          const bool last = (u == p.n_units - 1 && t == un.ntaps - 1);
-          for (int s = 0; s < p.sub; ++s) {
+          const bool last = (u == n_units - 1 && t == ntaps - 1);
+          const uint32_t a_tap = a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB;
+          for (int s = 0; s < sub; ++s) {
             const uint32_t use = acc_cnt + s;
             const int slot = use % NSLOT;
             if (first) {
               mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
               tc_fence_after();
             }
-            const uint32_t a_base = a_seg + (uint32_t)(un.tap_delta[t] + s * 128) * ROWB;
+            if (elect_one()) {
+              const uint32_t a_base = a_tap + (uint32_t)s * 128 * ROWB;
 #pragma unroll
-            for (int k = 0; k < K16; ++k) {
-              const uint64_t da = make_smem_desc(a_base + k * 32, 16, SBO, LAYOUT);
-              const uint64_t db = make_smem_desc(b_base + k * 32, 16, SBO, LAYOUT);
-              tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+              for (int k = 0; k < K16; ++k) {
+                const uint64_t da = desc_hi | (uint64_t)(((a_base + k * 32) >> 4) & 0x3FFF);
+                const uint64_t db = desc_hi | (uint64_t)(((b_base + k * 32) >> 4) & 0x3FFF);
+                tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+              }
+              if (last) tc_commit(&bar_acc_full[slot]);
             }
-            if (last) tc_commit(&bar_acc_full[slot]);
+            __syncwarp();
           }
-          tc_commit(&bar_w_empty[ws]);
+          if (elect_one()) tc_commit(&bar_w_empty[ws]);
+          __syncwarp();
           ++w_cnt;
         }
-        tc_commit(&bar_src_empty[st]);
+        if (elect_one()) tc_commit(&bar_src_empty[st]);
+        __syncwarp();
         ++src_cnt;
       }
-      acc_cnt += p.sub;
+      acc_cnt += sub;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
     const int ew = warp - 4;
     uint32_t acc_cnt = 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const long long q0 = (wi / p.n_blocks) * MT;
-      const int nb = (int)(wi % p.n_blocks);
-      for (int s = 0; s < p.sub; ++s) {
+      const long long q0 = (wi / n_blocks) * MT;
+      const int nb = (int)(wi % n_blocks);
+      for (int s = 0; s < sub; ++s) {
         const uint32_t use = acc_cnt + s;
         const int slot = use % NSLOT;
         mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
         tc_fence_before();
         mbar_arrive(&bar_acc_empty[slot]);
       }
-      acc_cnt += p.sub;
+      acc_cnt += sub;
     }
   }
   tc_fence_before();
@@ -205,8 +223,13 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------- host side
 template <int ROWB, int N>
 int launch_flatconv(const CUtensorMap& ms, const CUtensorMap& mw, const FcParams& p, const float* bias, __nv_bfloat16* out, cudaStream_t st) {
-  const size_t smem = 2 * (size_t)p.seg_rows * ROWB + (size_t)FC_WST * N * ROWB + 1024;
-  if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
+  // weight ring: as deep as shared memory allows (>= 2), so a tap's tile is in flight long before its MMAs issue
+  const size_t fixed = 2 * (size_t)p.seg_rows * ROWB + 1024;
+  if (fixed + 2 * (size_t)N * ROWB > 226 * 1024) return (int)cudaErrorInvalidValue;
+  long long wst = (long long)((226 * 1024 - fixed) / ((size_t)N * ROWB));
+  FcParams pp = p;
+  pp.wst = (int)(wst > FC_WST ? FC_WST : wst);
+  const size_t smem = fixed + (size_t)pp.wst * N * ROWB;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(flatconv_kernel<ROWB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -216,7 +239,7 @@ int launch_flatconv(const CUtensorMap& ms, const CUtensorMap& mw, const FcParams
   const long long MT = 128LL * p.sub;
   const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
-  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mw, p, bias, out);
+  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mw, pp, bias, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -429,12 +452,13 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   const uint32_t b1 = (uint32_t)p.qs * ROWB_B;
   const uint32_t stage_bytes = a_bytes + B_SLABS * b1;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int qs = p.qs, n_stages = p.n_stages;
   const int cib = blockIdx.y / p.co_blocks, cob = blockIdx.y % p.co_blocks;
   const long long p_begin = (long long)blockIdx.x * p.pix_per_cta;
   long long p_end = p_begin + p.pix_per_cta;
   if (p_end > p.rows) p_end = p.rows;
-  const int n_iter = p_begin < p_end ? (int)((p_end - p_begin + p.qs - 1) / p.qs) : 0;
+  const int n_iter = p_begin < p_end ? (int)((p_end - p_begin + qs - 1) / qs) : 0;
 
   if (tid == 0) {
     for (int i = 0; i < WG_MAX_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -449,44 +473,55 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     for (int it = 0; it < n_iter; ++it) {
-      const int st = it % p.n_stages;
-      mbar_wait(&bar_empty[st], ((it / p.n_stages) & 1) ^ 1);
-      mbar_expect_tx(&bar_full[st], stage_bytes);
-      const long long q = p_begin + (long long)it * p.qs;
-      const uint32_t base = smem_base + st * stage_bytes;
-      for (int sg = 0; sg < p.n_seg; ++sg)
-        for (int sl = 0; sl < A_SLABS; ++sl) {
-          const uint32_t dst = base + (sg * A_SLABS + sl) * seg1;
-          const int r0 = (int)(q + p.seg_row_off[sg]);
-          for (int r = 0; r < p.seg_rows; r += WG_BOXR_A) tma_load_2d(dst + r * ROWB_A, &map_a, cib * CI_BLK + sl * 64, r0 + r, &bar_full[st]);
+      const int st = it % n_stages;
+      mbar_wait(&bar_empty[st], ((it / n_stages) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_full[st], stage_bytes);
+        const long long q = p_begin + (long long)it * qs;
+        const uint32_t base = smem_base + st * stage_bytes;
+        for (int sg = 0; sg < p.n_seg; ++sg)
+          for (int sl = 0; sl < A_SLABS; ++sl) {
+            const uint32_t dst = base + (sg * A_SLABS + sl) * seg1;
+            const int r0 = (int)(q + p.seg_row_off[sg]);
+            for (int r = 0; r < p.seg_rows; r += WG_BOXR_A) tma_load_2d(dst + r * ROWB_A, &map_a, cib * CI_BLK + sl * 64, r0 + r, &bar_full[st]);
+          }
+        for (int sl = 0; sl < B_SLABS; ++sl) {
+          const uint32_t dst = base + a_bytes + sl * b1;
+          for (int r = 0; r < qs; r += WG_BOXR_B) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
         }
-      for (int sl = 0; sl < B_SLABS; ++sl) {
-        const uint32_t dst = base + a_bytes + sl * b1;
-        for (int r = 0; r < p.qs; r += WG_BOXR_B) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
       }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);
     const uint32_t lbo_a = A_SLABS == 2 ? seg1 : ROWB_A;
+    const uint64_t da_hi = make_smem_desc(0, lbo_a, 8 * ROWB_A, LAY_A);
+    const uint64_t db_hi = make_smem_desc(0, b1, 8 * ROWB_B, LAY_B);
+    const int n_groups = p.n_groups;
+    const int ksteps = qs / 16;
     for (int it = 0; it < n_iter; ++it) {
-      const int st = it % p.n_stages;
-      mbar_wait(&bar_full[st], (it / p.n_stages) & 1);
+      const int st = it % n_stages;
+      mbar_wait(&bar_full[st], (it / n_stages) & 1);
       tc_fence_after();
       const uint32_t base = smem_base + st * stage_bytes;
-      const int ksteps = p.qs / 16;
-      for (int k = 0; k < ksteps; ++k) {
-        const uint64_t db = make_smem_desc(base + a_bytes + k * 16 * ROWB_B, b1, 8 * ROWB_B, LAY_B);
-        for (int g = 0; g < p.n_groups; ++g) {
-          const uint32_t a_start = base + p.groups[g].seg * A_SLABS * seg1 + (uint32_t)(p.groups[g].delta + k * 16) * ROWB_A;
-          const uint64_t da = make_smem_desc(a_start, lbo_a, 8 * ROWB_A, LAY_A);
-          tc_mma_bf16(tmem_base + g * NB, da, db, idesc, (it | k) != 0);
+      if (elect_one()) {
+        for (int g = 0; g < n_groups; ++g) {
+          const uint32_t a0 = base + p.groups[g].seg * A_SLABS * seg1 + (uint32_t)p.groups[g].delta * ROWB_A;
+          const uint32_t tacc = tmem_base + g * NB;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = da_hi | (uint64_t)(((a0 + k * 16 * ROWB_A) >> 4) & 0x3FFF);
+            const uint64_t db = db_hi | (uint64_t)(((base + a_bytes + k * 16 * ROWB_B) >> 4) & 0x3FFF);
+            tc_mma_bf16(tacc, da, db, idesc, (it | k) != 0);
+          }
         }
+        tc_commit(&bar_empty[st]);
       }
-      tc_commit(&bar_empty[st]);
+      __syncwarp();
     }
-    tc_commit(&bar_done);
+    if (elect_one()) tc_commit(&bar_done);
+    __syncwarp();
   }
   __syncwarp();
   if (n_iter > 0) {
