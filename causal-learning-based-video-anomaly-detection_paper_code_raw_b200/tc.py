@@ -5,8 +5,8 @@ stride-2 convolution is written by its producer as four phase planes instead (se
 the eight 3x3 convolutions -- forward, data-gradient and weight-gradient -- is a sum of row-shifted GEMMs that TMA feeds
 straight into tcgen05.mma.  Statistics and parameter gradients are fp32.
 
-  x fp32 (B*T,1,240,360) --conv 7x7 s2 (fp32 FFMA, frozen stem)--> y1 fp32 NCHW
-      --bn1 batch stats--> fused BN+ReLU+MaxPool(3,2,1) --> a0 bf16 padded-flat (.,62,92,32)
+  x fp32 (B*T,1,240,360) --tcgen05 tf32 conv 7x7 s2, pass 1: bn1 batch statistics (nothing written)
+      --pass 2: conv + BN + ReLU--> bf16 NHWC --MaxPool(3,2,1)--> a0 bf16 padded-flat (.,62,92,32)
   for the 8 layers: raw_i = flatconv(a_{i-1}) ; (mean, invstd) = stats(raw_i) ; a_i = relu(bn(raw_i)) [plain | phase planes]
   features = AdaptiveAvgPool(4,6)(a_8) -> fp32 (B*T, 6144) in the reference's (c,h,w) order
 
@@ -50,25 +50,31 @@ class _BackboneBF16(torch.autograd.Function):
         dev = x.device
         N, _, H, W = x.shape
         st = _st()
-        # ---- stem (frozen in the reference's training recipe, cad:596-598): fp32 conv + bn1 statistics
-        y1 = ops.conv_act(x, bb.conv1.weight.detach(), bb.conv1.bias.detach(), 2, 3, ops.ACT_NONE)
-        C1 = y1.shape[1]
-        H1, W1 = y1.shape[2], y1.shape[3]
+        # ---- stem (frozen in the reference's training recipe, cad:596-598): tf32 tensor-core conv, two passes over x
+        bn1, conv1 = bb.bn1, bb.conv1
+        C1 = conv1.out_channels
+        if C1 != 32 or conv1.in_channels != 1 or conv1.kernel_size != (7, 7) or conv1.stride != (2, 2):
+            raise RuntimeError("the tensor-core stem implements the reference's 7x7 stride-2 1->32 convolution (cad:115)")
+        x = x.contiguous()
+        H1, W1 = out_hw(H, W, 2)
         mean = torch.empty(C1, device=dev, dtype=torch.float32)
         invstd = torch.empty_like(mean)
-        bn1 = bb.bn1
+        w1, b1 = conv1.weight.detach(), conv1.bias.detach()
         if bn1.training:
-            _call("cvad_bn_train_stats_f32", _ptr(y1), N, C1, H1 * W1, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps), float(bn1.momentum),
-                  _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
+            _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps),
+                  float(bn1.momentum), _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
         else:
             _call("cvad_bn_eval_prepare_f32", C1, float(bn1.eps), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(mean), _ptr(invstd), st)
+        y1 = torch.empty((N, H1, W1, C1), device=dev, dtype=BF16)
+        _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
+              _ptr(y1), st)
         h, w = out_hw(H1, W1, 2)
         layers = _layers(bb)
         strides = [conv.stride[0] for conv, _ in layers]
-        a = torch.empty(act_shape(N, h, w, C1, strides[0] == 2), device=dev, dtype=BF16)
         if strides[0] == 2:
             raise RuntimeError("the first 3x3 convolution after the stem is stride 1 in the reference (cad:150)")
-        _call("cvad_pad_stem_bn_relu_maxpool_bf16", _ptr(y1), N, C1, H1, W1, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias), _ptr(a), st)
+        a = torch.empty(act_shape(N, h, w, C1, False), device=dev, dtype=BF16)
+        _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
         del y1
         need_bwd = any(ctx.needs_input_grad)
         saved = []

@@ -159,3 +159,39 @@ def test_pad_stem_and_avgpool(dev):
     dxp = torch.zeros(N, H + 2, W + 2, C, device=dev, dtype=torch.bfloat16)
     _call("cvad_pad_avgpool_bf16_bwd", _ptr(go), N, H, W, C, 4, 6, _ptr(dxp), _st())
     assert rel(tc.from_padded(dxp, H, W), gxr) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 37, 53), (3, 240, 360), (1, 16, 20)])
+@pytest.mark.parametrize("training", [True, False])
+def test_stem_tf32(dev, N, H, W, training):
+    """conv 7x7 s2 p3 1->32 + bn1 (+ running statistics) + relu + maxpool(3,2,1), tf32 tensor-core passes vs fp32 torch."""
+    from cvad_b200 import ops, tc
+    from cvad_b200.ops import _call, _ptr, _st
+    x = (torch.rand(N, 1, H, W, generator=_g(1)) * 255.0).round().sub(0.5).div(0.5).to(dev)     # the reference's [-1, 509] range
+    w = (torch.randn(32, 1, 7, 7, generator=_g(2)) * 0.1).to(dev)
+    b = torch.randn(32, generator=_g(3)).to(dev)
+    gam = (torch.rand(32, generator=_g(4)) + 0.5).to(dev)
+    bet = torch.randn(32, generator=_g(5)).to(dev)
+    rm = torch.randn(32, generator=_g(6)).to(dev)
+    rv = (torch.rand(32, generator=_g(7)) * 100 + 50).to(dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    y = F.conv2d(x, w, b, stride=2, padding=3)
+    ref = F.max_pool2d(F.relu(F.batch_norm(y, rm, rv, gam, bet, training, 0.1, 1e-5)), 3, 2, 1)
+    mean, invstd = torch.empty(32, device=dev), torch.empty(32, device=dev)
+    nbt = torch.tensor(0, device=dev)
+    if training:
+        _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w), _ptr(b), N, H, W, _ptr(ops.bn_workspace(dev, 32)), 1e-5, 0.1, _ptr(mean), _ptr(invstd),
+              _ptr(rm2), _ptr(rv2), _ptr(nbt), _st())
+        assert rel(rm2, rm) < 1e-3 and rel(rv2, rv) < 2e-3 and int(nbt) == 1
+    else:
+        _call("cvad_bn_eval_prepare_f32", 32, 1e-5, _ptr(rm2), _ptr(rv2), _ptr(mean), _ptr(invstd), _st())
+    Ho, Wo = y.shape[2], y.shape[3]
+    y1 = torch.full((N, Ho, Wo, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w), _ptr(b), N, H, W, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), _ptr(y1), _st())
+    PH, PW = ref.shape[2], ref.shape[3]
+    a0 = torch.full((N, PH + 2, PW + 2, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, Ho, Wo, 32, _ptr(a0), _st())
+    torch.cuda.synchronize()
+    e = rel(a0.float(), tc.to_padded(ref).float())
+    print(f"[stem] N={N} {H}x{W} training={training}: rel err {e:.2e}")
+    assert e < 1e-2
