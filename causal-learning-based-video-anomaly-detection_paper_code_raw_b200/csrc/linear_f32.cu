@@ -17,7 +17,9 @@ template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(NT) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, long long lda,
                                                    const float* __restrict__ B, long long ldb, float* __restrict__ C, long long ldc,
                                                    const float* __restrict__ bias, int act, const float* __restrict__ mask,
-                                                   float mask_scale, int accumulate, int k_per_split, int atomic_out) {
+                                                   float mask_scale, int accumulate, int k_per_split, int atomic_out,
+                                                   const float* __restrict__ gate) {
+  if (gate && !(*gate > 0.f)) return;     // device-side "this branch received no gradient" switch
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -136,22 +138,34 @@ __global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
-// column sums over rows: out[j] (+)= sum_i x[i*ld + j]   (bias gradients)
-__global__ void colsum_kernel(const float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
-                              int accumulate) {
-  __shared__ float sh[32];
-  int j = blockIdx.x;
+// column sums over rows: out[j] (+)= sum_i x[i*ld + j]   (bias gradients).  One block = 32 columns x 8 row lanes; the 32
+// threads of a warp read 32 consecutive columns of one row (coalesced), row lanes are reduced through shared memory.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
+                                                     int accumulate) {
+  __shared__ float sh[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
+  const long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * chunk, r1 = r0 + chunk < rows ? r0 + chunk : rows;
   float s = 0.f;
-  for (long long i = threadIdx.x; i < rows; i += blockDim.x) s += x[i * ld + j];
-  s = block_sum(s, sh);
-  if (threadIdx.x == 0) out[j] = accumulate ? out[j] + s : s;
+  if (j < cols)
+    for (long long i = r0 + ry; i < r1; i += 8) s += x[i * ld + j];
+  sh[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && j < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cx];
+    if (gridDim.y > 1) atomicAdd(out + j, t);
+    else out[j] = accumulate ? out[j] + t : t;
+  }
 }
 
 }  // namespace
 
 CVAD_API int cvad_sgemm_f32(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb,
                             int b_kmajor, float* C, long long ldc, const float* bias, int act, const float* mask, float mask_scale,
-                            int accumulate, int splits, void* stream) {
+                            int accumulate, int splits, const float* gate, void* stream) {
   if (M <= 0 || N <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (splits < 1) splits = 1;
@@ -161,7 +175,7 @@ CVAD_API int cvad_sgemm_f32(int M, int N, int K, const float* A, long long lda, 
   if (splits < 1) splits = 1;
   int atomic_out = splits > 1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-#define GO(AK, BKM) sgemm_kernel<AK, BKM><<<grid, NT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, mask, mask_scale, accumulate, kps, atomic_out)
+#define GO(AK, BKM) sgemm_kernel<AK, BKM><<<grid, NT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, mask, mask_scale, accumulate, kps, atomic_out, gate)
   if (a_kmajor && b_kmajor) GO(true, true);
   else if (a_kmajor) GO(true, false);
   else if (b_kmajor) GO(false, true);
@@ -194,7 +208,16 @@ CVAD_API int cvad_act_mask_bwd_f32(const float* dy, const float* y, const float*
 
 CVAD_API int cvad_colsum_f32(const float* x, long long rows, int cols, long long ld, float* out, int accumulate, void* stream) {
   if (cols <= 0) return 0;
-  colsum_kernel<<<cols, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, out, accumulate);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int bx = (cols + 31) / 32;
+  int by = 1;
+  if (accumulate) {            // split long reductions over rows; partial sums are added atomically onto the running gradient
+    by = (int)((rows + 255) / 256);
+    const int cap = (2 * cvad_num_sms() + bx - 1) / bx;
+    if (by > cap) by = cap;
+    if (by < 1) by = 1;
+  }
+  colsum_kernel<<<dim3(bx, by), 256, 0, st>>>(x, rows, cols, ld, out, accumulate);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

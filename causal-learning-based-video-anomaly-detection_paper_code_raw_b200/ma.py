@@ -70,11 +70,11 @@ class ResNetBackbone(nn.Module):
         return h.reshape(B, T, -1)
 
 
-def _mlp(seq, idxs, x, acts, keeps=None, ps=None):
+def _mlp(seq, idxs, x, acts, keeps=None, ps=None, gate=None):
     h = x
     for i, (li, act) in enumerate(zip(idxs, acts)):
         keep = keeps[i] if keeps is not None else None
-        h = ops.linear_act(h, seq[li].weight, seq[li].bias, act, keep, ps[i] if keep is not None else 0.0)
+        h = ops.linear_act(h, seq[li].weight, seq[li].bias, act, keep, ps[i] if keep is not None else 0.0, gate)
     return h
 
 
@@ -100,8 +100,10 @@ class SimplePedestrianDetector(nn.Module):
         if training:
             keeps = [noise.keep_mask("det0", (B, T, 512), 0.3, features.device), noise.keep_mask("det1", (B, T, 256), 0.2, features.device),
                      None, None, None]
+        # flag: set on the device by det_decode when a real detection survives; otherwise the reference's detector output
+        # is the constant fallback box, its gradient is None and the backward GEMMs below switch themselves off
         raw = _mlp(self.detector_net, (0, 3, 6, 8, 10), features, (ACT_RELU, ACT_RELU, ACT_RELU, ACT_RELU, ACT_NONE), keeps,
-                   (0.3, 0.2, 0, 0, 0))
+                   (0.3, 0.2, 0, 0, 0), gate=flag)
         return ma_ops.det_decode(raw.view(B, T, 5, 4), flag)
 
 

@@ -155,23 +155,25 @@ def conv_act(x, weight, bias, stride=1, padding=0, act=ACT_NONE):
 
 
 # ------------------------------------------------------------------------------------------------ linear
-def _sgemm(M, N, K, A, lda, a_k, B, ldb, b_k, C, ldc, bias=None, act=ACT_NONE, mask=None, mask_scale=1.0, accumulate=0, splits=1):
+def _sgemm(M, N, K, A, lda, a_k, B, ldb, b_k, C, ldc, bias=None, act=ACT_NONE, mask=None, mask_scale=1.0, accumulate=0, splits=1, gate=None):
     _call("cvad_sgemm_f32", M, N, K, _ptr(A), lda, int(a_k), _ptr(B), ldb, int(b_k), _ptr(C), ldc, _ptr(bias), act, _ptr(mask),
-          float(mask_scale), int(accumulate), int(splits), _st())
+          float(mask_scale), int(accumulate), int(splits), _ptr(gate), _st())
 
 
 def _splits_for(M, N, K):
+    """Split the reduction over gridDim.z whenever the 64x64 output tiles alone cannot fill the 148 SMs."""
     tiles = ((M + 63) // 64) * ((N + 63) // 64)
-    if tiles >= 64 or K < 1024:
+    if tiles >= 148 or K < 128:
         return 1
-    return max(1, min(K // 256, 148 // tiles))
+    return max(1, min(K // 64, (2 * 148) // tiles))
 
 
 class _LinearAct(torch.autograd.Function):
-    """act(x @ W^T + b) * keep_mask / (1-p) over the last axis of x."""
+    """act(x @ W^T + b) * keep_mask / (1-p) over the last axis of x.  ``gate``: optional device scalar; when it is 0 at
+    backward time the layer's gradient GEMMs are skipped on the device and dx is exactly zero."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, act, mask, mask_scale):
+    def forward(ctx, x, weight, bias, act, mask, mask_scale, gate):
         _cuda(x, weight, bias, mask)
         shp = x.shape
         x2 = _f32c(x).reshape(-1, shp[-1])
@@ -189,7 +191,7 @@ class _LinearAct(torch.autograd.Function):
             y = torch.empty((M, O), device=x.device, dtype=torch.float32)
             _sgemm(M, O, K, x2, K, True, weight, K, True, y, O, bias, act, mask, mask_scale)
         ctx.meta = (act, mask_scale, shp)
-        ctx.weight, ctx.bias = weight, bias
+        ctx.weight, ctx.bias, ctx.gate = weight, bias, gate
         ctx.save_for_backward(x2, y if act != ACT_NONE else None, mask)
         return y.reshape(*shp[:-1], O)
 
@@ -197,7 +199,7 @@ class _LinearAct(torch.autograd.Function):
     def backward(ctx, dy):
         x2, y, mask = ctx.saved_tensors
         act, mask_scale, shp = ctx.meta
-        weight, bias = ctx.weight, ctx.bias
+        weight, bias, gate = ctx.weight, ctx.bias, ctx.gate
         M, K = x2.shape
         O = weight.shape[0]
         dz = _f32c(dy).reshape(M, O)
@@ -206,20 +208,24 @@ class _LinearAct(torch.autograd.Function):
             _call("cvad_act_mask_bwd_f32", _ptr(dz), _ptr(y), _ptr(mask), float(mask_scale), act, _ptr(out), dz.numel(), _st())
             dz = out
         if _wants_grad(weight):      # dW[o][i] += sum_m dz[m][o] x[m][i]
-            _sgemm(O, K, M, dz, O, False, x2, K, False, grad_buffer(weight), K, accumulate=1)
+            _sgemm(O, K, M, dz, O, False, x2, K, False, grad_buffer(weight), K, accumulate=1, splits=_splits_for(O, K, M), gate=gate)
         if _wants_grad(bias):
             _call("cvad_colsum_f32", _ptr(dz), M, O, O, _ptr(grad_buffer(bias)), 1, _st())
         dx = None
         if ctx.needs_input_grad[0]:  # dx[m][i] = sum_o dz[m][o] W[o][i]
-            dx = torch.empty((M, K), device=dz.device, dtype=torch.float32)
-            _sgemm(M, K, O, dz, O, True, weight, K, False, dx, K)
+            splits = _splits_for(M, K, O)
+            if splits > 1 or gate is not None:
+                dx = torch.zeros((M, K), device=dz.device, dtype=torch.float32)
+            else:
+                dx = torch.empty((M, K), device=dz.device, dtype=torch.float32)
+            _sgemm(M, K, O, dz, O, True, weight, K, False, dx, K, splits=splits, gate=gate)
             dx = dx.reshape(shp)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
-def linear_act(x, weight, bias, act=ACT_NONE, mask=None, p_drop=0.0):
+def linear_act(x, weight, bias, act=ACT_NONE, mask=None, p_drop=0.0, gate=None):
     scale = 1.0 / (1.0 - p_drop) if mask is not None else 1.0
-    return _LinearAct.apply(x, weight, bias, act, mask, scale)
+    return _LinearAct.apply(x, weight, bias, act, mask, scale, gate)
 
 
 # ------------------------------------------------------------------------------------------------ batch norm

@@ -56,10 +56,11 @@ int cvad_conv_wgrad_f32(const cvad_conv_desc* d, const float* x, const float* dy
 /* ---- fully connected layers (linear_f32.cu) ---------------------------------------------------------------------
  * C[i][j] (+)= sum_k A(i,k) B(k,j);  A(i,k)=A[i*lda+k] if a_kmajor else A[k*lda+i];  B(k,j)=B[j*ldb+k] if b_kmajor else B[k*ldb+j].
  * Epilogue: +bias[j], activation, *mask[i][j]*mask_scale (dropout keep-mask).  splits>1: split-K with atomic adds onto a
- * pre-zeroed C and no epilogue.  nn.Linear stacks: s2:24,43-48,77-89; mc3:60-69; cad:167-179,240-246,318-326,361-367,407-413,435-461,525-538. */
+ * pre-zeroed C and no epilogue.  gate (may be NULL): device scalar; the call does nothing unless *gate > 0 (a branch whose
+ * gradient is None in the reference, SURVEY fact 6, costs no GEMM time).  nn.Linear stacks: s2:24,43-48,77-89; mc3:60-69; cad:167-179,240-246,318-326,361-367,407-413,435-461,525-538. */
 int cvad_sgemm_f32(int M, int N, int K, const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor, float* C,
                    long long ldc, const float* bias, int act, const float* mask, float mask_scale, int accumulate, int splits,
-                   void* stream);
+                   const float* gate, void* stream);
 int cvad_bias_act_mask_f32(float* y, long long rows, int cols, const float* bias, int act, const float* mask, float mask_scale,
                            void* stream);
 /* dz = dy * mask*mask_scale * act'(y)  (y is the stored, post-mask output; NULL for ACT_NONE) */
