@@ -1,5 +1,5 @@
-// "Flat" tensor-core 3x3 convolution for the M-A backbone (cad:128-139, 150-153): forward and data-gradient as
-// TMA-fed tcgen05.mma GEMMs over a zero-bordered NHWC layout.
+// "Flat" tensor-core 3x3 convolution for the M-A backbone (cad:128-139, 150-153): forward, data-gradient and
+// weight-gradient as TMA-fed tcgen05.mma GEMMs over a zero-bordered NHWC layout.
 //
 // Layout in HBM.  An activation with logical shape (N,H,W,C) is stored as (N, H+2, W+2, C) bf16 with a zero border
 // ("padded-flat").  With q the flat pixel index of that buffer, a stride-1 3x3 convolution is a sum of nine row-shifted
@@ -10,16 +10,18 @@
 // sum: tap (kh,kw) reads plane (kh&1, kw&1) shifted by (kh>>1)*(Wo+2) + (kw>>1).  The data-gradients are the transposed
 // sums (negative shifts; one launch per phase plane for stride 2).
 //
-// Kernel.  Persistent, warp-specialised, one CTA per SM:
-//   warp 0 (one lane)  TMA producer: per K-unit (a 32/64-channel slab of one source plane) one activation segment of
-//                      128*SUB + halo rows, hardware-swizzled (SWIZZLE_64B / SWIZZLE_128B), double buffered; per tap one
-//                      [N x slab] weight tile through a 4-deep ring;
-//   warp 1 (one lane)  tcgen05.mma issuer: every tap is a ROW-SHIFTED VIEW of the resident segment (descriptor start
-//                      address + delta*row_bytes; the swizzle is a function of the absolute smem address, see
-//                      profiles/r01_umma_descriptor_probe.md), M=128 x N x K=16 MMAs into a ring of TMEM accumulators;
-//   warp 2             TMEM allocator;
-//   warps 4-7          epilogue: tcgen05.ld -> +bias -> bf16 -> global, overlapped with the next tile's MMAs.
-// So an activation element is fetched from L2/HBM ~1.1-1.4x (halo) instead of 9x, and no thread computes an address.
+// Forward / data-gradient kernel.  Persistent, warp-specialised, one CTA per SM:
+//   warp 0  TMA producer, activations: per K-unit (a 32/64-channel slab of one source plane) one segment of 128*SUB + halo
+//           rows, hardware-swizzled (SWIZZLE_64B / SWIZZLE_128B), double buffered;
+//   warp 2  TMA producer, weights: boxes of 256 packed rows (2-8 taps each) through a ring, or loaded once and kept
+//           resident when all taps fit; also owns the TMEM allocation;
+//   warp 1  tcgen05.mma issuer: every tap is a ROW-SHIFTED VIEW of the resident segment (descriptor start address +
+//           delta*row_bytes; the swizzle is a function of the absolute smem address, profiles/r01_umma_descriptor_probe.md),
+//           M=128 x N x K=16 MMAs into a ring of TMEM accumulators;
+//   warps 4-7  epilogue: tcgen05.ld -> +bias -> bf16 -> global, overlapped with the next tile's MMAs.
+// All role loops are warp-uniform and one elected lane issues, so descriptors live in uniform registers.  TMA boxes are as
+// large as the hardware allows (256 rows): a box costs ~700 cycles of TMA service however small it is
+// (profiles/r01_tma_box_probe.md).  An activation element is fetched from L2/HBM ~1.1-1.4x (halo) instead of 9x.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -31,38 +33,44 @@ namespace {
 using namespace cvad_tc;
 
 constexpr int FC_MAX_UNITS = 16;
-constexpr int FC_WST = 16;       // maximum weight-tile ring depth (the launch picks what fits)
-constexpr int FC_BOXR = 64;      // rows per activation TMA box
+constexpr int FC_WST_MAX = 8;        // maximum weight ring depth
+constexpr int FC_MAX_SLOTS = 16;     // TMEM accumulator ring
+constexpr int FC_BOX = 256;          // rows per big TMA box
+constexpr size_t FC_SMEM_BUDGET = 226 * 1024;
 
 struct FcUnit {
   int row_off;          // first segment row relative to the tile's first output row (may be negative)
   int col;              // first channel of the slab
   int ntaps;
-  int tap_delta[9];     // row shift of the tap inside the segment (>= 0)
-  int tap_wrow[9];      // first row of the tap's weight block in the packed weight matrix
+  int w_row0;           // first packed weight row of the unit's first tap (n-block 0); tap i follows at + i*N
+  int tap_delta[9];     // row shift of tap i inside the segment (>= 0)
 };
 
 struct FcParams {
   long long rows;        // output rows (flat pixels)
   long long out_row_base;
-  int n_units, seg_rows, sub, n_blocks, ld_out, wst;
+  int n_units, seg_rows, sub, n_blocks, ld_out, wst, w_resident;
+  int big_boxes, tail_rows;      // segment = big_boxes x 256 rows + one exact tail box (0 = none)
   FcUnit units[FC_MAX_UNITS];
 };
 
 template <int ROWB, int N>
-__global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_w,
-                                                          const FcParams p, const float* __restrict__ bias,
-                                                          __nv_bfloat16* __restrict__ out) {
-  constexpr int NSLOT = (512 / N) > 8 ? 8 : (512 / N);
+__global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
+                                                          const __grid_constant__ CUtensorMap map_w, const FcParams p,
+                                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
+  constexpr int NSLOT = (512 / N) > FC_MAX_SLOTS ? FC_MAX_SLOTS : (512 / N);
   constexpr uint32_t TMEM_COLS = NSLOT * N;
-  constexpr int W_BYTES = N * ROWB;
+  constexpr int TPO = FC_BOX / N;                  // taps per weight box
+  constexpr int WBOX_BYTES = FC_BOX * ROWB;
   constexpr int K16 = ROWB / 32;
   constexpr uint32_t SBO = ROWB * 8;
   constexpr int LAYOUT = ROWB == 128 ? UMMA_SW128 : UMMA_SW64;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_src_full[2], bar_src_empty[2], bar_w_full[FC_WST], bar_w_empty[FC_WST], bar_acc_full[8], bar_acc_empty[8];
+  __shared__ uint64_t bar_src_full[2], bar_src_empty[2], bar_w_full[FC_WST_MAX], bar_w_empty[FC_WST_MAX], bar_acc_full[FC_MAX_SLOTS],
+      bar_acc_empty[FC_MAX_SLOTS];
   __shared__ uint32_t tmem_base_sh;
+  __shared__ float s_bias[N];
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t seg_bytes = (uint32_t)p.seg_rows * ROWB;
@@ -70,17 +78,18 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
   const uint32_t s_w = smem_base + 2 * seg_bytes;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const int sub = p.sub, n_units = p.n_units, n_blocks = p.n_blocks, seg_rows = p.seg_rows, wst = p.wst;
+  const int sub = p.sub, n_units = p.n_units, n_blocks = p.n_blocks, wst = p.wst, resident = p.w_resident;
   const int MT = 128 * sub;
   const long long n_tiles = (p.rows + MT - 1) / MT;
   const long long total = n_tiles * n_blocks;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
-    for (int i = 0; i < FC_WST; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+    for (int i = 0; i < FC_WST_MAX; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
+    for (int i = 0; i < FC_MAX_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
     fence_barrier_init();
     prefetch_tmap(&map_src);
+    prefetch_tmap(&map_tail);
     prefetch_tmap(&map_w);
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_sh);
@@ -92,40 +101,44 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: activation segments
     uint32_t src_cnt = 0;
-    auto load_src = [&](long long q0, int u) {
-      const int st = src_cnt & 1;
-      mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&bar_src_full[st], seg_bytes);
-        const int r0 = (int)(q0 + p.units[u].row_off), col = p.units[u].col;
-        const uint32_t dst = s_src + st * seg_bytes;
-        for (int r = 0; r < seg_rows; r += FC_BOXR) tma_load_2d(dst + r * ROWB, &map_src, col, r0 + r, &bar_src_full[st]);
-      }
-      __syncwarp();
-      ++src_cnt;
-    };
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       const long long q0 = (wi / n_blocks) * MT;
-      for (int u = 0; u < n_units; ++u) load_src(q0, u);
+      for (int u = 0; u < n_units; ++u) {
+        const int st = src_cnt & 1;
+        mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&bar_src_full[st], seg_bytes);
+          const int r0 = (int)(q0 + p.units[u].row_off), col = p.units[u].col;
+          const uint32_t dst = s_src + st * seg_bytes;
+          for (int b = 0; b < p.big_boxes; ++b) tma_load_2d(dst + b * (FC_BOX * ROWB), &map_src, col, r0 + b * FC_BOX, &bar_src_full[st]);
+          if (p.tail_rows) tma_load_2d(dst + p.big_boxes * (FC_BOX * ROWB), &map_tail, col, r0 + p.big_boxes * FC_BOX, &bar_src_full[st]);
+        }
+        __syncwarp();
+        ++src_cnt;
+      }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ TMA producer: per-tap weight tiles
+    // ------------------------------------------------------------------ TMA producer: weight boxes (TPO taps each)
     uint32_t w_cnt = 0;
+    bool first_item = true;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       const int nb = (int)(wi % n_blocks);
+      if (resident && !first_item) break;
       for (int u = 0; u < n_units; ++u) {
         const int ntaps = p.units[u].ntaps, col = p.units[u].col;
-        for (int t = 0; t < ntaps; ++t) {
-          const int st = w_cnt % wst;
-          mbar_wait(&bar_w_empty[st], ((w_cnt / wst) & 1) ^ 1);
+        const int row0 = p.units[u].w_row0 + nb * 9 * N;
+        for (int c = 0; c * TPO < ntaps; ++c) {
+          const int st = resident ? c : (int)(w_cnt % wst);
+          if (!resident) mbar_wait(&bar_w_empty[st], ((w_cnt / wst) & 1) ^ 1);
           if (elect_one()) {
-            mbar_expect_tx(&bar_w_full[st], W_BYTES);
-            tma_load_2d(s_w + st * W_BYTES, &map_w, col, p.units[u].tap_wrow[t] + nb * N, &bar_w_full[st]);
+            mbar_expect_tx(&bar_w_full[st], WBOX_BYTES);
+            tma_load_2d(s_w + st * WBOX_BYTES, &map_w, col, row0 + c * FC_BOX, &bar_w_full[st]);
           }
           __syncwarp();
           ++w_cnt;
         }
       }
+      first_item = false;
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp walks the loops, one lane issues)
@@ -139,35 +152,41 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
         mbar_wait(&bar_src_full[st], (src_cnt >> 1) & 1);
         tc_fence_after();
         const uint32_t a_seg = s_src + st * seg_bytes;
-        for (int t = 0; t < ntaps; ++t) {
-          const int ws = w_cnt % wst;
-          mbar_wait(&bar_w_full[ws], (w_cnt / wst) & 1);
+        for (int c = 0; c * TPO < ntaps; ++c) {
+          const int ws = resident ? c : (int)(w_cnt % wst);
+          mbar_wait(&bar_w_full[ws], resident ? 0u : ((w_cnt / wst) & 1));
           tc_fence_after();
-          const uint32_t b_base = s_w + ws * W_BYTES;
-          const bool first = (u == 0 && t == 0);
-          const bool last = (u == n_units - 1 && t == ntaps - 1);
-          const uint32_t a_tap = a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB;
-          for (int s = 0; s < sub; ++s) {
-            const uint32_t use = acc_cnt + s;
-            const int slot = use % NSLOT;
-            if (first) {
-              mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-              const uint32_t a_base = a_tap + (uint32_t)s * 128 * ROWB;
-#pragma unroll
-              for (int k = 0; k < K16; ++k) {
-                const uint64_t da = desc_hi | (uint64_t)(((a_base + k * 32) >> 4) & 0x3FFF);
-                const uint64_t db = desc_hi | (uint64_t)(((b_base + k * 32) >> 4) & 0x3FFF);
-                tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+          const int tin = ntaps - c * TPO < TPO ? ntaps - c * TPO : TPO;
+          for (int j = 0; j < tin; ++j) {
+            const int t = c * TPO + j;
+            const uint32_t b_base = s_w + ws * WBOX_BYTES + j * (N * ROWB);
+            const bool first = (u == 0 && t == 0);
+            const bool last = (u == n_units - 1 && t == ntaps - 1);
+            const uint32_t a_tap = a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB;
+            for (int s = 0; s < sub; ++s) {
+              const uint32_t use = acc_cnt + s;
+              const int slot = use % NSLOT;
+              if (first) {
+                mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
+                tc_fence_after();
               }
-              if (last) tc_commit(&bar_acc_full[slot]);
+              if (elect_one()) {
+                const uint32_t a_base = a_tap + (uint32_t)s * 128 * ROWB;
+#pragma unroll
+                for (int k = 0; k < K16; ++k) {
+                  const uint64_t da = desc_hi | (uint64_t)(((a_base + k * 32) >> 4) & 0x3FFF);
+                  const uint64_t db = desc_hi | (uint64_t)(((b_base + k * 32) >> 4) & 0x3FFF);
+                  tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+                }
+                if (last) tc_commit(&bar_acc_full[slot]);
+              }
+              __syncwarp();
             }
+          }
+          if (!resident) {
+            if (elect_one()) tc_commit(&bar_w_empty[ws]);
             __syncwarp();
           }
-          if (elect_one()) tc_commit(&bar_w_empty[ws]);
-          __syncwarp();
           ++w_cnt;
         }
         if (elect_one()) tc_commit(&bar_src_empty[st]);
@@ -180,9 +199,16 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
     // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
     const int ew = warp - 4;
     uint32_t acc_cnt = 0;
+    int cur_nb = -1;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       const long long q0 = (wi / n_blocks) * MT;
       const int nb = (int)(wi % n_blocks);
+      if (nb != cur_nb) {                       // stage this n-block's bias once (epilogue warps only: named barrier 1)
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        for (int i = tid - 128; i < N; i += 128) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        cur_nb = nb;
+      }
       for (int s = 0; s < sub; ++s) {
         const uint32_t use = acc_cnt + s;
         const int slot = use % NSLOT;
@@ -200,8 +226,7 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
-              if (bias) { a += __ldg(bias + nb * N + c0 + 2 * i); b += __ldg(bias + nb * N + c0 + 2 * i + 1); }
+              const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
               pk[i] = *reinterpret_cast<uint32_t*>(&h);
             }
@@ -221,86 +246,114 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------- host side
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int n_block_of(int nout) { return nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32); }
+
 template <int ROWB, int N>
-int launch_flatconv(const CUtensorMap& ms, const CUtensorMap& mw, const FcParams& p, const float* bias, __nv_bfloat16* out, cudaStream_t st) {
-  // weight ring: as deep as shared memory allows (>= 2), so a tap's tile is in flight long before its MMAs issue
+int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk, long long w_rows, FcParams& p, const float* bias,
+                    __nv_bfloat16* out, cudaStream_t st) {
+  constexpr int TPO = FC_BOX / N;
+  int max_delta = 0, max_chunks = 0;
+  for (int u = 0; u < p.n_units; ++u) {
+    for (int t = 0; t < p.units[u].ntaps; ++t) max_delta = p.units[u].tap_delta[t] > max_delta ? p.units[u].tap_delta[t] : max_delta;
+    const int ch = (p.units[u].ntaps + TPO - 1) / TPO;
+    max_chunks = ch > max_chunks ? ch : max_chunks;
+  }
+  // rows per work item: as many 128-row sub-tiles as TMEM and shared memory allow while the machine stays filled
+  static const int cand[] = {8, 6, 4, 3, 2, 1};
+  const int sub_max = N == 32 ? 8 : 4;
+  p.sub = 0;
+  for (int sub : cand) {
+    if (sub > sub_max) continue;
+    const long long items = ((p.rows + 128LL * sub - 1) / (128LL * sub)) * p.n_blocks;
+    if (sub > 1 && items < (3LL * cvad_num_sms()) / 2) continue;
+    const int seg = round_up(128 * sub + max_delta, 64);
+    if (2 * (size_t)seg * ROWB + 1024 + 2 * (size_t)FC_BOX * ROWB > FC_SMEM_BUDGET) continue;
+    p.sub = sub;
+    p.seg_rows = seg;
+    break;
+  }
+  if (!p.sub) return (int)cudaErrorInvalidValue;
   const size_t fixed = 2 * (size_t)p.seg_rows * ROWB + 1024;
-  if (fixed + 2 * (size_t)N * ROWB > 226 * 1024) return (int)cudaErrorInvalidValue;
-  long long wst = (long long)((226 * 1024 - fixed) / ((size_t)N * ROWB));
-  FcParams pp = p;
-  pp.wst = (int)(wst > FC_WST ? FC_WST : wst);
-  const size_t smem = fixed + (size_t)pp.wst * N * ROWB;
+  long long wst = (long long)((FC_SMEM_BUDGET - fixed) / ((size_t)FC_BOX * ROWB));
+  p.wst = (int)(wst > FC_WST_MAX ? FC_WST_MAX : wst);
+  p.w_resident = (p.n_units == 1 && p.n_blocks == 1 && max_chunks <= p.wst) ? 1 : 0;
+  p.big_boxes = p.seg_rows / FC_BOX;
+  p.tail_rows = p.seg_rows % FC_BOX;
+  const size_t smem = fixed + (size_t)p.wst * FC_BOX * ROWB;
+  CUtensorMap ms, mt, mw;
+  int e = make_tmap_2d(&ms, src, src_rows, K, FC_BOX, ROWB / 2, ROWB);
+  if (e) return e;
+  e = make_tmap_2d(&mt, src, src_rows, K, p.tail_rows ? p.tail_rows : 64, ROWB / 2, ROWB);
+  if (e) return e;
+  e = make_tmap_2d(&mw, wpk, w_rows, K, FC_BOX, ROWB / 2, ROWB);
+  if (e) return e;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(flatconv_kernel<ROWB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    cudaError_t ce = cudaFuncSetAttribute(flatconv_kernel<ROWB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return (int)ce;
     configured = smem;
   }
   const long long MT = 128LL * p.sub;
   const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
-  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mw, pp, bias, out);
+  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mt, mw, p, bias, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
-int dispatch_flatconv(int rowb, int n, const CUtensorMap& ms, const CUtensorMap& mw, const FcParams& p, const float* bias, __nv_bfloat16* out,
-                      cudaStream_t st) {
-  if (rowb == 64) {
-    if (n == 32) return launch_flatconv<64, 32>(ms, mw, p, bias, out, st);
-    if (n == 64) return launch_flatconv<64, 64>(ms, mw, p, bias, out, st);
-    if (n == 128) return launch_flatconv<64, 128>(ms, mw, p, bias, out, st);
-  } else {
-    if (n == 32) return launch_flatconv<128, 32>(ms, mw, p, bias, out, st);
-    if (n == 64) return launch_flatconv<128, 64>(ms, mw, p, bias, out, st);
-    if (n == 128) return launch_flatconv<128, 128>(ms, mw, p, bias, out, st);
-  }
-  return (int)cudaErrorInvalidValue;
-}
-
-inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-
-// Common driver: `K` reduction channels (the gathered tensor's channel count), `Nout` output channels.
-// src_rows: rows of the gathered buffer (all planes); w_rows: rows of the packed weight matrix (9 * Nout).
-int run_flat(const void* src, long long src_rows, int K, const void* wpk, int Nout, const float* bias, void* out, FcParams& p,
-             cudaStream_t st) {
+// `K` reduction channels (the gathered tensor's channel count), `Nout` output channels.
+int run_flat(const void* src, long long src_rows, int K, const void* wpk, int Nout, const float* bias, void* out, FcParams& p, cudaStream_t st) {
   if (K % 32 || Nout % 32) return (int)cudaErrorInvalidValue;
-  const int rowb = K >= 64 ? 128 : 64;
   if (K >= 64 && K % 64) return (int)cudaErrorInvalidValue;
-  const int n = Nout % 128 == 0 ? 128 : (Nout % 64 == 0 ? 64 : 32);
+  const int rowb = K >= 64 ? 128 : 64;
+  const int n = n_block_of(Nout);
   p.n_blocks = Nout / n;
   p.ld_out = Nout;
-  // fewer sub-tiles per work item when the problem would not fill the machine
-  p.sub = 4;
-  while (p.sub > 1 && ((p.rows + 128LL * p.sub - 1) / (128LL * p.sub)) * p.n_blocks < 2LL * cvad_num_sms()) p.sub >>= 1;
-  int max_delta = 0;
-  for (int u = 0; u < p.n_units; ++u)
-    for (int t = 0; t < p.units[u].ntaps; ++t) max_delta = p.units[u].tap_delta[t] > max_delta ? p.units[u].tap_delta[t] : max_delta;
-  p.seg_rows = round_up(128 * p.sub + max_delta, FC_BOXR);
-  CUtensorMap ms, mw;
-  int e = make_tmap_2d(&ms, src, src_rows, K, FC_BOXR, rowb / 2, rowb);
-  if (e) return e;
-  e = make_tmap_2d(&mw, wpk, 9LL * Nout, K, n, rowb / 2, rowb);
-  if (e) return e;
-  return dispatch_flatconv(rowb, n, ms, mw, p, bias, (__nv_bfloat16*)out, st);
+  const long long w_rows = 9LL * Nout;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  if (rowb == 64) {
+    if (n == 32) return launch_flatconv<64, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+    if (n == 64) return launch_flatconv<64, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+    return launch_flatconv<64, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+  }
+  if (n == 32) return launch_flatconv<128, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+  if (n == 64) return launch_flatconv<128, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+  return launch_flatconv<128, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
 }
 
-// OIHW fp32 (Co, Ci, 3, 3) -> fwd [tap][Co][Ci] bf16 and dgrad [tap][Ci][Co] bf16
-__global__ void pack_w3x3_flat_kernel(const float* __restrict__ w, int Co, int Ci, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+// packed tap order: stride 1 natural; stride 2 grouped by phase plane (kh&1, kw&1) so every unit's taps are contiguous rows
+__host__ __device__ inline int packed_tap(int stride, int i) {
+  const int s2[9] = {0, 2, 6, 8, 1, 7, 3, 5, 4};
+  return stride == 2 ? s2[i] : i;
+}
+// index of the first packed tap of phase plane pl and the number of taps in it (stride 2)
+inline void plane_taps(int pl, int& first, int& count) {
+  static const int f[4] = {0, 4, 6, 8}, c[4] = {4, 2, 2, 1};
+  first = f[pl];
+  count = c[pl];
+}
+
+// OIHW fp32 (Co, Ci, 3, 3) -> fwd [n-block][packed tap][N][Ci] bf16 (N = block of Co) and dgrad [n-block][packed tap][Nd][Co] (Nd = block of Ci)
+__global__ void pack_w3x3_flat_kernel(const float* __restrict__ w, int Co, int Ci, int stride, int nf, int nd, __nv_bfloat16* __restrict__ wf,
+                                      __nv_bfloat16* __restrict__ wd) {
   const int total = Co * Ci * 9;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
-    const __nv_bfloat16 v = __float2bfloat16(w[i]);
-    if (wf) wf[((long long)tap * Co + co) * Ci + ci] = v;
-    if (wd) wd[((long long)tap * Ci + ci) * Co + co] = v;
+    const int ti = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+    const int tap = packed_tap(stride, ti);
+    const __nv_bfloat16 v = __float2bfloat16(w[((long long)co * Ci + ci) * 9 + tap]);
+    if (wf) wf[((long long)((co / nf) * 9 + ti) * nf + (co % nf)) * Ci + ci] = v;
+    if (wd) wd[((long long)((ci / nd) * 9 + ti) * nd + (ci % nd)) * Co + co] = v;
   }
 }
 
 }  // namespace
 
-CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, void* w_fwd, void* w_dgrad, void* stream) {
+CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int stride, void* w_fwd, void* w_dgrad, void* stream) {
+  if (Cout % 32 || Cin % 32 || (stride != 1 && stride != 2)) return (int)cudaErrorInvalidValue;
   int total = Cout * Cin * 9;
-  pack_w3x3_flat_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
+  pack_w3x3_flat_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, stride, n_block_of(Cout), n_block_of(Cin),
+                                                                               (__nv_bfloat16*)w_fwd, (__nv_bfloat16*)w_dgrad);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -310,9 +363,9 @@ CVAD_API int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const 
   if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
   const int slab = Cin >= 64 ? 64 : 32;
   const int nslab = Cin / slab;
+  const int nblk = n_block_of(Cout);
   FcParams p;
   memset(&p, 0, sizeof(p));
-  p.out_row_base = 0;
   long long src_rows;
   if (stride == 1) {
     const int Wp = W + 2;
@@ -325,30 +378,28 @@ CVAD_API int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const 
       u.row_off = -(Wp + 1);
       u.col = s * slab;
       u.ntaps = 9;
-      for (int t = 0; t < 9; ++t) { u.tap_delta[t] = (t / 3) * Wp + (t % 3); u.tap_wrow[t] = t * Cout; }
+      u.w_row0 = 0;
+      for (int t = 0; t < 9; ++t) u.tap_delta[t] = (t / 3) * Wp + (t % 3);
     }
   } else {
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
     p.rows = (long long)N * (Ho + 2) * Wq;
     src_rows = 4 * p.rows;
-    if (4 * nslab > FC_MAX_UNITS) return (int)cudaErrorInvalidValue;
+    if (4 * nslab > FC_MAX_UNITS || 3 * p.rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
     p.n_units = 4 * nslab;
     for (int pl = 0; pl < 4; ++pl)
       for (int s = 0; s < nslab; ++s) {
         FcUnit& u = p.units[pl * nslab + s];
-        const int a = pl >> 1, b = pl & 1;
-        u.row_off = 0;                      // plane offset does not fit an int: folded into tap_delta-free base below
-        u.col = s * slab;
-        u.ntaps = 0;
-        for (int t = 0; t < 9; ++t) {
-          const int kh = t / 3, kw = t % 3;
-          if ((kh & 1) != a || (kw & 1) != b) continue;
-          u.tap_delta[u.ntaps] = (kh >> 1) * Wq + (kw >> 1);
-          u.tap_wrow[u.ntaps] = t * Cout;
-          ++u.ntaps;
-        }
-        if (pl * p.rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
+        int first, count;
+        plane_taps(pl, first, count);
         u.row_off = (int)(pl * p.rows);
+        u.col = s * slab;
+        u.ntaps = count;
+        u.w_row0 = first * nblk;
+        for (int i = 0; i < count; ++i) {
+          const int t = packed_tap(2, first + i), kh = t / 3, kw = t % 3;
+          u.tap_delta[i] = (kh >> 1) * Wq + (kw >> 1);
+        }
       }
   }
   return run_flat(x, src_rows, Cin, w_fwd, Cout, bias, y, p, (cudaStream_t)stream);
@@ -361,6 +412,7 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
   if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
   const int slab = Cout >= 64 ? 64 : 32;
   const int nslab = Cout / slab;
+  const int nblk = n_block_of(Cin);
   if (nslab > FC_MAX_UNITS) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   if (stride == 1) {
@@ -374,30 +426,30 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
       u.row_off = -(Wp + 1);
       u.col = s * slab;
       u.ntaps = 9;
-      for (int t = 0; t < 9; ++t) { u.tap_delta[t] = (2 - t / 3) * Wp + (2 - t % 3); u.tap_wrow[t] = t * Cin; }
+      u.w_row0 = 0;
+      for (int t = 0; t < 9; ++t) u.tap_delta[t] = (2 - t / 3) * Wp + (2 - t % 3);
     }
     return run_flat(dy, p.rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
   const long long rows = (long long)N * (Ho + 2) * Wq;
   for (int pl = 0; pl < 4; ++pl) {
-    const int a = pl >> 1, b = pl & 1;
     FcParams p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
     p.out_row_base = pl * rows;
     p.n_units = nslab;
+    int first, count;
+    plane_taps(pl, first, count);
     for (int s = 0; s < nslab; ++s) {
       FcUnit& u = p.units[s];
       u.row_off = -(Wq + 1);
       u.col = s * slab;
-      u.ntaps = 0;
-      for (int t = 0; t < 9; ++t) {
-        const int kh = t / 3, kw = t % 3;
-        if ((kh & 1) != a || (kw & 1) != b) continue;
-        u.tap_delta[u.ntaps] = (Wq + 1) - ((kh >> 1) * Wq + (kw >> 1));
-        u.tap_wrow[u.ntaps] = t * Cin;
-        ++u.ntaps;
+      u.ntaps = count;
+      u.w_row0 = first * nblk;
+      for (int i = 0; i < count; ++i) {
+        const int t = packed_tap(2, first + i), kh = t / 3, kw = t % 3;
+        u.tap_delta[i] = (Wq + 1) - ((kh >> 1) * Wq + (kw >> 1));
       }
     }
     int e = run_flat(dy, rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
@@ -414,29 +466,34 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
 //                covers up to four (two) taps of a kernel row; with >= 128 channels the atoms are two channel slabs.
 //   B (N = NB):  the dy tile.
 // One accumulator [128 x NB] per tap group lives in TMEM for the CTA's whole pixel range; the epilogue adds it atomically
-// into the OIHW fp32 gradient (a slice of the flat gradient arena).
+// into the OIHW fp32 gradient (a slice of the flat gradient arena).  A launch covers all tap groups (blockIdx.z = "variant":
+// kernel row for wide layers, phase plane for stride 2) with ONE wave of CTAs, so the number of pixel chunks -- and with it
+// the number of atomics, chunks x |dW| -- stays minimal.
 namespace {
 
-constexpr int WG_BOXR_A = 32;
-constexpr int WG_BOXR_B = 64;
 constexpr int WG_MAX_STAGES = 4;
 
 struct WgGroup {
   int seg, delta;
   int tap[4];            // tap index of each M atom (pixel shift j), -1 = unused lanes
 };
-struct WgParams {
-  long long rows;        // flat pixels
-  long long pix_per_cta; // multiple of qs
-  int n_seg, n_groups, seg_rows, qs, n_stages;
-  int Cin, Cout, ci_blocks, co_blocks;
+struct WgVariant {
+  int n_seg, n_groups;
   int seg_row_off[4];
   WgGroup groups[9];
 };
+struct WgParams {
+  long long rows;        // flat pixels
+  long long pix_per_cta; // multiple of qs
+  int seg_rows, qs, n_stages, n_variants;
+  int Cin, Cout, ci_blocks, co_blocks;
+  int a_big, a_tail, b_box, max_seg;
+  WgVariant v[4];
+};
 
 template <int ROWB_A, int ROWB_B, int NB, int A_SLABS>
-__global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                           const WgParams p, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_at,
+                                                           const __grid_constant__ CUtensorMap map_b, const WgParams p, float* __restrict__ dw) {
   constexpr int B_SLABS = (NB * 2 + ROWB_B - 1) / ROWB_B;
   constexpr int LAY_A = ROWB_A == 128 ? UMMA_SW128 : UMMA_SW64;
   constexpr int LAY_B = ROWB_B == 128 ? UMMA_SW128 : UMMA_SW64;
@@ -446,11 +503,14 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[WG_MAX_STAGES], bar_empty[WG_MAX_STAGES], bar_done;
   __shared__ uint32_t tmem_base_sh;
+  const WgVariant& var = p.v[blockIdx.z];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t seg1 = (uint32_t)p.seg_rows * ROWB_A;            // one slab of one segment
-  const uint32_t a_bytes = (uint32_t)p.n_seg * A_SLABS * seg1;
+  const uint32_t a_bytes = (uint32_t)var.n_seg * A_SLABS * seg1;
+  const uint32_t a_bytes_max = (uint32_t)p.max_seg * A_SLABS * seg1;
   const uint32_t b1 = (uint32_t)p.qs * ROWB_B;
-  const uint32_t stage_bytes = a_bytes + B_SLABS * b1;
+  const uint32_t stage_bytes = a_bytes_max + B_SLABS * b1;
+  const uint32_t tx_bytes = a_bytes + B_SLABS * b1;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int qs = p.qs, n_stages = p.n_stages;
@@ -465,6 +525,7 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
     mbar_init(&bar_done, 1);
     fence_barrier_init();
     prefetch_tmap(&map_a);
+    prefetch_tmap(&map_at);
     prefetch_tmap(&map_b);
   }
   if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
@@ -478,18 +539,19 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
       const int st = it % n_stages;
       mbar_wait(&bar_empty[st], ((it / n_stages) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&bar_full[st], stage_bytes);
+        mbar_expect_tx(&bar_full[st], tx_bytes);
         const long long q = p_begin + (long long)it * qs;
         const uint32_t base = smem_base + st * stage_bytes;
-        for (int sg = 0; sg < p.n_seg; ++sg)
+        for (int sg = 0; sg < var.n_seg; ++sg)
           for (int sl = 0; sl < A_SLABS; ++sl) {
             const uint32_t dst = base + (sg * A_SLABS + sl) * seg1;
-            const int r0 = (int)(q + p.seg_row_off[sg]);
-            for (int r = 0; r < p.seg_rows; r += WG_BOXR_A) tma_load_2d(dst + r * ROWB_A, &map_a, cib * CI_BLK + sl * 64, r0 + r, &bar_full[st]);
+            const int r0 = (int)(q + var.seg_row_off[sg]), col = cib * CI_BLK + sl * 64;
+            for (int b = 0; b < p.a_big; ++b) tma_load_2d(dst + b * (FC_BOX * ROWB_A), &map_a, col, r0 + b * FC_BOX, &bar_full[st]);
+            if (p.a_tail) tma_load_2d(dst + p.a_big * (FC_BOX * ROWB_A), &map_at, col, r0 + p.a_big * FC_BOX, &bar_full[st]);
           }
         for (int sl = 0; sl < B_SLABS; ++sl) {
-          const uint32_t dst = base + a_bytes + sl * b1;
-          for (int r = 0; r < qs; r += WG_BOXR_B) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
+          const uint32_t dst = base + a_bytes_max + sl * b1;
+          for (int r = 0; r < qs; r += p.b_box) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
         }
       }
       __syncwarp();
@@ -499,7 +561,7 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
     const uint32_t lbo_a = A_SLABS == 2 ? seg1 : ROWB_A;
     const uint64_t da_hi = make_smem_desc(0, lbo_a, 8 * ROWB_A, LAY_A);
     const uint64_t db_hi = make_smem_desc(0, b1, 8 * ROWB_B, LAY_B);
-    const int n_groups = p.n_groups;
+    const int n_groups = var.n_groups;
     const int ksteps = qs / 16;
     for (int it = 0; it < n_iter; ++it) {
       const int st = it % n_stages;
@@ -508,11 +570,11 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
       const uint32_t base = smem_base + st * stage_bytes;
       if (elect_one()) {
         for (int g = 0; g < n_groups; ++g) {
-          const uint32_t a0 = base + p.groups[g].seg * A_SLABS * seg1 + (uint32_t)p.groups[g].delta * ROWB_A;
+          const uint32_t a0 = base + var.groups[g].seg * A_SLABS * seg1 + (uint32_t)var.groups[g].delta * ROWB_A;
           const uint32_t tacc = tmem_base + g * NB;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = da_hi | (uint64_t)(((a0 + k * 16 * ROWB_A) >> 4) & 0x3FFF);
-            const uint64_t db = db_hi | (uint64_t)(((base + a_bytes + k * 16 * ROWB_B) >> 4) & 0x3FFF);
+            const uint64_t db = db_hi | (uint64_t)(((base + a_bytes_max + k * 16 * ROWB_B) >> 4) & 0x3FFF);
             tc_mma_bf16(tacc, da, db, idesc, (it | k) != 0);
           }
         }
@@ -532,8 +594,8 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
     const int j = m / AW;
     const int ci = cib * CI_BLK + (m % AW);
     const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
-    for (int g = 0; g < p.n_groups; ++g) {
-      const int tap = p.groups[g].tap[j];
+    for (int g = 0; g < var.n_groups; ++g) {
+      const int tap = var.groups[g].tap[j];
 #pragma unroll
       for (int c0 = 0; c0 < NB; c0 += 16) {
         if ((((c0 >> 4) + g) & 1) != half) continue;
@@ -562,32 +624,42 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
   p.ci_blocks = (p.Cin + CI_BLK - 1) / CI_BLK;
   p.co_blocks = p.Cout / NB;
   int max_delta = 0;
-  for (int g = 0; g < p.n_groups; ++g) max_delta = p.groups[g].delta > max_delta ? p.groups[g].delta : max_delta;
+  p.max_seg = 0;
+  for (int v = 0; v < p.n_variants; ++v) {
+    if (p.v[v].n_groups * NB > 512) return (int)cudaErrorInvalidValue;
+    p.max_seg = p.v[v].n_seg > p.max_seg ? p.v[v].n_seg : p.max_seg;
+    for (int g = 0; g < p.v[v].n_groups; ++g) max_delta = p.v[v].groups[g].delta > max_delta ? p.v[v].groups[g].delta : max_delta;
+  }
   const int shifts = A_SLABS == 2 ? 0 : (128 / CI_BLK - 1);   // extra rows touched by the pixel-shift atoms
   // stage size: largest qs in {512, 256, 128, 64} that leaves room for >= 2 stages
   int qs = 512;
   size_t stage = 0;
   for (;; qs >>= 1) {
-    p.seg_rows = round_up(qs + max_delta + shifts, WG_BOXR_A);
-    stage = (size_t)p.n_seg * A_SLABS * p.seg_rows * ROWB_A + (size_t)B_SLABS * qs * ROWB_B;
-    if (2 * stage + 1024 <= 227 * 1024 || qs == 64) break;
+    p.seg_rows = round_up(qs + max_delta + shifts, 32);
+    stage = (size_t)p.max_seg * A_SLABS * p.seg_rows * ROWB_A + (size_t)B_SLABS * qs * ROWB_B;
+    if (2 * stage + 1024 <= FC_SMEM_BUDGET || qs == 64) break;
   }
-  if (2 * stage + 1024 > 227 * 1024) return (int)cudaErrorInvalidValue;
+  if (2 * stage + 1024 > FC_SMEM_BUDGET) return (int)cudaErrorInvalidValue;
   p.qs = qs;
-  p.n_stages = (int)((227 * 1024 - 1024) / stage);
+  p.n_stages = (int)((FC_SMEM_BUDGET - 1024) / stage);
   if (p.n_stages > WG_MAX_STAGES) p.n_stages = WG_MAX_STAGES;
+  p.a_big = p.seg_rows / FC_BOX;
+  p.a_tail = p.seg_rows % FC_BOX;
+  p.b_box = qs < FC_BOX ? qs : FC_BOX;
   const size_t smem = p.n_stages * stage + 1024;
-  const int yblocks = p.ci_blocks * p.co_blocks;
-  long long chunks = (2LL * cvad_num_sms() + yblocks - 1) / yblocks;
+  const int yz = p.ci_blocks * p.co_blocks * p.n_variants;
+  long long chunks = cvad_num_sms() / yz;                         // one wave of CTAs
   const long long max_chunks = (p.rows + qs - 1) / qs;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
   p.pix_per_cta = ((p.rows + chunks - 1) / chunks + qs - 1) / qs * qs;
   chunks = (p.rows + p.pix_per_cta - 1) / p.pix_per_cta;
-  CUtensorMap ma, mb;
-  int e = make_tmap_2d(&ma, src, src_rows, p.Cin, WG_BOXR_A, ROWB_A / 2, ROWB_A);
+  CUtensorMap ma, mat, mb;
+  int e = make_tmap_2d(&ma, src, src_rows, p.Cin, FC_BOX, ROWB_A / 2, ROWB_A);
   if (e) return e;
-  e = make_tmap_2d(&mb, dy, p.rows, p.Cout, WG_BOXR_B, ROWB_B / 2, ROWB_B);
+  e = make_tmap_2d(&mat, src, src_rows, p.Cin, p.a_tail ? p.a_tail : 32, ROWB_A / 2, ROWB_A);
+  if (e) return e;
+  e = make_tmap_2d(&mb, dy, p.rows, p.Cout, p.b_box, ROWB_B / 2, ROWB_B);
   if (e) return e;
   static size_t configured = 0;
   if (smem > configured) {
@@ -595,7 +667,7 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
     if (ce != cudaSuccess) return (int)ce;
     configured = smem;
   }
-  flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS><<<dim3((unsigned)chunks, yblocks), 256, smem, st>>>(ma, mb, p, dw);
+  flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS><<<dim3((unsigned)chunks, p.ci_blocks * p.co_blocks, p.n_variants), 256, smem, st>>>(ma, mat, mb, p, dw);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -616,54 +688,47 @@ CVAD_API int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* 
   cudaStream_t st = (cudaStream_t)stream;
   const int apm = Cin == 32 ? 4 : (Cin == 64 ? 2 : 1);     // taps one MMA can cover through pixel-shift atoms
   WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.Cin = Cin; p.Cout = Cout;
   if (stride == 1) {
     const int Wp = W + 2;
-    const long long rows = (long long)N * (H + 2) * Wp;
-    // big layers: one launch per kernel row keeps 3 accumulators of 128 columns in TMEM; small layers: all nine taps at once
-    const int launches = apm == 1 ? 3 : 1;
-    for (int l = 0; l < launches; ++l) {
-      memset(&p, 0, sizeof(p));
-      p.rows = rows; p.Cin = Cin; p.Cout = Cout;
-      p.n_seg = 1;
+    p.rows = (long long)N * (H + 2) * Wp;
+    // wide layers: one variant per kernel row keeps 3 accumulators of 128 columns in TMEM; narrow layers: all nine taps at once
+    p.n_variants = apm == 1 ? 3 : 1;
+    for (int l = 0; l < p.n_variants; ++l) {
+      WgVariant& v = p.v[l];
+      v.n_seg = 1;
       const int kh0 = apm == 1 ? l : 0, kh1 = apm == 1 ? l + 1 : 3;
-      p.seg_row_off[0] = (kh0 - 1) * Wp - 1;
+      v.seg_row_off[0] = (kh0 - 1) * Wp - 1;
       for (int kh = kh0; kh < kh1; ++kh)
         for (int kw = 0; kw < 3; kw += apm) {
-          WgGroup& g = p.groups[p.n_groups++];
+          WgGroup& g = v.groups[v.n_groups++];
           g.seg = 0;
           g.delta = (kh - kh0) * Wp + kw;
           for (int j = 0; j < 4; ++j) g.tap[j] = (j < apm && kw + j < 3) ? kh * 3 + kw + j : -1;
         }
-      int e = dispatch_wgrad(x, rows, dy, p, dw, st);
-      if (e) return e;
     }
-    return 0;
+    return dispatch_wgrad(x, p.rows, dy, p, dw, st);
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
-  const long long rows = (long long)N * (Ho + 2) * Wq;
-  if (3 * rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
-  // per phase plane (a,b): taps with (kh&1, kw&1) = (a,b), shift (kh>>1)*Wq + (kw>>1)
-  const int launches = apm == 1 ? 4 : 1;
-  for (int l = 0; l < launches; ++l) {
-    memset(&p, 0, sizeof(p));
-    p.rows = rows; p.Cin = Cin; p.Cout = Cout;
-    for (int pl = 0; pl < 4; ++pl) {
-      if (apm == 1 && pl != l) continue;
-      const int a = pl >> 1, b = pl & 1;
-      const int sg = p.n_seg++;
-      p.seg_row_off[sg] = (int)(pl * rows);
-      for (int kh = a; kh < 3; kh += 2)
-        for (int kw = b; kw < 3; kw += 2 * (apm > 1 ? 2 : 1)) {
-          WgGroup& g = p.groups[p.n_groups++];
-          g.seg = sg;
-          g.delta = (kh >> 1) * Wq + (kw >> 1);
-          for (int j = 0; j < 4; ++j) g.tap[j] = -1;
-          g.tap[0] = kh * 3 + kw;
-          if (apm > 1 && kw + 2 < 3) g.tap[1] = kh * 3 + kw + 2;      // the next same-parity tap is one plane pixel further
-        }
-    }
-    int e = dispatch_wgrad(x, 4 * rows, dy, p, dw, st);
-    if (e) return e;
+  p.rows = (long long)N * (Ho + 2) * Wq;
+  if (3 * p.rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
+  // per phase plane (a,b): taps with (kh&1, kw&1) = (a,b), shift (kh>>1)*Wq + (kw>>1); wide layers: one variant per plane
+  p.n_variants = apm == 1 ? 4 : 1;
+  for (int pl = 0; pl < 4; ++pl) {
+    WgVariant& v = p.v[apm == 1 ? pl : 0];
+    const int a = pl >> 1, b = pl & 1;
+    const int sg = v.n_seg++;
+    v.seg_row_off[sg] = (int)(pl * p.rows);
+    for (int kh = a; kh < 3; kh += 2)
+      for (int kw = b; kw < 3; kw += 2 * (apm > 1 ? 2 : 1)) {
+        WgGroup& g = v.groups[v.n_groups++];
+        g.seg = sg;
+        g.delta = (kh >> 1) * Wq + (kw >> 1);
+        for (int j = 0; j < 4; ++j) g.tap[j] = -1;
+        g.tap[0] = kh * 3 + kw;
+        if (apm > 1 && kw + 2 < 3) g.tap[1] = kh * 3 + kw + 2;      // the next same-parity tap is one plane pixel further
+      }
   }
-  return 0;
+  return dispatch_wgrad(x, 4 * p.rows, dy, p, dw, st);
 }

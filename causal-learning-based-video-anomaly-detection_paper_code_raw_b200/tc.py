@@ -83,7 +83,7 @@ class _BackboneBF16(torch.autograd.Function):
             cout, stride = conv.out_channels, strides[i]
             wf = torch.empty((9 * cout, cin), device=dev, dtype=BF16)
             wd = torch.empty((9 * cin, cout), device=dev, dtype=BF16) if need_bwd and i > 0 else None
-            _call("cvad_flat_pack_w3x3_bf16", _ptr(conv.weight), cout, cin, _ptr(wf), _ptr(wd), st)
+            _call("cvad_flat_pack_w3x3_bf16", _ptr(conv.weight), cout, cin, stride, _ptr(wf), _ptr(wd), st)
             ho, wo = out_hw(h, w, stride)
             raw = torch.empty((N, ho + 2, wo + 2, cout), device=dev, dtype=BF16)
             _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)

@@ -196,8 +196,10 @@ int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, int C, in
  * an activation (N,H,W,C) is stored "padded-flat" as (N,H+2,W+2,C) bf16; the input of a stride-2 convolution is stored as
  * four phase planes P_ab[n][i][j] = padded(2(i-1)+a, 2(j-1)+b), each in the geometry (N,Ho+2,Wo+2,C) of that convolution's
  * output, plane index a*2+b outermost.  Convolution outputs / data-gradients carry junk in their border rows. */
-/* OIHW fp32 -> w_fwd [tap][Cout][Cin] bf16, w_dgrad [tap][Cin][Cout] bf16 (either may be NULL) */
-int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, void* w_fwd, void* w_dgrad, void* stream);
+/* OIHW fp32 -> w_fwd [n-block][packed tap][N][Cin] bf16 (N = 128/64/32-channel block of Cout), w_dgrad likewise with the roles of
+ * Cin and Cout swapped; either may be NULL.  Taps are packed in natural order for stride 1 and grouped by phase plane for stride 2,
+ * so the taps one TMA box fetches are contiguous rows.  Both buffers hold 9*Cout*Cin elements. */
+int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int stride, void* w_fwd, void* w_dgrad, void* stream);
 /* (N,H,W,Cin) = input geometry.  stride 1: x, y padded-flat.  stride 2: x = phase planes, y padded-flat (N,Ho+2,Wo+2,Cout). */
 int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                                int stride, void* stream);

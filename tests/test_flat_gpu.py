@@ -50,7 +50,7 @@ def test_flat_conv3x3_fwd_dgrad_wgrad(dev, case):
     Ho, Wo = ref.shape[2], ref.shape[3]
     wf = torch.empty(9 * Co, Ci, device=dev, dtype=torch.bfloat16)
     wd = torch.empty(9 * Ci, Co, device=dev, dtype=torch.bfloat16)
-    _call("cvad_flat_pack_w3x3_bf16", _ptr(w), Co, Ci, _ptr(wf), _ptr(wd), _st())
+    _call("cvad_flat_pack_w3x3_bf16", _ptr(w), Co, Ci, s, _ptr(wf), _ptr(wd), _st())
     xin = tc.to_padded(x) if s == 1 else tc.to_phase(x)
     # junk-filled outputs: the kernels must write every interior element themselves
     y = torch.full((N, Ho + 2, Wo + 2, Co), 7.0, device=dev, dtype=torch.bfloat16)
