@@ -316,20 +316,43 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
     s[i] = 0.f; q[i] = 0.f;
     if (BWD) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; ga[i] = gamma[cg * 8 + i]; be[i] = beta[cg * 8 + i]; }
   }
-  const int rows = g.N * g.H;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int h = r % g.H, n = r / g.H;
-    const long long base = plain_row(g, n, h + 1, 1);
-    for (int w = slot; w < g.W; w += slots) {
+  // Interior pixels as one flat index space p = (n*H + h)*W + w, strided over the block's pixel slots; four independent
+  // 16-byte loads (eight in the backward) are in flight per thread before any is consumed.
+  const int P = g.N * g.H * g.W;               // < 2^31 (checked by the launcher)
+  const int chunk = (P + gridDim.x - 1) / gridDim.x;
+  const int p_end = min(P, (int)(blockIdx.x + 1) * chunk);
+  constexpr int U = 4;
+  for (int p0 = blockIdx.x * chunk + slot; p0 < p_end; p0 += U * slots) {
+    uint4 xv[U], dv[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p0 + u * slots;
+      ok[u] = pp < p_end;
+      if (ok[u]) {
+        const int t = pp / g.W;
+        const int w = pp - t * g.W;
+        const int n = t / g.H;
+        const int h = t - n * g.H;
+        const long long row = plain_row(g, n, h + 1, w + 1);
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(raw) + ((row << g.lg) + cg));
+        if (BWD) {
+          const long long drow = PHASE ? phase_row(g, n, h + 1, w + 1) : row;
+          dv[u] = __ldg(reinterpret_cast<const uint4*>(dact) + ((drow << g.lg) + cg));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
       float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + (((base + w) << g.lg) + cg)), f);
+      unpack8(xv[u], f);
       if (!BWD) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
       } else {
-        const long long drow = PHASE ? phase_row(g, n, h + 1, w + 1) : base + w;
         float d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dact) + ((drow << g.lg) + cg)), d);
+        unpack8(dv[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xh = (f[i] - mu[i]) * is[i];
@@ -431,50 +454,68 @@ __global__ void stem_bn_relu_maxpool_pad_kernel(const float* __restrict__ y, int
   for (int i = threadIdx.x; i < rowlen / 8; i += blockDim.x) o4[i] = t4[i];
 }
 
-// AdaptiveAvgPool2d on a padded-flat input; out (N, C, OH, OW) fp32
+// AdaptiveAvgPool2d on a padded-flat input; out (N, C, OH, OW) fp32.  One thread = one output bin x 8 channels: 16-byte loads
+// over the bin, eight strided fp32 stores (the reference's (c,h,w) flatten order, cad:155).
 __global__ void avgpool_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int OH, int OW, float* __restrict__ out) {
-  const long long total = (long long)N * OH * OW * C;
+  const int groups = C >> 3;
+  const long long total = (long long)N * OH * OW * groups;
   const int Wp = W + 2, Hp = H + 2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % C);
-    long long r = t / C;
+    const int cg = (int)(t % groups);
+    long long r = t / groups;
     const int ow = (int)(r % OW); r /= OW;
     const int oh = (int)(r % OH);
     const int n = (int)(r / OH);
     const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH), w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
-    float s = 0.f;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
     for (int h = h0; h < h1; ++h)
-      for (int w = w0; w < w1; ++w) s += __bfloat162float(x[(((long long)n * Hp + h + 1) * Wp + w + 1) * C + c]);
-    out[(((long long)n * C + c) * OH + oh) * OW + ow] = s / (float)((h1 - h0) * (w1 - w0));
+      for (int w = w0; w < w1; ++w) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + (((long long)n * Hp + h + 1) * Wp + w + 1) * groups + cg), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i];
+      }
+    const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[(((long long)n * C + cg * 8 + i) * OH + oh) * OW + ow] = s[i] * inv;
   }
 }
-// dout (N,C,OH,OW) fp32 -> dx padded-flat bf16 (interior only; the border is never read)
+// dout (N,C,OH,OW) fp32 -> dx padded-flat bf16 (interior only; the border is never read).  One thread = one pixel x 8 channels;
+// a pixel lies in at most a 3x3 neighbourhood of (possibly overlapping) adaptive bins.
 __global__ void avgpool_pad_bwd_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
                                        __nv_bfloat16* __restrict__ dx) {
-  const long long total = (long long)N * H * W * C;
+  const int groups = C >> 3;
+  const long long total = (long long)N * H * W * groups;
   const int Wp = W + 2, Hp = H + 2;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % C);
-    long long r = t / C;
+    const int cg = (int)(t % groups);
+    long long r = t / groups;
     const int w = (int)(r % W); r /= W;
     const int h = (int)(r % H);
     const int n = (int)(r / H);
-    float s = 0.f;
-    for (int oh = 0; oh < OH; ++oh) {
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+    const int ohc = (h * OH) / H, owc = (w * OW) / W;
+    for (int oh = max(0, ohc - 1); oh <= min(OH - 1, ((h + 1) * OH) / H + 1); ++oh) {
       const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH);
       if (h < h0 || h >= h1) continue;
-      for (int ow = 0; ow < OW; ++ow) {
+      for (int ow = max(0, owc - 1); ow <= min(OW - 1, ((w + 1) * OW) / W + 1); ++ow) {
         const int w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
         if (w < w0 || w >= w1) continue;
-        s += __ldg(dout + (((long long)n * C + c) * OH + oh) * OW + ow) / (float)((h1 - h0) * (w1 - w0));
+        const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += __ldg(dout + (((long long)n * C + cg * 8 + i) * OH + oh) * OW + ow) * inv;
       }
     }
-    dx[(((long long)n * Hp + h + 1) * Wp + w + 1) * C + c] = __float2bfloat16(s);
+    reinterpret_cast<uint4*>(dx)[(((long long)n * Hp + h + 1) * Wp + w + 1) * groups + cg] = pack8(s);
   }
 }
 
 inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
-  if (C % 8 || C > 256 || (C / 8) & (C / 8 - 1)) return 1;
+  if (C % 8 || C > 256 || (C / 8) & (C / 8 - 1) || (long long)N * (H + 2) * (W + 2) * 4 > 0x7fffffffLL) return 1;
   g.N = N; g.H = H; g.W = W; g.C = C;
   g.Hq = phase ? (H - 1) / 2 + 3 : 0;
   g.Wq = phase ? (W - 1) / 2 + 3 : 0;
@@ -576,7 +617,7 @@ CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C,
   PadGeo g;
   if (make_geo(g, N, H, W, C, 0)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
+  int blocks = N * H < 8 * cvad_num_sms() ? N * H : 8 * cvad_num_sms();
   pad_reduce_kernel<false, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)raw, nullptr, g, nullptr, nullptr, nullptr,
                                                                               nullptr, ws);
   CVAD_LAUNCH_CHECK();
@@ -608,7 +649,7 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   if (make_geo(g, N, H, W, C, phase_in)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
+  int blocks = N * H < 8 * cvad_num_sms() ? N * H : 8 * cvad_num_sms();
   if (phase_in)
     pad_reduce_kernel<true, 1><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
   else
@@ -631,16 +672,16 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
 }
 
 CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream) {
-  long long total = (long long)N * OH * OW * C;
-  if (total <= 0) return 0;
+  long long total = (long long)N * OH * OW * (C / 8);
+  if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;
   avgpool_pad_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream) {
-  long long total = (long long)N * H * W * C;
-  if (total <= 0) return 0;
+  long long total = (long long)N * H * W * (C / 8);
+  if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;
   avgpool_pad_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
   CVAD_LAUNCH_CHECK();
   return 0;

@@ -48,6 +48,36 @@ class GraphedStep:
         self.launches = ops.LAUNCHES[0] - n0          # cvad ABI calls inside one replay
         self.outputs = out if isinstance(out, tuple) else (out,)
 
+    # ---- input prefetch: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes
+    def _init_prefetch(self):
+        self.staging = [torch.empty_like(s) for s in self.static_inputs]
+        self.copy_stream = torch.cuda.Stream()
+        self.ev_ready, self.ev_free = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_free.record(torch.cuda.current_stream())
+
+    def prefetch(self, *inputs):
+        """Start copying the NEXT step's inputs (pinned host or device tensors) into a staging buffer, asynchronously."""
+        if not hasattr(self, "staging"):
+            self._init_prefetch()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_free)           # the previous step has consumed the staging buffer
+            for st, t in zip(self.staging, inputs):
+                st.copy_(t, non_blocking=True)
+            self.ev_ready.record(self.copy_stream)
+
+    def run_prefetched(self):
+        """Run one step on the inputs handed to the last ``prefetch`` call."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.ev_ready)
+        for s, st in zip(self.static_inputs, self.staging):
+            s.copy_(st, non_blocking=True)                      # device-to-device, ~55 us for the 177 MB batch
+        self.ev_free.record(cur)
+        if self.pre_replay is not None:
+            self.pre_replay()
+        self.graph.replay()
+        ops.LAUNCHES[0] += self.launches
+        return self.outputs
+
     def __call__(self, *inputs):
         for s, t in zip(self.static_inputs, inputs):
             if t is not s:
