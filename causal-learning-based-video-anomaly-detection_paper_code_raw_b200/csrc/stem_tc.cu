@@ -2,14 +2,22 @@
 // tcgen05 kind::tf32 implicit GEMM, fused with the BatchNorm batch statistics (pass 1) or with BN + ReLU (pass 2);
 // MaxPool2d(3,2,1) (cad:118,148) follows as a 16-byte-vector bandwidth kernel that writes the padded-flat bf16 layout.
 //
-// GEMM view: M = output positions (N*Ho*Wo, 128 per tile), N = 32 channels, K = 49 taps padded to 56 (7 MMAs of K=8).
-// With a single input channel an im2col row has no contiguous 16-byte piece, so TMA cannot build the A tile; instead the
-// four "builder" warps gather it: thread r loads the 49 fp32 pixels of its output position straight from global memory
-// (neighbouring threads' windows overlap, so L1 serves ~12 of every 13 reads) and writes one 256-byte K-major row into the
-// SWIZZLE_128B layout the MMA descriptor expects.  A fifth warp issues the MMAs; the builder warps then read the 128x32
-// fp32 accumulator back from TMEM (they own TMEM lanes 32w..32w+31) and either accumulate per-channel sum / sum of
-// squares in registers across all tiles of the CTA (pass 1: no conv output is ever written), or apply BN + ReLU and
-// store bf16 NHWC rows (pass 2).  A tiles and accumulators are double buffered so gather, MMA and epilogue overlap.
+// With one input channel an im2col row has no contiguous 16-byte piece, so neither TMA nor a UMMA descriptor can address it.
+// A 2x2 space-to-depth turns the problem into one they can: X4[n][i][j][a*2+b] = x[n][2(i-2)+a][2(j-2)+b] (zero outside the
+// frame) is an NHWC tensor with 4 fp32 channels = one 16-byte "pixel", and the 7x7 stride-2 convolution becomes a 4x4
+// stride-1 convolution over it (kh = 2u+a-1, kw = 2v+b-1; the 15 combinations outside the 7x7 window get zero weights).
+// Over the flat pixel index q of X4 (geometry (Ho+3) x (Wo+3) per frame) the output is
+//        out[q][:] = sum_{u,v} X4[q + u*(Wo+3) + v][0:4] * W4[u][v]            (positions with i >= Ho or j >= Wo are junk)
+// and the A operand of one MMA (K = 8 tf32 = two horizontally adjacent pixels) is a VIEW OF THE RAW PIXEL STREAM: rows are
+// consecutive pixels (16-byte pitch = the no-swizzle core-matrix row pitch), the second K chunk is the same stream one pixel
+// later (LBO = 16 B, overlapping), 8-row groups follow at SBO = 128 B.  So TMA copies the stream into shared memory as is
+// (one box of up to 32 KiB per tile) and tcgen05.mma performs the im2col through its descriptor -- no thread touches an
+// input element (profiles/r01_umma_descriptor_probe.md, config 15).
+//
+// Kernel: persistent, warp-specialised like flatconv_tc.cu -- warp 0 TMA producer (double-buffered stream segments), warp 1
+// MMA issuer (8 MMAs of M=128, N=32, K=8 per 128 positions, 16-slot TMEM accumulator ring), warp 2 TMEM owner, warps 4-7
+// epilogue: pass 1 accumulates per-channel sum / sum of squares of the valid rows in registers across the whole CTA (no
+// convolution output is ever written), pass 2 applies BN + ReLU and stores bf16 NHWC rows.
 // The frozen stem needs no gradient (cad:596-598).  fp32 inputs are rounded to tf32 (10-bit mantissa) by the MMA.
 #include "common.cuh"
 #include "cvad_b200.h"
@@ -21,12 +29,15 @@ using namespace cvad_tc;
 
 constexpr int ST_C = 32;             // output channels
 constexpr int ST_K = 7;              // kernel size
-constexpr int ST_A_BYTES = 2 * 128 * 128;   // two 32-float K slabs of 128 rows
-constexpr int ST_W_BYTES = 2 * ST_C * 128;
+constexpr int ST_SUB = 8;            // 128-position sub-tiles per tile
+constexpr int ST_SLOTS = 16;         // TMEM accumulator ring (16 x 32 columns)
+constexpr int ST_W_BYTES = 8 * 1024; // 8 MMAs x [2 chunks][32 rows][16 B]
 
 struct StemGeo {
-  int N, H, W, Ho, Wo;
-  long long total;        // N*Ho*Wo
+  int N, H, W, Ho, Wo, Hq, Wq;
+  long long np4;          // N*Hq*Wq pixels of X4 (= GEMM rows incl. junk)
+  long long n_tiles;
+  int seg_rows;           // 128-byte rows (8 pixels) per stream segment
 };
 
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -38,121 +49,153 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
-// MODE 0: statistics (ws[c] += sum y, ws[32+c] += sum y^2, y = conv + bias).  MODE 1: out = relu(y*sc + sh) bf16 NHWC.
+// x (N,1,H,W) fp32 -> X4 (N,Hq,Wq,4) fp32, one 16-byte pixel per thread
+__global__ void stem_s2d_kernel(const float* __restrict__ x, StemGeo g, float4* __restrict__ x4) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.np4; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % g.Wq);
+    const long long r = t / g.Wq;
+    const int i = (int)(r % g.Hq), n = (int)(r / g.Hq);
+    const int h0 = 2 * (i - 2), w0 = 2 * (j - 2);
+    const float* xn = x + (long long)n * g.H * g.W;
+    float v[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int h = h0 + a, w = w0 + b;
+        v[a * 2 + b] = ((unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W) ? __ldg(xn + (long long)h * g.W + w) : 0.f;
+      }
+    x4[t] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// MODE 0: statistics of the raw accumulator (ws[c] += sum acc, ws[32+c] += sum acc^2 over valid rows; the bias is folded in by
+// the finalize kernel).  MODE 1: out = relu((acc + bias - mean) * invstd * gamma + beta) bf16 NHWC (N,Ho,Wo,32).
 template <int MODE>
-__global__ void __launch_bounds__(160) stem_tf32_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                                        StemGeo g, const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        double* __restrict__ ws, __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant__ CUtensorMap map_x4, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, StemGeo g, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, double* __restrict__ ws,
+                                                           __nv_bfloat16* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_a_full[2], bar_a_empty[2], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint64_t bar_seg_full[2], bar_seg_empty[2], bar_acc_full[ST_SLOTS], bar_acc_empty[ST_SLOTS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float s_sc[ST_C], s_sh[ST_C];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t s_a = smem_base;                    // 2 stages x 32 KiB
-  const uint32_t s_w = smem_base + 2 * ST_A_BYTES;   // 8 KiB
+  const uint32_t seg_bytes = (uint32_t)g.seg_rows * 128;
+  const uint32_t s_w = smem_base;                           // 8 KiB of packed weights
+  const uint32_t s_seg = smem_base + ST_W_BYTES;            // 2 stream segments
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const long long n_tiles = (g.total + 127) / 128;
+  constexpr int MT = 128 * ST_SUB;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_a_full[i], 128);
-      mbar_init(&bar_a_empty[i], 1);
-      mbar_init(&bar_acc_full[i], 1);
-      mbar_init(&bar_acc_empty[i], 128);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_seg_full[i], 1); mbar_init(&bar_seg_empty[i], 1); }
+    for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
     fence_barrier_init();
+    prefetch_tmap(&map_x4);
   }
   if (tid < ST_C) {
-    if (MODE == 1) {
-      const float sc = invstd[tid] * gamma[tid];
-      s_sc[tid] = sc;
-      s_sh[tid] = (bias[tid] - mean[tid]) * sc + beta[tid];
-    } else {
-      s_sc[tid] = 1.f;
-      s_sh[tid] = bias[tid];
-    }
+    const float sc = MODE == 1 ? invstd[tid] * gamma[tid] : 1.f;
+    s_sc[tid] = sc;
+    s_sh[tid] = MODE == 1 ? (bias[tid] - mean[tid]) * sc + beta[tid] : 0.f;
   }
-  // weights -> K-major SWIZZLE_128B tile [32 rows][64 floats] (taps 49..63 zero)
-  for (int i = tid; i < ST_C * 64; i += blockDim.x) {
-    const int n = i >> 6, k = i & 63;
-    const float v = k < ST_K * ST_K ? w[n * ST_K * ST_K + k] : 0.f;
-    const int slab = k >> 5, chunk = (k & 31) >> 2, e = k & 3;
-    *reinterpret_cast<float*>(smem_gen + 2 * ST_A_BYTES + slab * (ST_C * 128) + n * 128 + ((chunk ^ (n & 7)) << 4) + e * 4) = v;
+  // weights -> [mma = u*2+vp][K chunk c][n][4 floats]; chunk c of MMA (u,vp) is tap column v = 2vp+c, element e = a*2+b
+  for (int i = tid; i < 8 * 2 * ST_C * 4; i += blockDim.x) {
+    const int e = i & 3, n = (i >> 2) & 31, c = (i >> 7) & 1, m = i >> 8;
+    const int u = m >> 1, v = 2 * (m & 1) + c, a = e >> 1, b = e & 1;
+    const int kh = 2 * u + a - 1, kw = 2 * v + b - 1;
+    const float val = ((unsigned)kh < (unsigned)ST_K && (unsigned)kw < (unsigned)ST_K) ? w[n * ST_K * ST_K + kh * ST_K + kw] : 0.f;
+    reinterpret_cast<float*>(smem_gen)[i] = val;
   }
-  if (warp == 4) tmem_alloc<64>(&tmem_base_sh);
+  if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
 
-  if (warp < 4) {
-    // ---------------------------------------------------------------- builders + epilogue: thread <-> one tile row / TMEM lane
-    const int r = tid;
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: one box per tile
+    uint32_t cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_empty[st], ((cnt >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_seg_full[st], seg_bytes);
+        tma_load_2d(s_seg + st * seg_bytes, &map_x4, 0, (int)(t * (MT / 8)), &bar_seg_full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    uint32_t idesc = 0;
+    idesc |= 1u << 4;                 // D = f32
+    idesc |= 2u << 7;                 // A = tf32
+    idesc |= 2u << 10;                // B = tf32
+    idesc |= (uint32_t)(ST_C >> 3) << 17;
+    idesc |= (uint32_t)(128 >> 4) << 24;
+    const uint64_t da_hi = make_smem_desc(0, 16, 128, UMMA_NOSW);     // pixel stream: K chunks overlap by one pixel
+    const uint64_t db_hi = make_smem_desc(0, 512, 128, UMMA_NOSW);
+    uint32_t cnt = 0, acc_cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_full[st], (cnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t seg = s_seg + st * seg_bytes;
+      for (int s = 0; s < ST_SUB; ++s) {
+        const uint32_t use = acc_cnt + s;
+        const int slot = use % ST_SLOTS;
+        mbar_wait(&bar_acc_empty[slot], ((use / ST_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const uint32_t a_addr = seg + (uint32_t)(s * 128 + (m >> 1) * g.Wq + 2 * (m & 1)) * 16;
+            const uint64_t da = da_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+            const uint64_t db = db_hi | (uint64_t)(((s_w + m * 1024) >> 4) & 0x3FFF);
+            tc_mma_tf32(tmem_base + slot * ST_C, da, db, idesc, m != 0);
+          }
+          tc_commit(&bar_acc_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&bar_seg_empty[st]);
+      __syncwarp();
+      acc_cnt += ST_SUB;
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: thread <-> TMEM lane (row) 32*(warp-4)+lane
+    const int ew = warp - 4;
     float s[ST_C], q[ST_C];
     if (MODE == 0) {
 #pragma unroll
       for (int c = 0; c < ST_C; ++c) { s[c] = 0.f; q[c] = 0.f; }
     }
-    const int HoWo = g.Ho * g.Wo;
-    int it = 0;
-    long long prev_m = -1;
-    for (long long t = blockIdx.x; ; t += gridDim.x, ++it) {
-      const bool have = t < n_tiles;
-      if (have) {
-        const int st = it & 1;
-        mbar_wait(&bar_a_empty[st], ((it >> 1) & 1) ^ 1);
-        const long long m = t * 128 + r;
-        float v[56];
-#pragma unroll
-        for (int i = 0; i < 56; ++i) v[i] = 0.f;
-        if (m < g.total) {
-          const int n = (int)(m / HoWo);
-          const int rem = (int)(m - (long long)n * HoWo);
-          const int oh = rem / g.Wo, ow = rem - oh * g.Wo;
-          const float* xn = x + (long long)n * g.H * g.W;
-          const int iw0 = 2 * ow - 3;
-#pragma unroll
-          for (int kh = 0; kh < ST_K; ++kh) {
-            const int ih = 2 * oh + kh - 3;
-            if ((unsigned)ih < (unsigned)g.H) {
-              const float* xr = xn + (long long)ih * g.W;
-#pragma unroll
-              for (int kw = 0; kw < ST_K; ++kw) {
-                const int iw = iw0 + kw;
-                if ((unsigned)iw < (unsigned)g.W) v[kh * ST_K + kw] = __ldg(xr + iw);
-              }
-            }
-          }
-        }
-        uint8_t* arow = smem_gen + st * ST_A_BYTES + r * 128;
-#pragma unroll
-        for (int j = 0; j < 14; ++j) {
-          const int slab = j >> 3, chunk = j & 7;
-          *reinterpret_cast<float4*>(arow + slab * (128 * 128) + ((chunk ^ (r & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_arrive(&bar_a_full[st]);
-      }
-      // epilogue of the previous tile
-      if (it > 0) {
-        const int pst = (it - 1) & 1;
-        mbar_wait(&bar_acc_full[pst], ((it - 1) >> 1) & 1);
+    const int frame = g.Hq * g.Wq;
+    uint32_t acc_cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+      for (int sb = 0; sb < ST_SUB; ++sb) {
+        const uint32_t use = acc_cnt + sb;
+        const int slot = use % ST_SLOTS;
+        mbar_wait(&bar_acc_full[slot], (use / ST_SLOTS) & 1);
         tc_fence_after();
         uint32_t a0[16], a1[16];
-        const uint32_t taddr = tmem_base + pst * ST_C + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem_base + slot * ST_C + ((uint32_t)(ew * 32) << 16);
         tmem_ld16(taddr, a0);
         tmem_ld16(taddr + 16, a1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&bar_acc_empty[pst]);
-        if (prev_m < g.total) {
+        mbar_arrive(&bar_acc_empty[slot]);
+        const long long qq = t * MT + sb * 128 + ew * 32 + lane;
+        const int n = (int)(qq / frame);
+        const int rem = (int)(qq - (long long)n * frame);
+        const int i = rem / g.Wq, j = rem - i * g.Wq;
+        if (qq < g.np4 && i < g.Ho && j < g.Wo) {
           if (MODE == 0) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-              const float y0 = __uint_as_float(a0[c]) + s_sh[c], y1 = __uint_as_float(a1[c]) + s_sh[16 + c];
+              const float y0 = __uint_as_float(a0[c]), y1 = __uint_as_float(a1[c]);
               s[c] += y0; q[c] = fmaf(y0, y0, q[c]);
               s[16 + c] += y1; q[16 + c] = fmaf(y1, y1, q[16 + c]);
             }
@@ -168,7 +211,7 @@ __global__ void __launch_bounds__(160) stem_tf32_kernel(const float* __restrict_
               pk[c] = *reinterpret_cast<uint32_t*>(&h0);
               pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
             }
-            uint4* o = reinterpret_cast<uint4*>(out + prev_m * ST_C);
+            uint4* o = reinterpret_cast<uint4*>(out + (((long long)n * g.Ho + i) * g.Wo + j) * ST_C);
             o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
@@ -176,65 +219,38 @@ __global__ void __launch_bounds__(160) stem_tf32_kernel(const float* __restrict_
           }
         }
       }
-      if (!have) break;
-      prev_m = t * 128 + r;
+      acc_cnt += ST_SUB;
     }
     if (MODE == 0) {
-      // CTA reduction over the 128 row-threads (reuses A stage 0: every MMA has retired, see the last acc_full wait)
-      float* red = reinterpret_cast<float*>(smem_gen);          // [128][65]
+      // CTA reduction over the 128 row-threads; the stream segments are free (every MMA retired before its acc_full fired)
+      float* red = reinterpret_cast<float*>(smem_gen + ST_W_BYTES);          // [128][65]
+      const int r = tid - 128;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
 #pragma unroll
       for (int c = 0; c < ST_C; ++c) { red[r * 65 + c] = s[c]; red[r * 65 + 32 + c] = q[c]; }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       if (r < 64) {
         double acc = 0.0;
-        for (int i = 0; i < 128; ++i) acc += (double)red[i * 65 + r];
+        for (int k = 0; k < 128; ++k) acc += (double)red[k * 65 + r];
         atomicAdd(ws + r, acc);
       }
-    }
-  } else {
-    // ---------------------------------------------------------------- MMA issuer
-    uint32_t idesc = 0;
-    idesc |= 1u << 4;                 // D = f32
-    idesc |= 2u << 7;                 // A = tf32
-    idesc |= 2u << 10;                // B = tf32
-    idesc |= (uint32_t)(ST_C >> 3) << 17;
-    idesc |= (uint32_t)(128 >> 4) << 24;
-    const uint64_t desc_hi = make_smem_desc(0, 16, 1024, UMMA_SW128);
-    int it = 0;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int st = it & 1;
-      mbar_wait(&bar_a_full[st], (it >> 1) & 1);
-      mbar_wait(&bar_acc_empty[st], ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int ks = 0; ks < 7; ++ks) {
-          const uint32_t a_addr = s_a + st * ST_A_BYTES + (ks >> 2) * (128 * 128) + (ks & 3) * 32;
-          const uint32_t b_addr = s_w + (ks >> 2) * (ST_C * 128) + (ks & 3) * 32;
-          const uint64_t da = desc_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
-          const uint64_t db = desc_hi | (uint64_t)((b_addr >> 4) & 0x3FFF);
-          tc_mma_tf32(tmem_base + st * ST_C, da, db, idesc, ks != 0);
-        }
-        tc_commit(&bar_a_empty[st]);
-        tc_commit(&bar_acc_full[st]);
-      }
-      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<64>(tmem_base);
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-__global__ void stem_finalize_kernel(double* __restrict__ ws, double count, float eps, float momentum, float* __restrict__ mean,
-                                     float* __restrict__ invstd, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                     long long* __restrict__ nbt) {
+// ws holds sum / sum of squares of the RAW accumulator; y = acc + bias: mean_y = mean_acc + b, var_y = var_acc
+__global__ void stem_finalize_kernel(double* __restrict__ ws, const float* __restrict__ bias, double count, float eps, float momentum,
+                                     float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                     float* __restrict__ running_var, long long* __restrict__ nbt) {
   const int c = threadIdx.x;
   if (c < ST_C) {
-    const double m = ws[c] / count;
-    double var = ws[ST_C + c] / count - m * m;
+    const double ma = ws[c] / count;
+    double var = ws[ST_C + c] / count - ma * ma;
     if (var < 0.0) var = 0.0;
+    const double m = ma + (double)bias[c];
     mean[c] = (float)m;
     invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean) {
@@ -287,49 +303,93 @@ __global__ void maxpool3x3s2_pad_kernel(const __nv_bfloat16* __restrict__ y, int
   }
 }
 
-int stem_launch(int mode, const float* x, const float* w, const float* bias, int N, int H, int W, const float* mean, const float* invstd,
-                const float* gamma, const float* beta, double* ws, void* out, cudaStream_t st) {
-  StemGeo g;
+int stem_geo(StemGeo& g, int N, int H, int W) {
   g.N = N; g.H = H; g.W = W;
-  g.Ho = (H + 6 - 7) / 2 + 1;
-  g.Wo = (W + 6 - 7) / 2 + 1;
-  g.total = (long long)N * g.Ho * g.Wo;
-  const size_t smem = 2 * ST_A_BYTES + ST_W_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
+  g.Ho = (H - 1) / 2 + 1;
+  g.Wo = (W - 1) / 2 + 1;
+  g.Hq = g.Ho + 3;
+  g.Wq = g.Wo + 3;
+  g.np4 = (long long)N * g.Hq * g.Wq;
+  const int MT = 128 * ST_SUB;
+  g.n_tiles = (g.np4 + MT - 1) / MT;
+  const int seg_px = MT + 3 * g.Wq + 3;
+  g.seg_rows = (seg_px + 7) / 8;
+  if (g.seg_rows > 256 || g.np4 / 8 > 0x7fffffffLL) return 1;      // one TMA box per tile (frames up to ~1000 px wide)
+  return 0;
+}
+
+int stem_launch(int mode, const float* x4, const float* w, const float* bias, const StemGeo& g, const float* mean, const float* invstd,
+                const float* gamma, const float* beta, double* ws, void* out, cudaStream_t st) {
+  // X4 as a matrix of 128-byte rows (8 pixels); the last partial row is covered by the buffer's 128-byte slack
+  CUtensorMap mx;
+  {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    memset(&mx, 0, sizeof(mx));
+    cuuint64_t dims[2] = {32, (cuuint64_t)((g.np4 + 7) / 8)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)g.seg_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x4), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   }
-  const long long n_tiles = (g.total + 127) / 128;
-  long long grid = 3LL * cvad_num_sms();
-  if (grid > n_tiles) grid = n_tiles;
+  const size_t smem = ST_W_BYTES + 2 * (size_t)g.seg_rows * 128 + 1024 + (mode == 0 ? 0 : 0);
+  const size_t need = smem < (size_t)(ST_W_BYTES + 128 * 65 * 4 + 1024) ? (size_t)(ST_W_BYTES + 128 * 65 * 4 + 1024) : smem;
+  static size_t configured = 0;
+  if (need > configured) {
+    cudaError_t e = cudaFuncSetAttribute(stem_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+    if (e != cudaSuccess) return (int)e;
+    configured = need;
+  }
+  long long grid = cvad_num_sms();
+  if (grid > g.n_tiles) grid = g.n_tiles;
   if (mode == 0)
-    stem_tf32_kernel<0><<<(unsigned)grid, 160, smem, st>>>(x, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
+    stem_tf32_kernel<0><<<(unsigned)grid, 256, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
   else
-    stem_tf32_kernel<1><<<(unsigned)grid, 160, smem, st>>>(x, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
+    stem_tf32_kernel<1><<<(unsigned)grid, 256, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 }  // namespace
 
-CVAD_API int cvad_stem_tf32_stats(const float* x, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
-                                  float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
-                                  void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  int e = stem_launch(0, x, w, bias, N, H, W, nullptr, nullptr, nullptr, nullptr, ws, nullptr, st);
-  if (e) return e;
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  stem_finalize_kernel<<<1, 32, 0, st>>>(ws, (double)N * Ho * Wo, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked);
+CVAD_API long long cvad_stem_x4_floats(int N, int H, int W) {
+  StemGeo g;
+  if (stem_geo(g, N, H, W)) return -1;
+  return ((g.np4 + 7) / 8) * 32 + 32;
+}
+
+CVAD_API int cvad_stem_space_to_depth_f32(const float* x, int N, int H, int W, float* x4, void* stream) {
+  StemGeo g;
+  if (stem_geo(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  long long blocks = (g.np4 + 255) / 256;
+  if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
+  stem_s2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<float4*>(x4));
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
-CVAD_API int cvad_stem_tf32_bn_relu(const float* x, const float* w, const float* bias, int N, int H, int W, const float* mean,
+CVAD_API int cvad_stem_tf32_stats(const float* x4, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
+                                  float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                  void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  StemGeo g;
+  if (stem_geo(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  int e = stem_launch(0, x4, w, bias, g, nullptr, nullptr, nullptr, nullptr, ws, nullptr, st);
+  if (e) return e;
+  stem_finalize_kernel<<<1, 32, 0, st>>>(ws, bias, (double)N * g.Ho * g.Wo, eps, momentum, mean, invstd, running_mean, running_var,
+                                         num_batches_tracked);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean,
                                     const float* invstd, const float* gamma, const float* beta, void* y, void* stream) {
-  return stem_launch(1, x, w, bias, N, H, W, mean, invstd, gamma, beta, nullptr, y, (cudaStream_t)stream);
+  StemGeo g;
+  if (stem_geo(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  return stem_launch(1, x4, w, bias, g, mean, invstd, gamma, beta, nullptr, y, (cudaStream_t)stream);
 }
 
 CVAD_API int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream) {

@@ -5,7 +5,7 @@ stride-2 convolution is written by its producer as four phase planes instead (se
 the eight 3x3 convolutions -- forward, data-gradient and weight-gradient -- is a sum of row-shifted GEMMs that TMA feeds
 straight into tcgen05.mma.  Statistics and parameter gradients are fp32.
 
-  x fp32 (B*T,1,240,360) --tcgen05 tf32 conv 7x7 s2, pass 1: bn1 batch statistics (nothing written)
+  x fp32 (B*T,1,240,360) --2x2 space-to-depth--> X4 (16-byte pixels) --tcgen05 tf32 conv, pass 1: bn1 batch statistics
       --pass 2: conv + BN + ReLU--> bf16 NHWC --MaxPool(3,2,1)--> a0 bf16 padded-flat (.,62,92,32)
   for the 8 layers: raw_i = flatconv(a_{i-1}) ; (mean, invstd) = stats(raw_i) ; a_i = relu(bn(raw_i)) [plain | phase planes]
   features = AdaptiveAvgPool(4,6)(a_8) -> fp32 (B*T, 6144) in the reference's (c,h,w) order
@@ -60,6 +60,12 @@ class _BackboneBF16(torch.autograd.Function):
         mean = torch.empty(C1, device=dev, dtype=torch.float32)
         invstd = torch.empty_like(mean)
         w1, b1 = conv1.weight.detach(), conv1.bias.detach()
+        n4 = int(ops.L().cvad_stem_x4_floats(N, H, W))
+        if n4 < 0:
+            raise RuntimeError(f"frame size {H}x{W} is outside the tensor-core stem's range")
+        x4 = torch.empty(n4, device=dev, dtype=torch.float32)       # 2x2 space-to-depth of the batch: 16-byte pixels
+        _call("cvad_stem_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x4), st)
+        x = x4
         if bn1.training:
             _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps),
                   float(bn1.momentum), _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
@@ -75,7 +81,7 @@ class _BackboneBF16(torch.autograd.Function):
             raise RuntimeError("the first 3x3 convolution after the stem is stride 1 in the reference (cad:150)")
         a = torch.empty(act_shape(N, h, w, C1, False), device=dev, dtype=BF16)
         _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
-        del y1
+        del y1, x4, x
         need_bwd = any(ctx.needs_input_grad)
         saved = []
         cin = C1

@@ -225,12 +225,16 @@ int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH,
 int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream);
 
 /* ---- tensor-core stem (stem_tc.cu): conv 7x7 s2 p3, 1 -> 32 (cad:115,145) as a tcgen05 kind::tf32 implicit GEMM -----------
- * x (N,1,H,W) fp32, w (32,1,7,7) fp32 OIHW, bias (32).  Pass 1: bn1 batch statistics of conv(x)+bias without writing the
- * convolution output (ws = 64 zeroed doubles, re-zeroed by the call; running statistics updated).  Pass 2: relu(bn1(conv))
- * as bf16 NHWC (N,Ho,Wo,32).  Then MaxPool2d(3,2,1) (cad:118) of a post-ReLU bf16 NHWC tensor into the padded-flat layout. */
-int cvad_stem_tf32_stats(const float* x, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
+ * x (N,1,H,W) fp32, w (32,1,7,7) fp32 OIHW, bias (32).  First a 2x2 space-to-depth of x into X4 (N,Ho+3,Wo+3,4) fp32 -- 16-byte
+ * pixels that TMA streams and the MMA descriptor turns into im2col rows; x4 must hold cvad_stem_x4_floats(N,H,W) floats.
+ * Pass 1: bn1 batch statistics of conv(x)+bias without writing the convolution output (ws = 64 zeroed doubles, re-zeroed by
+ * the call; running statistics updated).  Pass 2: relu(bn1(conv)) as bf16 NHWC (N,Ho,Wo,32).  Then MaxPool2d(3,2,1) (cad:118)
+ * of a post-ReLU bf16 NHWC tensor into the padded-flat layout. */
+long long cvad_stem_x4_floats(int N, int H, int W);
+int cvad_stem_space_to_depth_f32(const float* x, int N, int H, int W, float* x4, void* stream);
+int cvad_stem_tf32_stats(const float* x4, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
                          float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
-int cvad_stem_tf32_bn_relu(const float* x, const float* w, const float* bias, int N, int H, int W, const float* mean, const float* invstd,
+int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean, const float* invstd,
                            const float* gamma, const float* beta, void* y, void* stream);
 int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream);
 

@@ -161,7 +161,7 @@ def test_pad_stem_and_avgpool(dev):
     assert rel(tc.from_padded(dxp, H, W), gxr) < 1e-2
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 37, 53), (3, 240, 360), (1, 16, 20)])
+@pytest.mark.parametrize("N,H,W", [(2, 37, 53), (3, 240, 360), (1, 16, 20), (5, 64, 64)])
 @pytest.mark.parametrize("training", [True, False])
 def test_stem_tf32(dev, N, H, W, training):
     """conv 7x7 s2 p3 1->32 + bn1 (+ running statistics) + relu + maxpool(3,2,1), tf32 tensor-core passes vs fp32 torch."""
@@ -179,6 +179,9 @@ def test_stem_tf32(dev, N, H, W, training):
     ref = F.max_pool2d(F.relu(F.batch_norm(y, rm, rv, gam, bet, training, 0.1, 1e-5)), 3, 2, 1)
     mean, invstd = torch.empty(32, device=dev), torch.empty(32, device=dev)
     nbt = torch.tensor(0, device=dev)
+    x_nchw = x
+    x = torch.full((int(ops.L().cvad_stem_x4_floats(N, H, W)),), float("nan"), device=dev)      # 2x2 space-to-depth buffer
+    _call("cvad_stem_space_to_depth_f32", _ptr(x_nchw), N, H, W, _ptr(x), _st())
     if training:
         _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w), _ptr(b), N, H, W, _ptr(ops.bn_workspace(dev, 32)), 1e-5, 0.1, _ptr(mean), _ptr(invstd),
               _ptr(rm2), _ptr(rv2), _ptr(nbt), _st())

@@ -196,7 +196,7 @@ int main(int argc, char** argv) {
   // A(i,m,k): K-major TA[ars + m][acs_i + k] ; MN-major TA[ars_i + k][acol(m)]
   int shiftA = 0, shiftB = 0;
   const char* name = "";
-  enum { K_SW128, K_SW64, MN_SW128, MN_SW64_LBO64, MN_SW64_LBO0, K_NOSW, MN_NOSW } kind = K_SW128;
+  enum { K_SW128, K_SW64, MN_SW128, MN_SW64_LBO64, MN_SW64_LBO0, K_NOSW, MN_NOSW, K_NOSW_STREAM } kind = K_SW128;
   switch (cfg) {
     case 0: kind = K_SW128; shiftA = 0; p.base_off_mode = 0; name = "K-major SW128 shift0"; break;
     case 1: kind = K_SW128; shiftA = 3; p.base_off_mode = 0; name = "K-major SW128 shiftA3 bo0"; break;
@@ -213,6 +213,7 @@ int main(int argc, char** argv) {
     case 12: kind = MN_NOSW; shiftB = 3; name = "MN-major no-swizzle shiftB3 (16B)"; break;
     case 13: kind = K_SW64; shiftA = 0; p.base_off_mode = 0; name = "K-major SW64 shift0"; break;
     case 14: kind = MN_SW128; shiftB = 11; p.base_off_mode = 0; name = "MN-major SW128 shiftB11 bo0"; break;
+    case 15: kind = K_NOSW_STREAM; shiftA = 5; name = "K-major no-swizzle pixel stream: LBO=16B (overlapping K chunks), SBO=128B"; break;
     default: printf("unknown config\n"); return 1;
   }
   p.N = 32;
@@ -255,6 +256,15 @@ int main(int argc, char** argv) {
       p.a_lbo = 160 * 16; p.a_sbo = 128; p.b_lbo = 32 * 16; p.b_sbo = 128; p.a_layout = 0; p.b_layout = 0;
       p.nsteps = 4;
       for (int i = 0; i < 4; ++i) { p.steps[i].a_off = shiftA * 16 + i * 2 * 160 * 16; p.steps[i].b_off = i * 2 * 32 * 16; }
+      break;
+    case K_NOSW_STREAM:
+      // A operand = a linear stream of 16-byte pixels TA[p][8]; row m, K chunk c reads pixel (shift + m + c): LBO = 16 B, SBO = 128 B.
+      // B = TB[n][k] (32 x 32) in the [chunk][row][16B] layout.  Two MMAs of K=16 (the second starts two pixels later).
+      p.use_tma = 0;
+      a_rows = 192; a_cols = 8; b_rows = 32; b_cols = 32;
+      p.a_lbo = 16; p.a_sbo = 128; p.b_lbo = 32 * 16; p.b_sbo = 128; p.a_layout = 0; p.b_layout = 0;
+      p.nsteps = 2;
+      for (int i = 0; i < 2; ++i) { p.steps[i].a_off = (shiftA + 2 * i) * 16; p.steps[i].b_off = i * 2 * 32 * 16; }
       break;
     case MN_NOSW:
       // A = TA[k][m] (48 x 128), B = TB[k + shiftB][n] (64 x 64), [chunk][row][16B]: M-group stride (SBO) = rows*16, K-group stride (LBO) = 128
@@ -306,6 +316,7 @@ int main(int argc, char** argv) {
         case MN_SW128: case MN_NOSW: for (int k = 0; k < 32; ++k) ref += TA(k, m) * TB(k + shiftB, n); break;
         case MN_SW64_LBO64: for (int k = 0; k < 32; ++k) ref += TA(k + m / 32, m % 32) * TB(k, n); break;
         case MN_SW64_LBO0: for (int k = 0; k < 32; ++k) ref += TA(k, m % 32) * TB(k, n); break;
+        case K_NOSW_STREAM: for (int k = 0; k < 32; ++k) ref += TA(shiftA + m + k / 8, k % 8) * TB(n, k); break;
       }
       double e = fabs(ref - out[m * p.N + n]);
       if (e > maxerr) maxerr = e;
