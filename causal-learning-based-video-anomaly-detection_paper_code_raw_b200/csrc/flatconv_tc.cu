@@ -18,7 +18,8 @@
 //   warp 1  tcgen05.mma issuer: every tap is a ROW-SHIFTED VIEW of the resident segment (descriptor start address +
 //           delta*row_bytes; the swizzle is a function of the absolute smem address, profiles/r01_umma_descriptor_probe.md),
 //           M=128 x N x K=16 MMAs into a ring of TMEM accumulators;
-//   warps 4-7  epilogue: tcgen05.ld -> +bias -> bf16 -> global, overlapped with the next tile's MMAs.
+//   warps 4-11 epilogue (two groups on alternate sub-tiles): tcgen05.ld -> +bias -> bf16 -> global, overlapped with the
+//           next tile's MMAs.
 // All role loops are warp-uniform and one elected lane issues, so descriptors live in uniform registers.  TMA boxes are as
 // large as the hardware allows (256 rows): a box costs ~700 cycles of TMA service however small it is
 // (profiles/r01_tma_box_probe.md).  An activation element is fetched from L2/HBM ~1.1-1.4x (halo) instead of 9x.
@@ -55,7 +56,7 @@ struct FcParams {
 };
 
 template <int ROWB, int N>
-__global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
+__global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
                                                           const __grid_constant__ CUtensorMap map_w, const FcParams p,
                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
   constexpr int NSLOT = (512 / N) > FC_MAX_SLOTS ? FC_MAX_SLOTS : (512 / N);
@@ -197,19 +198,20 @@ __global__ void __launch_bounds__(256, 1) flatconv_kernel(const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
-    const int ew = warp - 4;
+    // two groups of four warps (4-7, 8-11) take alternate sub-tiles; warp w reads TMEM lanes 32*(w%4)..
+    const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
     uint32_t acc_cnt = 0;
     int cur_nb = -1;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       const long long q0 = (wi / n_blocks) * MT;
       const int nb = (int)(wi % n_blocks);
       if (nb != cur_nb) {                       // stage this n-block's bias once (epilogue warps only: named barrier 1)
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
-        for (int i = tid - 128; i < N; i += 128) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         cur_nb = nb;
       }
-      for (int s = 0; s < sub; ++s) {
+      for (int s = eg; s < sub; s += 2) {
         const uint32_t use = acc_cnt + s;
         const int slot = use % NSLOT;
         mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
@@ -297,7 +299,7 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   const long long MT = 128LL * p.sub;
   const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
-  flatconv_kernel<ROWB, N><<<grid, 256, smem, st>>>(ms, mt, mw, p, bias, out);
+  flatconv_kernel<ROWB, N><<<grid, 384, smem, st>>>(ms, mt, mw, p, bias, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

@@ -15,8 +15,8 @@
 // input element (profiles/r01_umma_descriptor_probe.md, config 15).
 //
 // Kernel: persistent, warp-specialised like flatconv_tc.cu -- warp 0 TMA producer (double-buffered stream segments), warp 1
-// MMA issuer (8 MMAs of M=128, N=32, K=8 per 128 positions, 16-slot TMEM accumulator ring), warp 2 TMEM owner, warps 4-7
-// epilogue: pass 1 accumulates per-channel sum / sum of squares of the valid rows in registers across the whole CTA (no
+// MMA issuer (8 MMAs of M=128, N=32, K=8 per 128 positions, 16-slot TMEM accumulator ring), warp 2 TMEM owner, warps 4-11
+// epilogue (two groups on alternate sub-tiles): pass 1 accumulates per-channel sum / sum of squares of the valid rows in registers across the whole CTA (no
 // convolution output is ever written), pass 2 applies BN + ReLU and stores bf16 NHWC rows.
 // The frozen stem needs no gradient (cad:596-598).  fp32 inputs are rounded to tf32 (10-bit mantissa) by the MMA.
 #include "common.cuh"
@@ -72,7 +72,7 @@ __global__ void stem_s2d_kernel(const float* __restrict__ x, StemGeo g, float4* 
 // MODE 0: statistics of the raw accumulator (ws[c] += sum acc, ws[32+c] += sum acc^2 over valid rows; the bias is folded in by
 // the finalize kernel).  MODE 1: out = relu((acc + bias - mean) * invstd * gamma + beta) bf16 NHWC (N,Ho,Wo,32).
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant__ CUtensorMap map_x4, const float* __restrict__ w,
+__global__ void __launch_bounds__(384, 1) stem_tf32_kernel(const __grid_constant__ CUtensorMap map_x4, const float* __restrict__ w,
                                                            const float* __restrict__ bias, StemGeo g, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, double* __restrict__ ws,
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue: thread <-> TMEM lane (row) 32*(warp-4)+lane
-    const int ew = warp - 4;
+    // two groups of four warps (warps 4-7 and 8-11) take alternate sub-tiles; warp w reads TMEM lanes 32*(w%4)..
+    const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
     float s[ST_C], q[ST_C];
     if (MODE == 0) {
 #pragma unroll
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant
     const int frame = g.Hq * g.Wq;
     uint32_t acc_cnt = 0;
     for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-      for (int sb = 0; sb < ST_SUB; ++sb) {
+      for (int sb = eg; sb < ST_SUB; sb += 2) {
         const uint32_t use = acc_cnt + sb;
         const int slot = use % ST_SLOTS;
         mbar_wait(&bar_acc_full[slot], (use / ST_SLOTS) & 1);
@@ -187,11 +188,11 @@ __global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bar_acc_empty[slot]);
-        const long long qq = t * MT + sb * 128 + ew * 32 + lane;
-        const int n = (int)(qq / frame);
-        const int rem = (int)(qq - (long long)n * frame);
-        const int i = rem / g.Wq, j = rem - i * g.Wq;
-        if (qq < g.np4 && i < g.Ho && j < g.Wo) {
+        const uint32_t qq = (uint32_t)(t * MT) + sb * 128 + ew * 32 + lane;      // np4 < 2^31 (checked by the launcher)
+        const uint32_t n = qq / (uint32_t)frame;
+        const uint32_t rem = qq - n * (uint32_t)frame;
+        const int i = (int)(rem / (uint32_t)g.Wq), j = (int)(rem - (uint32_t)i * (uint32_t)g.Wq);
+        if ((long long)qq < g.np4 && i < g.Ho && j < g.Wo) {
           if (MODE == 0) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
@@ -223,15 +224,15 @@ __global__ void __launch_bounds__(256, 1) stem_tf32_kernel(const __grid_constant
     }
     if (MODE == 0) {
       // CTA reduction over the 128 row-threads; the stream segments are free (every MMA retired before its acc_full fired)
-      float* red = reinterpret_cast<float*>(smem_gen + ST_W_BYTES);          // [128][65]
+      float* red = reinterpret_cast<float*>(smem_gen + ST_W_BYTES);          // [256][65]
       const int r = tid - 128;
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
 #pragma unroll
       for (int c = 0; c < ST_C; ++c) { red[r * 65 + c] = s[c]; red[r * 65 + 32 + c] = q[c]; }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
       if (r < 64) {
         double acc = 0.0;
-        for (int k = 0; k < 128; ++k) acc += (double)red[k * 65 + r];
+        for (int k = 0; k < 256; ++k) acc += (double)red[k * 65 + r];
         atomicAdd(ws + r, acc);
       }
     }
@@ -314,7 +315,7 @@ int stem_geo(StemGeo& g, int N, int H, int W) {
   g.n_tiles = (g.np4 + MT - 1) / MT;
   const int seg_px = MT + 3 * g.Wq + 3;
   g.seg_rows = (seg_px + 7) / 8;
-  if (g.seg_rows > 256 || g.np4 / 8 > 0x7fffffffLL) return 1;      // one TMA box per tile (frames up to ~1000 px wide)
+  if (g.seg_rows > 256 || g.np4 + 128 * ST_SUB > 0x7fffffffLL) return 1;      // one TMA box per tile (frames up to ~1000 px wide)
   return 0;
 }
 
@@ -335,7 +336,7 @@ int stem_launch(int mode, const float* x4, const float* w, const float* bias, co
     if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
   }
   const size_t smem = ST_W_BYTES + 2 * (size_t)g.seg_rows * 128 + 1024 + (mode == 0 ? 0 : 0);
-  const size_t need = smem < (size_t)(ST_W_BYTES + 128 * 65 * 4 + 1024) ? (size_t)(ST_W_BYTES + 128 * 65 * 4 + 1024) : smem;
+  const size_t need = smem < (size_t)(ST_W_BYTES + 256 * 65 * 4 + 1024) ? (size_t)(ST_W_BYTES + 256 * 65 * 4 + 1024) : smem;
   static size_t configured = 0;
   if (need > configured) {
     cudaError_t e = cudaFuncSetAttribute(stem_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
@@ -346,9 +347,9 @@ int stem_launch(int mode, const float* x4, const float* w, const float* bias, co
   long long grid = cvad_num_sms();
   if (grid > g.n_tiles) grid = g.n_tiles;
   if (mode == 0)
-    stem_tf32_kernel<0><<<(unsigned)grid, 256, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
+    stem_tf32_kernel<0><<<(unsigned)grid, 384, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
   else
-    stem_tf32_kernel<1><<<(unsigned)grid, 256, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
+    stem_tf32_kernel<1><<<(unsigned)grid, 384, need, st>>>(mx, w, bias, g, mean, invstd, gamma, beta, ws, (__nv_bfloat16*)out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
