@@ -39,6 +39,10 @@ constexpr int FC_MAX_SLOTS = 16;     // TMEM accumulator ring
 constexpr int FC_BOX = 256;          // rows per big TMA box
 constexpr size_t FC_SMEM_BUDGET = 226 * 1024;
 
+// optional profiling hook (tools/conv_probe.py): when set, the MMA-issuing warp of every CTA records the cycles it spent
+// waiting on each barrier class: dbg[cta*8 + {0 total, 1 src_full, 2 w_full, 3 acc_empty, 4 work items}]
+__device__ long long* g_fc_debug = nullptr;
+
 struct FcUnit {
   int row_off;          // first segment row relative to the tile's first output row (may be negative)
   int col;              // first channel of the slab
@@ -146,40 +150,60 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint64_t desc_hi = make_smem_desc(0, 16, SBO, LAYOUT);
     uint32_t src_cnt = 0, w_cnt = 0, acc_cnt = 0;
+    long long* dbg = g_fc_debug;
+    long long t_src = 0, t_w = 0, t_acc = 0, n_items = 0;
+    const long long t_begin = dbg ? clock64() : 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
+      ++n_items;
       for (int u = 0; u < n_units; ++u) {
         const int ntaps = p.units[u].ntaps;
         const int st = src_cnt & 1;
+        long long tq = dbg ? clock64() : 0;
         mbar_wait(&bar_src_full[st], (src_cnt >> 1) & 1);
+        if (dbg) t_src += clock64() - tq;
         tc_fence_after();
         const uint32_t a_seg = s_src + st * seg_bytes;
         for (int c = 0; c * TPO < ntaps; ++c) {
           const int ws = resident ? c : (int)(w_cnt % wst);
+          tq = dbg ? clock64() : 0;
           mbar_wait(&bar_w_full[ws], resident ? 0u : ((w_cnt / wst) & 1));
+          if (dbg) t_w += clock64() - tq;
           tc_fence_after();
           const int tin = ntaps - c * TPO < TPO ? ntaps - c * TPO : TPO;
           for (int j = 0; j < tin; ++j) {
             const int t = c * TPO + j;
-            const uint32_t b_base = s_w + ws * WBOX_BYTES + j * (N * ROWB);
             const bool first = (u == 0 && t == 0);
             const bool last = (u == n_units - 1 && t == ntaps - 1);
-            const uint32_t a_tap = a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB;
-            for (int s = 0; s < sub; ++s) {
-              const uint32_t use = acc_cnt + s;
-              const int slot = use % NSLOT;
-              if (first) {
+            // descriptors advance by plain adds: (bytes >> 4) never carries out of the 14-bit address field (smem < 256 KiB)
+            const uint64_t db0 = desc_hi | (uint64_t)(((s_w + ws * WBOX_BYTES + j * (N * ROWB)) >> 4) & 0x3FFF);
+            const uint64_t da0 = desc_hi | (uint64_t)(((a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB) >> 4) & 0x3FFF);
+            if (first) {
+              // first tap of a tile: each accumulator slot must have been drained by the epilogue (overwrite, no accumulate)
+              for (int s = 0; s < sub; ++s) {
+                const uint32_t use = acc_cnt + s;
+                const int slot = use % NSLOT;
+                tq = dbg ? clock64() : 0;
                 mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
+                if (dbg) t_acc += clock64() - tq;
                 tc_fence_after();
-              }
-              if (elect_one()) {
-                const uint32_t a_base = a_tap + (uint32_t)s * 128 * ROWB;
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < K16; ++k) {
-                  const uint64_t da = desc_hi | (uint64_t)(((a_base + k * 32) >> 4) & 0x3FFF);
-                  const uint64_t db = desc_hi | (uint64_t)(((b_base + k * 32) >> 4) & 0x3FFF);
-                  tc_mma_bf16(tmem_base + slot * N, da, db, idesc, !(first && k == 0));
+                  for (int k = 0; k < K16; ++k) tc_mma_bf16(tmem_base + slot * N, da0 + (uint64_t)(s * (128 * ROWB / 16) + 2 * k), db0 + 2 * k, idesc, k != 0);
+                  if (last) tc_commit(&bar_acc_full[slot]);
                 }
-                if (last) tc_commit(&bar_acc_full[slot]);
+                __syncwarp();
+              }
+            } else {
+              if (elect_one()) {
+                uint32_t slot = acc_cnt % NSLOT;
+                uint64_t da = da0;
+                for (int s = 0; s < sub; ++s) {
+#pragma unroll
+                  for (int k = 0; k < K16; ++k) tc_mma_bf16(tmem_base + slot * N, da + 2 * k, db0 + 2 * k, idesc, 1u);
+                  if (last) tc_commit(&bar_acc_full[slot]);
+                  da += 128 * ROWB / 16;
+                  slot = slot + 1 == NSLOT ? 0 : slot + 1;
+                }
               }
               __syncwarp();
             }
@@ -195,6 +219,10 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         ++src_cnt;
       }
       acc_cnt += sub;
+    }
+    if (dbg && lane == 0) {
+      long long* d = dbg + (long long)blockIdx.x * 8;
+      d[0] = clock64() - t_begin; d[1] = t_src; d[2] = t_w; d[3] = t_acc; d[4] = n_items;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
@@ -350,6 +378,11 @@ __global__ void pack_w3x3_flat_kernel(const float* __restrict__ w, int Co, int C
 }
 
 }  // namespace
+
+// development hook: device buffer of 8 int64 per CTA (NULL switches the instrumentation off)
+CVAD_API int cvad_flat_debug_buffer(long long* buf) {
+  return (int)cudaMemcpyToSymbol(g_fc_debug, &buf, sizeof(buf));
+}
 
 CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int stride, void* w_fwd, void* w_dgrad, void* stream) {
   if (Cout % 32 || Cin % 32 || (stride != 1 && stride != 2)) return (int)cudaErrorInvalidValue;

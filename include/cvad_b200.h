@@ -200,6 +200,8 @@ int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, int C, in
  * Cin and Cout swapped; either may be NULL.  Taps are packed in natural order for stride 1 and grouped by phase plane for stride 2,
  * so the taps one TMA box fetches are contiguous rows.  Both buffers hold 9*Cout*Cin elements. */
 int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int stride, void* w_fwd, void* w_dgrad, void* stream);
+/* development hook (tools/conv_probe.py): 8 int64 per CTA receive the MMA warp's wait-cycle breakdown; NULL = off (default) */
+int cvad_flat_debug_buffer(long long* buf);
 /* (N,H,W,Cin) = input geometry.  stride 1: x, y padded-flat.  stride 2: x = phase planes, y padded-flat (N,Ho+2,Wo+2,Cout). */
 int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                                int stride, void* stream);
