@@ -120,6 +120,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the image; stdout carries exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch.distributed as dist
     import cvad_b200
     from cvad_b200 import ops
@@ -220,8 +223,6 @@ def run_ours(args):
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
-    if world > 1:
-        dist.destroy_process_group()
     if rank != 0:
         return
     tf_peak, hbm_peak, src = peaks()
@@ -270,12 +271,20 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
+    ap.add_argument("--watchdog", type=int, default=300, help="seconds after which a stuck run dumps its stack and exits non-zero")
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)     # a hang must never eat the GPU budget
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    # Leave without tearing NCCL down: the captured step graphs still reference the communicator, and destroying it first can
+    # block.  Everything that matters has been printed and flushed.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
