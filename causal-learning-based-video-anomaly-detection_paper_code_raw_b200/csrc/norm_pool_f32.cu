@@ -80,6 +80,17 @@ __global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__
 }
 
 // backward pass 1: g = dy * act'(pre); ws[c] += sum g ; ws[C+c] += sum g * xhat
+// derivative of the activation expressed through its PRE-activation value
+__device__ __forceinline__ float act_grad_from_pre(float pre, int act) {
+  switch (act) {
+    case ACT_RELU: return pre > 0.f ? 1.f : 0.f;
+    case ACT_LEAKY01: return pre > 0.f ? 1.f : 0.1f;
+    case ACT_SIGMOID: { const float sg = 1.f / (1.f + expf(-pre)); return sg * (1.f - sg); }
+    case ACT_TANH: { const float th = tanhf(pre); return 1.f - th * th; }
+    default: return 1.f;
+  }
+}
+
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x, int N, int C, long long S,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, int act, double* __restrict__ ws) {
@@ -96,9 +107,7 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* 
     long long off = ((long long)n * C + c) * S + sp;
     float xh = (__ldg(x + off) - mu) * is;
     float pre = fmaf(xh, ga, be);
-    float g = __ldg(dy + off);
-    if (act == ACT_RELU) g = pre > 0.f ? g : 0.f;
-    else if (act == ACT_LEAKY01) g = pre > 0.f ? g : 0.1f * g;
+    float g = __ldg(dy + off) * act_grad_from_pre(pre, act);
     s += g;
     sx += (double)g * xh;
   }
@@ -129,9 +138,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     for (long long i = threadIdx.x; i < S; i += blockDim.x) {
       float xh = (xp[i] - mu) * is;
       float pre = fmaf(xh, ga, be);
-      float g = gp[i];
-      if (act == ACT_RELU) g = pre > 0.f ? g : 0.f;
-      else if (act == ACT_LEAKY01) g = pre > 0.f ? g : 0.1f * g;
+      const float g = gp[i] * act_grad_from_pre(pre, act);
       dp[i] = k * (g - mg - xh * mgx);
     }
   }

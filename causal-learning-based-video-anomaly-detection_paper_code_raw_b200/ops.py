@@ -521,3 +521,213 @@ def bn_workspace(device, C):
         ws = torch.zeros(2 * C, device=device, dtype=torch.float64)
         _BN_WS[key] = ws
     return ws
+
+
+# ------------------------------------------------------------------------------------------------ M-D building blocks
+class _ConvTranspose2d(torch.autograd.Function):
+    """nn.ConvTranspose2d without bias (cad1:162-177).  Its forward IS the data-gradient kernel of the convolution that maps
+    (Cout_T -> Cin_T) with the same weight tensor (Cin_T, Cout_T, kH, kW); its backward is that convolution's forward (dx)
+    and weight-gradient (dw) with the roles of x and dy exchanged."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding):
+        _cuda(x, weight)
+        x = _f32c(x)
+        N, Ci, Hi, Wi = x.shape
+        _, Co, kH, kW = weight.shape
+        Ho = (Hi - 1) * stride - 2 * padding + kH
+        Wo = (Wi - 1) * stride - 2 * padding + kW
+        y = torch.empty((N, Co, Ho, Wo), device=x.device, dtype=torch.float32)
+        # "convolution" view: input = y-shaped (N,Co,1,Ho,Wo), output = x-shaped (N,Ci,1,Hi,Wi), weight (Ci,Co,1,kH,kW)
+        y5, x5, w5 = y.unsqueeze(2), x.unsqueeze(2), weight.unsqueeze(2)
+        d = _conv_desc(y5, w5, x5, (1, stride, stride), (0, padding, padding))
+        _call("cvad_conv_dgrad_f32", ctypes.byref(d), _ptr(x5), _ptr(weight), _ptr(y5), 0, _st())
+        ctx.geom = (stride, padding)
+        ctx.weight = weight
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        stride, padding = ctx.geom
+        weight = ctx.weight
+        dy = _f32c(dy)
+        dy5, x5, w5 = dy.unsqueeze(2), x.unsqueeze(2), weight.unsqueeze(2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx5 = torch.empty(x5.shape, device=x.device, dtype=torch.float32)
+            d = _conv_desc(dy5, w5, dx5, (1, stride, stride), (0, padding, padding))
+            _call("cvad_conv_fwd_f32", ctypes.byref(d), _ptr(dy5), _ptr(weight), None, _ptr(dx5), ACT_NONE, _st())
+            dx = dx5.squeeze(2)
+        if _wants_grad(weight):
+            d = _conv_desc(dy5, w5, x5, (1, stride, stride), (0, padding, padding))
+            _call("cvad_conv_wgrad_f32", ctypes.byref(d), _ptr(dy5), _ptr(x5), _ptr(grad_buffer(weight)), _st())
+        return dx, None, None, None
+
+
+def conv_transpose2d(x, weight, stride, padding):
+    return _ConvTranspose2d.apply(x, weight, stride, padding)
+
+
+class _ChannelBiasAct(torch.autograd.Function):
+    """y = act(x + bias[c]) on (N,C,H,W): the BatchNorm apply / backward kernels with mean 0, invstd 1, gamma 1."""
+
+    @staticmethod
+    def forward(ctx, x, bias, act):
+        _cuda(x, bias)
+        x = _f32c(x)
+        N, C = x.shape[:2]
+        S = x[0, 0].numel()
+        zeros = torch.zeros(C, device=x.device, dtype=torch.float32)
+        ones = torch.ones(C, device=x.device, dtype=torch.float32)
+        y = torch.empty_like(x)
+        _call("cvad_bn_apply_f32", _ptr(x), _ptr(y), N, C, S, _ptr(zeros), _ptr(ones), _ptr(ones), _ptr(bias), act, _st())
+        ctx.meta = act
+        ctx.bias = bias
+        ctx.save_for_backward(x, zeros, ones)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, zeros, ones = ctx.saved_tensors
+        bias, act = ctx.bias, ctx.meta
+        dy = _f32c(dy)
+        N, C = x.shape[:2]
+        S = x[0, 0].numel()
+        dx = torch.empty_like(x)
+        db = grad_buffer(bias) if _wants_grad(bias) else None
+        _call("cvad_bn_bwd_f32", _ptr(dy), _ptr(x), _ptr(dx), N, C, S, _ptr(zeros), _ptr(ones), _ptr(ones), _ptr(bias), act, 0,
+              _ptr(bn_workspace(x.device, C)), None, _ptr(db), _st())
+        return dx, None, None
+
+
+def channel_bias_act(x, bias, act=ACT_NONE):
+    return _ChannelBiasAct.apply(x, bias, act)
+
+
+class _GroupedBatchNormAct(torch.autograd.Function):
+    """BatchNorm + activation applied to ``groups`` consecutive slices of the batch axis as separate calls, in order: what the
+    reference does when it runs the frame encoder once per time step (cad1:227-231): per-step batch statistics and ``groups``
+    sequential running-statistics updates.  groups = 1 is the ordinary op."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, nbt, ws, training, act, eps, momentum, groups):
+        _cuda(x, gamma, beta)
+        x = _f32c(x)
+        NT, C = x.shape[:2]
+        assert NT % groups == 0
+        N = NT // groups
+        S = x[0, 0].numel()
+        mean = torch.empty((groups, C), device=x.device, dtype=torch.float32)
+        invstd = torch.empty_like(mean)
+        y = torch.empty_like(x)
+        for gi in range(groups):
+            xs, ys = x[gi * N:(gi + 1) * N], y[gi * N:(gi + 1) * N]
+            if training:
+                _call("cvad_bn_train_stats_f32", _ptr(xs), N, C, S, _ptr(ws), float(eps), float(momentum), _ptr(mean[gi]), _ptr(invstd[gi]),
+                      _ptr(running_mean), _ptr(running_var), _ptr(nbt), _st())
+            else:
+                _call("cvad_bn_eval_prepare_f32", C, float(eps), _ptr(running_mean), _ptr(running_var), _ptr(mean[gi]), _ptr(invstd[gi]), _st())
+            _call("cvad_bn_apply_f32", _ptr(xs), _ptr(ys), N, C, S, _ptr(mean[gi]), _ptr(invstd[gi]), _ptr(gamma), _ptr(beta), act, _st())
+        ctx.meta = (training, act, groups)
+        ctx.gamma, ctx.beta, ctx.ws = gamma, beta, ws
+        ctx.save_for_backward(x, mean, invstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, invstd = ctx.saved_tensors
+        training, act, groups = ctx.meta
+        gamma, beta, ws = ctx.gamma, ctx.beta, ctx.ws
+        dy = _f32c(dy)
+        NT, C = x.shape[:2]
+        N = NT // groups
+        S = x[0, 0].numel()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dg = grad_buffer(gamma) if _wants_grad(gamma) else None
+        db = grad_buffer(beta) if _wants_grad(beta) else None
+        for gi in range(groups):
+            sl = slice(gi * N, (gi + 1) * N)
+            _call("cvad_bn_bwd_f32", _ptr(dy[sl]), _ptr(x[sl]), _ptr(dx[sl]) if dx is not None else None, N, C, S, _ptr(mean[gi]),
+                  _ptr(invstd[gi]), _ptr(gamma), _ptr(beta), act, int(training), _ptr(ws), _ptr(dg), _ptr(db), _st())
+        return (dx,) + (None,) * 11
+
+
+def grouped_batchnorm_act(x, bn, act, groups=1):
+    return _GroupedBatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                      bn_workspace(x.device, bn.num_features), bn.training, act, bn.eps, bn.momentum, groups)
+
+
+class _LstmLast(torch.autograd.Function):
+    """Last hidden state of nn.LSTM(64->64) given the precomputed input projection gi (N,T,256) (cad1:238-239)."""
+
+    @staticmethod
+    def forward(ctx, gi, w_hh, b_hh):
+        _cuda(gi, w_hh, b_hh)
+        gi = _f32c(gi)
+        N, T, _ = gi.shape
+        hT = torch.empty((N, 64), device=gi.device, dtype=torch.float32)
+        need = ctx.needs_input_grad[0] or w_hh.requires_grad
+        saved = torch.empty((N, T, 6, 64), device=gi.device, dtype=torch.float32) if need else None
+        _call("cvad_lstm_fwd_f32", _ptr(gi), _ptr(w_hh), _ptr(b_hh), N, T, _ptr(hT), _ptr(saved), _st())
+        ctx.w_hh, ctx.b_hh, ctx.shape = w_hh, b_hh, (N, T)
+        ctx.save_for_backward(saved)
+        return hT
+
+    @staticmethod
+    def backward(ctx, dhT):
+        (saved,) = ctx.saved_tensors
+        N, T = ctx.shape
+        w_hh, b_hh = ctx.w_hh, ctx.b_hh
+        dgi = torch.empty((N, T, 256), device=dhT.device, dtype=torch.float32)
+        dw = grad_buffer(w_hh) if _wants_grad(w_hh) else None
+        db = grad_buffer(b_hh) if _wants_grad(b_hh) else None
+        _call("cvad_lstm_bwd_f32", _ptr(_f32c(dhT)), _ptr(saved), _ptr(w_hh), N, T, _ptr(dgi), _ptr(dw), _ptr(db), _st())
+        return dgi, None, None
+
+
+def lstm_last(gi, w_hh, b_hh):
+    return _LstmLast.apply(gi, w_hh, b_hh)
+
+
+class _ReconMse(torch.autograd.Function):
+    """mean((recon - frames)^2) (cad1:323-344) where recon is (B,T,E) or one reconstruction per clip (B,E) broadcast over T.
+    Returns (loss, per-clip mean error (B,))."""
+
+    @staticmethod
+    def forward(ctx, recon, frames, flag):
+        _cuda(recon, frames)
+        frames = _f32c(frames)
+        B, T = frames.shape[:2]
+        E = frames[0, 0].numel()
+        recon = _f32c(recon)
+        rts = 0 if recon.numel() == B * E else E
+        ws = torch.zeros(B, device=frames.device, dtype=torch.float64)
+        clip = torch.empty(B, device=frames.device, dtype=torch.float32)
+        loss = torch.empty(1, device=frames.device, dtype=torch.float32)
+        dr = torch.empty_like(recon) if ctx.needs_input_grad[0] else None
+        _call("cvad_recon_mse_f32", _ptr(recon), rts, _ptr(frames), B, T, E, _ptr(ws), _ptr(clip), _ptr(loss), _ptr(dr), _ptr(flag), _st())
+        ctx.save_for_backward(dr)
+        ctx.mark_non_differentiable(clip)
+        return loss[0], clip
+
+    @staticmethod
+    def backward(ctx, g, _g2):
+        (dr,) = ctx.saved_tensors
+        return dr * g, None, None
+
+
+def recon_mse(recon, frames, flag=None):
+    return _ReconMse.apply(recon, frames, flag)
+
+
+def memory_score(seq, memory, n_filled):
+    """cad1:262-301 (no gradient: the score is an evaluation signal)."""
+    _cuda(seq, memory)
+    seq = _f32c(seq.detach())
+    B, D = seq.shape
+    out = torch.zeros(B, device=seq.device, dtype=torch.float32)
+    if n_filled >= 10:
+        _call("cvad_memory_score_f32", _ptr(seq), _ptr(memory), B, int(n_filled), D, _ptr(out), _st())
+    return out

@@ -240,6 +240,21 @@ int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, i
                            const float* gamma, const float* beta, void* y, void* stream);
 int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream);
 
+/* ---- M-D: conv autoencoder + LSTM + memory bank (md_kernels.cu), causal_anomaly_detection1.py --------------------------------
+ * nn.LSTM(64->64, 1 layer) recurrence (cad1:182-188, 238-239); gi (N,T,256) = x W_ih^T + b_ih precomputed, gate order i,f,g,o;
+ * hT (N,64) = last hidden state; saved (N,T,6,64) = i,f,g,o,c_prev,h_prev (may be NULL in inference). */
+int cvad_lstm_fwd_f32(const float* gi, const float* w_hh, const float* b_hh, int N, int T, float* hT, float* saved, void* stream);
+/* dgi (N,T,256): gradient of the gate pre-activations; dw_hh (256,64) / db_hh (256) are ADDED (may be NULL) */
+int cvad_lstm_bwd_f32(const float* dhT, const float* saved, const float* w_hh, int N, int T, float* dgi, float* dw_hh, float* db_hh,
+                      void* stream);
+/* cad1:279-294: score[b] = clamp(min_m(1 - clamp(cos(seq_b, memory_m), -1, 1)), 0, 2) / 2 over the first n_filled rows */
+int cvad_memory_score_f32(const float* seq, const float* memory, int B, int n_filled, int D, float* score, void* stream);
+/* cad1:323-344, 545-547: MSE between frames (B,T,E) and a reconstruction (B,T,E) (recon_t_stride = E) or one reconstruction per
+ * clip broadcast over T (recon_t_stride = 0, cad1:254-257).  ws = B zeroed doubles (re-zeroed).  clip_err (B) per-clip mean
+ * error, loss = mean over everything, drecon = d loss / d recon in recon's own shape; any of the three may be NULL. */
+int cvad_recon_mse_f32(const float* recon, long long recon_t_stride, const float* frames, int B, int T, long long E, double* ws,
+                       float* clip_err, float* loss, float* drecon, float* nonfinite_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,11 @@ def ma_clips(B, T, H=240, W=360, seed=1234, wide=True):
     return torch.rand(B, T, 1, H, W, generator=g) * 2 - 1
 
 
+def md_clips(B, T, H=64, W=64, seed=1234):
+    """M-D input (B,T,1,H,W) in [0.001, 0.999] (cad1:110-114 semantics)."""
+    return torch.rand(B, T, 1, H, W, generator=gen(seed)) * 0.998 + 0.001
+
+
 def keep_mask(shape, p, seed):
     """Dropout keep-mask (1 = keep) with drop probability p."""
     return (torch.rand(*shape, generator=gen(seed)) >= p).float()

@@ -339,3 +339,107 @@ def test_ma_bf16_tensor_core_path(dev, gold, idx):
             worst = max(worst, abs(float(p.grad.double().norm()) - sm["norm"]) / sm["norm"])
         print(f"[bf16] case {c['name']}: worst grad-norm rel err {worst:.2e}")
         assert worst < 0.15   # bf16 activations + 8-9 frame batches: per-tensor gradient norms carry a few % of rounding noise
+
+
+# --------------------------------------------------------------------------------------------------------- M-D
+def _md_model(dev, c):
+    from cvad_b200.md import VideoAutoEncoder
+    from test_oracle_golden import md_reference_order, md_state_like, md_synth_state
+    m = VideoAutoEncoder()
+    assert list(m.state_dict().keys()) == c["state_keys"]          # same names, same order as the reference module
+    m.load_state_dict(md_state_like(md_reference_order(md_synth_state(c["seed"]), c["state_keys"]), c["seed"]), strict=True)
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_md_eval_parity(dev, gold, idx):
+    """a19-a20: reconstruction, LSTM sequence feature, memory score and the combined clip score (cad1:545-552), fp32."""
+    from cvad_b200 import md
+    c = gold("md.pt")["cases"][idx]
+    assert not c["train"]
+    m = _md_model(dev, c).eval()
+    x = synth.md_clips(c["B"], c["T"], seed=c["xseed"])
+    with torch.no_grad():
+        out = m(x.to(dev))
+    assert out["reconstructed"].shape == (c["B"], c["T"], 1, 64, 64)
+    assert rel(out["reconstructed"][:, 0], c["recon_frame0"]) < 2e-5 and rel(out["reconstructed"][:, -1], c["recon_frame0"]) < 2e-5
+    assert rel(out["sequence_feature"], c["sequence_feature"]) < 2e-5
+    assert rel(out["frame_features"], c["frame_features"]) < 2e-5
+    assert rel(out["anomaly_score"], c["anomaly_score"], floor=1e-6) < 2e-5
+    scores, labels, recons, mems = md.calculate_anomaly_scores(m, [(x, torch.zeros(c["B"]))], device=dev)
+    assert rel(torch.tensor(scores), c["combined"]) < 2e-5 and labels.shape == (c["B"],)
+
+
+@pytest.mark.parametrize("idx", [2, 3])
+def test_md_train_step_parity(dev, gold, idx):
+    """Reconstruction loss, every parameter gradient, T sequential BN running-stat updates, memory-bank update (cad1:380-425)."""
+    from cvad_b200.md import MDTrainer
+    c = gold("md.pt")["cases"][idx]
+    assert c["train"]
+    tr = MDTrainer(_md_model(dev, c), dev)
+    tr.model.train()
+    x = synth.md_clips(c["B"], c["T"], seed=c["xseed"]).to(dev)
+    tr.optimizer.zero_grad()
+    out = tr.model(x)
+    from cvad_b200.md import reconstruction_loss
+    loss = reconstruction_loss(x, out["reconstructed"])
+    tr.model.update_memory(out["sequence_feature"])
+    loss.backward()
+    assert abs(float(loss) - c["loss"]) < 2e-5 * max(1.0, abs(c["loss"]))
+    gmax = max(v["norm"] for v in c["grads"].values())
+    for k, p in tr.model.named_parameters():
+        gs = c["grads"][k]
+        # per-time-step BatchNorm over 32..96 values amplifies fp32 round-off (the reference and its own restatement differ by ~1e-3)
+        assert abs(float(p.grad.double().norm()) - gs["norm"]) <= 5e-3 * gmax, (k, float(p.grad.norm()), gs["norm"])
+        if gs["full"] is not None and gs["norm"] > 1e-2 * gmax:
+            assert float((p.grad.cpu() - gs["full"]).double().norm()) <= 2e-2 * gs["norm"] + 1e-3 * gmax, k
+    sd = tr.model.state_dict()
+    for k, v in c["new_stats"].items():
+        assert rel(sd[k].float(), v.float(), floor=1e-6) < 5e-5, k
+    assert rel(sd["normal_memory"][37:37 + c["B"]], c["memory_rows"]) < 2e-5
+    before = tr.model.encoder[13].weight.detach().clone()
+    tr.optimizer.step()
+    assert not torch.equal(before, tr.model.encoder[13].weight.detach())
+
+
+@pytest.mark.parametrize("N,T", [(3, 5), (7, 1), (2, 16)])
+def test_lstm_kernel_vs_torch(dev, N, T):
+    from cvad_b200 import ops
+    lstm = torch.nn.LSTM(64, 64, batch_first=True)           # plain fp32 reference on the CPU (cuDNN's RNN may use TF32)
+    x = torch.randn(N, T, 64, requires_grad=True)
+    _, (h, _) = lstm(x)
+    gy = torch.randn(N, 64)
+    gr = torch.autograd.grad(h[-1], [x, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0], gy)
+    gy = gy.to(dev)
+    x2 = x.detach().clone().to(dev).requires_grad_(True)
+    ps = [p.detach().clone().to(dev).requires_grad_(True) for p in (lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)]
+    gi = ops.linear_act(x2.reshape(N * T, 64), ps[0], ps[2]).reshape(N, T, 256)
+    hT = ops.lstm_last(gi, ps[1], ps[3])
+    assert rel(hT, h[-1]) < 1e-5
+    hT.backward(gy)
+    assert rel(x2.grad, gr[0]) < 1e-4
+    for p, g in zip(ps, gr[1:]):
+        assert rel(p.grad, g) < 1e-4
+
+
+def test_conv_transpose_and_memory_score_vs_torch(dev):
+    import torch.nn.functional as F
+    from cvad_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False          # the torch reference must be plain fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.randn(3, 16, 5, 7, device=dev, requires_grad=True)
+    w = (torch.randn(16, 8, 4, 4, device=dev) * 0.1).requires_grad_(True)
+    b = torch.randn(8, device=dev, requires_grad=True)
+    ref = torch.sigmoid(F.conv_transpose2d(x, w, b, stride=2, padding=1))
+    gy = torch.randn_like(ref)
+    gr = torch.autograd.grad(ref, (x, w, b), gy)
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    y = ops.channel_bias_act(ops.conv_transpose2d(x2, w2, 2, 1), b2, ops.ACT_SIGMOID)
+    assert y.shape == ref.shape and rel(y, ref) < 1e-5
+    y.backward(gy)
+    assert rel(x2.grad, gr[0]) < 1e-4 and rel(w2.grad, gr[1]) < 1e-4 and rel(b2.grad, gr[2]) < 1e-4
+    seq, mem = torch.randn(5, 64, device=dev), torch.randn(500, 64, device=dev)
+    zn, mn = F.normalize(seq, dim=-1), F.normalize(mem[:123], dim=-1)
+    want = (1 - (zn @ mn.t()).clamp(-1, 1)).min(dim=1)[0].clamp(0, 2) / 2
+    assert rel(ops.memory_score(seq, mem, 123), want, floor=1e-6) < 1e-5
+    assert float(ops.memory_score(seq, mem, 9).abs().max()) == 0.0

@@ -202,3 +202,78 @@ def ma_noise(c):
             "scorer0": synth.keep_mask((B, 64), 0.2, xs + 4), "cls0": synth.keep_mask((B, 512), 0.3, xs + 5),
             "cls1": synth.keep_mask((B, 256), 0.2, xs + 6)}
     return eps, keep
+
+
+# --------------------------------------------------------------------------------------------------------- M-D
+def md_synth_state(seed):
+    """The state tools/make_golden.py gave the reference VideoAutoEncoder (rebuilt from seeds, no reference needed)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    keys = {}
+    enc = [(1, 32), (32, 64), (64, 128), (128, 128)]
+    for i, (ci, co) in enumerate(enc):
+        keys[f"encoder.{3 * i}.weight"] = torch.zeros(co, ci, 4, 4)
+        keys[f"encoder.{3 * i}.bias"] = torch.zeros(co)
+        for n_, v in (("weight", torch.ones(co)), ("bias", torch.zeros(co)), ("running_mean", torch.zeros(co)), ("running_var", torch.ones(co)),
+                      ("num_batches_tracked", torch.tensor(0))):
+            keys[f"encoder.{3 * i + 1}.{n_}"] = v
+    keys["encoder.13.weight"], keys["encoder.13.bias"] = torch.zeros(64, 2048), torch.zeros(64)
+    keys["decoder.0.weight"], keys["decoder.0.bias"] = torch.zeros(2048, 64), torch.zeros(2048)
+    dec = [(128, 128), (128, 64), (64, 32)]
+    for i, (ci, co) in enumerate(dec):
+        keys[f"decoder.{3 * i + 3}.weight"] = torch.zeros(ci, co, 4, 4)
+        keys[f"decoder.{3 * i + 3}.bias"] = torch.zeros(co)
+        for n_, v in (("weight", torch.ones(co)), ("bias", torch.zeros(co)), ("running_mean", torch.zeros(co)), ("running_var", torch.ones(co)),
+                      ("num_batches_tracked", torch.tensor(0))):
+            keys[f"decoder.{3 * i + 4}.{n_}"] = v
+    keys["decoder.12.weight"], keys["decoder.12.bias"] = torch.zeros(32, 1, 4, 4), torch.zeros(1)
+    for n_, shp in (("weight_ih_l0", (256, 64)), ("weight_hh_l0", (256, 64)), ("bias_ih_l0", (256,)), ("bias_hh_l0", (256,))):
+        keys[f"temporal_encoder.{n_}"] = torch.zeros(shp)
+    keys["normal_memory"] = torch.zeros(500, 64)
+    keys["memory_ptr"] = torch.zeros(1, dtype=torch.long)
+    keys["temperature"] = torch.tensor(1.0)
+    return keys
+
+
+def md_state_like(model_state, seed):
+    """synth_fill in the REFERENCE's state_dict key order + the partly filled memory bank used by the golden generator."""
+    sd = synth.synth_fill(model_state, 700 + seed, skip=("normal_memory", "memory_ptr", "temperature", "num_batches_tracked"))
+    sd["normal_memory"] = torch.zeros(500, 64)
+    sd["normal_memory"][:37] = torch.randn(37, 64, generator=synth.gen(900 + seed))
+    sd["memory_ptr"] = torch.tensor([37])
+    return sd
+
+
+def md_reference_order(keys, order):
+    """Re-order to the reference module's state_dict key order (recorded in the fixture)."""
+    assert set(order) == set(keys), set(order) ^ set(keys)
+    return {k: keys[k] for k in order}
+
+
+def test_md_oracle_matches_reference(gold):
+    from oracle import md as o_md
+    g = gold("md.pt")
+    for c in g["cases"]:
+        P = md_state_like(md_reference_order(md_synth_state(c["seed"]), c["state_keys"]), c["seed"])
+        x = synth.md_clips(c["B"], c["T"], seed=c["xseed"])
+        if c["train"]:
+            for k, v in P.items():
+                if v.is_floating_point() and "running" not in k and k not in ("normal_memory", "temperature"):
+                    v.requires_grad_(True)
+        rec, z, ff, ms = o_md.md_forward(P, x, c["train"])
+        assert rel(rec[:, 0], c["recon_frame0"]) < 1e-5, c["name"]
+        assert rel(z, c["sequence_feature"]) < 1e-5 and rel(ff, c["frame_features"]) < 1e-5
+        assert rel(ms, c["anomaly_score"], floor=1e-6) < 1e-5
+        if not c["train"]:
+            assert rel(o_md.combined_scores(x, rec, ms), c["combined"]) < 1e-5
+        else:
+            loss = o_md.recon_loss(x, rec)
+            assert abs(float(loss) - c["loss"]) < 1e-6
+            loss.backward()
+            gmax = max(v["norm"] for v in c["grads"].values())
+            for k, gs in c["grads"].items():
+                assert abs(float(P[k].grad.double().norm()) - gs["norm"]) < 5e-3 * gmax, k
+            o_md.update_memory(P, z)
+            for k, v in c["new_stats"].items():
+                assert rel(P[k].detach().float(), v.float(), floor=1e-6) < 1e-5, k
+            assert rel(P["normal_memory"][37:37 + c["B"]].detach(), c["memory_rows"]) < 1e-5

@@ -7,7 +7,9 @@ Each fixture stores seeds + (small) tensors; big inputs / weights are rebuilt fr
 """
 from __future__ import annotations
 
+import contextlib
 import copy
+import io
 import os
 import sys
 
@@ -24,6 +26,7 @@ from ref_harness import NoiseInjector, import_ref  # noqa: E402
 from oracle import ma as o_ma  # noqa: E402
 from oracle import mb as o_mb  # noqa: E402
 from oracle import mc as o_mc  # noqa: E402
+from oracle import md as o_md  # noqa: E402
 from oracle import optim as o_opt  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -354,8 +357,79 @@ def make_ma():
     torch.save(out, os.path.join(GOLD, "ma.pt"))
 
 
+
+def md_state(cad1, seed):
+    """Reference VideoAutoEncoder with reproducible, trained-like weights and a partly filled memory bank."""
+    torch.manual_seed(seed)
+    m = cad1.VideoAutoEncoder()
+    sd = synth.synth_fill(m.state_dict(), 700 + seed, skip=("normal_memory", "memory_ptr", "temperature", "num_batches_tracked"))
+    sd["normal_memory"] = torch.zeros(500, 64)
+    sd["normal_memory"][:37] = torch.randn(37, 64, generator=synth.gen(900 + seed))
+    sd["memory_ptr"] = torch.tensor([37])
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def make_md():
+    """M-D: eval forward + combined score, and one training step (loss, every gradient, running statistics, memory update)."""
+    print("== M-D (causal_anomaly_detection1.py)")
+    cad1 = import_ref("causal_anomaly_detection1")
+    cases = []
+    for name, B, T, train, seed in (("eval_b3_t4", 3, 4, False, 1), ("eval_b2_t8", 2, 8, False, 2), ("train_b4_t4", 4, 4, True, 3),
+                                    ("train_b6_t3", 6, 3, True, 4)):
+        m = md_state(cad1, seed).to("cpu")
+        P0 = {k: v.clone() for k, v in m.state_dict().items()}
+        x = synth.md_clips(B, T, seed=40 + seed)
+        m.train(train)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = m(x)
+        P = {k: v.clone() for k, v in P0.items()}
+        rec, z, ff, ms = o_md.md_forward(P, x, train)
+        close(rec, out["reconstructed"], 2e-6, f"{name} oracle reconstructed")
+        close(z, out["sequence_feature"], 2e-6, f"{name} oracle sequence_feature")
+        close(ff, out["frame_features"], 2e-6, f"{name} oracle frame_features")
+        close(ms, out["anomaly_score"], 2e-6, f"{name} oracle anomaly_score", floor=1e-6)
+        c = {"name": name, "B": B, "T": T, "train": train, "seed": seed, "xseed": 40 + seed, "state_keys": list(P0.keys()),
+             "recon_frame0": out["reconstructed"][:, 0].detach().clone(), "sequence_feature": out["sequence_feature"].detach().clone(),
+             "frame_features": out["frame_features"].detach().clone(), "anomaly_score": out["anomaly_score"].detach().clone()}
+        if not train:
+            ref_err = torch.nn.functional.mse_loss(out["reconstructed"], x, reduction="none").view(B, -1).mean(dim=1)
+            comb = 0.7 * ref_err + 0.3 * out["anomaly_score"]
+            close(o_md.combined_scores(x, rec, ms), comb, 2e-6, f"{name} oracle combined score")
+            c["combined"] = comb.detach().clone()
+        else:
+            with contextlib.redirect_stdout(io.StringIO()):
+                loss = cad1.reconstruction_loss(x, out["reconstructed"])
+            m.update_memory(out["sequence_feature"])
+            loss.backward()
+            Pg = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and k not in ("normal_memory", "temperature"))
+                  for k, v in P0.items()}
+            rec2, z2, _, _ = o_md.md_forward(Pg, x, True)
+            lo = o_md.recon_loss(x, rec2)
+            lo.backward()
+            close(lo, loss, 2e-6, f"{name} oracle loss")
+            grads = {}
+            gmax = max(float(p_.grad.abs().max()) for p_ in m.parameters())     # biases feeding a BatchNorm carry pure round-off
+            for k, p_ in m.named_parameters():
+                # per-time-step BatchNorm over B x 4 x 4 = 32..64 values amplifies fp32 round-off: two orderings of the same
+                # arithmetic (reference autograd vs this restatement) already differ by up to ~1e-3 of the largest gradient
+                close(Pg[k].grad, p_.grad, 2e-3, f"{name} oracle grad {k}", floor=gmax)
+                grads[k] = {"norm": float(p_.grad.double().norm()), "full": p_.grad.detach().clone() if p_.numel() <= 4096 else None}
+            o_md.update_memory(Pg, z2)
+            sd = m.state_dict()
+            for k in sd:
+                if "running" in k or "num_batches" in k or k in ("normal_memory", "memory_ptr"):
+                    close(Pg[k].detach().float(), sd[k].float(), 2e-6, f"{name} oracle state {k}", floor=1e-6)
+            c.update({"loss": float(loss), "grads": grads,
+                      "new_stats": {k: v.clone() for k, v in sd.items() if "running" in k or "num_batches" in k or k == "memory_ptr"},
+                      "memory_rows": sd["normal_memory"][37:37 + B].clone()})
+        cases.append(c)
+    torch.save({"cases": cases}, os.path.join(GOLD, "md.pt"))
+    print("   wrote md.pt", os.path.getsize(os.path.join(GOLD, "md.pt")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mb", "mc", "ma"]
+    which = sys.argv[1:] or ["mb", "mc", "ma", "md"]
     os.makedirs(GOLD, exist_ok=True)
     if "mb" in which:
         make_mb()
@@ -363,4 +437,6 @@ if __name__ == "__main__":
         make_mc()
     if "ma" in which:
         make_ma()
+    if "md" in which:
+        make_md()
     print("golden fixtures written to", GOLD)
