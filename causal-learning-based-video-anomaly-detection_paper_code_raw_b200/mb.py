@@ -229,3 +229,19 @@ class MiniCausalVAD(ImprovedMiniCausalVAD):
         self.model.load_state_dict(sd, strict=True)
         if isinstance(ck, dict) and "optimizer_state_dict" in ck:
             self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+
+
+@torch.no_grad()
+def create_unsupervised_labels(test_loader, model, threshold_percentile=95):
+    """avenue_training_script1.py:36-67: scores of the whole loader, their percentile threshold and the pseudo-labels above it.
+    ``model`` is a MiniCausalVAD-style trainer (``.model`` callable returning a 3-tuple, ``.device``).  Scores stay on the
+    device until one concatenated read-back (the reference copies every batch)."""
+    model.model.eval()
+    parts = []
+    for videos, _ in test_loader:
+        s, _, _ = model.model(videos.to(model.device, non_blocking=True))
+        parts.append(s.reshape(-1))
+    all_scores = torch.cat(parts).cpu().numpy() if parts else np.zeros(0, dtype=np.float32)
+    threshold = float(np.percentile(all_scores, threshold_percentile)) if all_scores.size else 0.0
+    pseudo_labels = (all_scores > threshold).astype(float)
+    return all_scores, pseudo_labels, threshold

@@ -443,3 +443,42 @@ def test_conv_transpose_and_memory_score_vs_torch(dev):
     want = (1 - (zn @ mn.t()).clamp(-1, 1)).min(dim=1)[0].clamp(0, 2) / 2
     assert rel(ops.memory_score(seq, mem, 123), want, floor=1e-6) < 1e-5
     assert float(ops.memory_score(seq, mem, 9).abs().max()) == 0.0
+
+
+# --------------------------------------------------------------------------------------------------------- M-E / windows / pseudo-labels
+def test_me_forward_and_sliding_windows(dev, gold):
+    """a21: the visualiser's model (bbox:51-101) on a batch, and all stride-4 windows of a video scored in one batch
+    (bbox:392-415 scores them one batch-1 forward at a time) -- same scores, same adjacency."""
+    from cvad_b200 import me
+    g = gold("me.pt")
+    m = me.CausalAnomalyDetector()
+    assert list(m.state_dict().keys()) == g["state_keys"]
+    m.load_state_dict(synth.synth_fill(m.state_dict(), 555), strict=True)
+    m = m.to(dev).eval()
+    x = synth.mb_clips(4, 8, 64, 64, 77)
+    with torch.no_grad():
+        s, a, f = m(x.to(dev))
+    assert s.shape == (4,) and a.shape == (4, 16, 16) and f.shape == (4, 1024)
+    assert rel(s, g["scores"]) < 2e-5 and rel(a, g["adj"]) < 2e-5 and rel(f, g["feat"]) < 2e-5
+    frames = torch.rand(41, 3, 64, 64, generator=synth.gen(78))
+    starts, scores, adjs, feats = me.score_windows(m, frames, device=dev)
+    assert list(starts) == list(range(0, 41 - 8, 4))
+    assert rel(torch.tensor(scores), g["win_scores"]) < 2e-5 and rel(torch.tensor(adjs), g["win_adj"]) < 2e-5
+    one = me.predict_anomaly_for_clip(m, frames[4:12].permute(1, 0, 2, 3).numpy(), device=dev)
+    assert abs(one[0] - float(g["win_scores"][1])) < 2e-5 and one[1].shape == (16, 16)
+    recs = me.extract_anomalous_windows(m, frames, threshold=float(g["win_scores"].median()), device=dev)
+    assert len(recs) == int((g["win_scores"] > g["win_scores"].median()).sum()) and all(r["end_frame"] - r["start_frame"] == 8 for r in recs)
+
+
+def test_create_unsupervised_labels(dev, gold):
+    """a22 (s1:36-67): p95 threshold over all scores of a loader."""
+    import numpy as np
+    from cvad_b200.mb import MiniCausalVAD, create_unsupervised_labels
+    tr = MiniCausalVAD(device=dev)
+    tr.model.load_state_dict(gold("best_improved_model.pth")["model_state_dict"], strict=True)
+    loader = [(synth.mb_clips_bright(4, 8, 64, 64, 500 + i), torch.zeros(4)) for i in range(6)]
+    scores, labels, thr = create_unsupervised_labels(loader, tr, 95)
+    assert scores.shape == (24,) and labels.shape == (24,)
+    assert abs(thr - np.percentile(scores, 95)) < 1e-12 and int(labels.sum()) == int((scores > thr).sum()) >= 1
+    ref = torch.cat([tr.model(v.to(dev))[0].reshape(-1) for v, _ in loader]).detach().cpu().numpy()
+    assert np.allclose(scores, ref, rtol=0, atol=1e-7)

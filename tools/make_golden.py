@@ -428,8 +428,33 @@ def make_md():
     print("   wrote md.pt", os.path.getsize(os.path.join(GOLD, "md.pt")) // 1024, "KiB")
 
 
+
+def make_me():
+    """M-E: the bbox visualiser's placeholder model, eval forward on a batch and on sliding windows (bbox:51-101, 328-357, 392)."""
+    print("== M-E (avenue_training_script_bbox.py)")
+    bbox = import_ref("avenue_training_script_bbox")
+    torch.manual_seed(0)
+    m = bbox.CausalAnomalyDetector().eval()
+    sd = synth.synth_fill(m.state_dict(), 555)
+    m.load_state_dict(sd, strict=True)
+    x = synth.mb_clips(4, 8, 64, 64, 77)
+    with torch.no_grad():
+        s, a, f = m(x)
+    frames = torch.rand(41, 3, 64, 64, generator=synth.gen(78))
+    ws, wa = [], []
+    with torch.no_grad():
+        for st in range(0, 41 - 8, 4):                                  # bbox:392
+            clip = frames[st:st + 8].permute(1, 0, 2, 3).unsqueeze(0)   # (1,3,8,64,64), bbox:397-411 layout
+            s1, a1, _ = m(clip)
+            ws.append(float(s1))
+            wa.append(a1[0].clone())
+    torch.save({"state_keys": list(sd.keys()), "scores": s.clone(), "adj": a.clone(), "feat": f.clone(), "win_scores": torch.tensor(ws),
+                "win_adj": torch.stack(wa)}, os.path.join(GOLD, "me.pt"))
+    print("   wrote me.pt", os.path.getsize(os.path.join(GOLD, "me.pt")) // 1024, "KiB;", len(ws), "windows")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mb", "mc", "ma", "md"]
+    which = sys.argv[1:] or ["mb", "mc", "ma", "md", "me"]
     os.makedirs(GOLD, exist_ok=True)
     if "mb" in which:
         make_mb()
@@ -439,4 +464,6 @@ if __name__ == "__main__":
         make_ma()
     if "md" in which:
         make_md()
+    if "me" in which:
+        make_me()
     print("golden fixtures written to", GOLD)
