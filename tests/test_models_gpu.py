@@ -482,3 +482,49 @@ def test_create_unsupervised_labels(dev, gold):
     assert abs(thr - np.percentile(scores, 95)) < 1e-12 and int(labels.sum()) == int((scores > thr).sum()) >= 1
     ref = torch.cat([tr.model(v.to(dev))[0].reshape(-1) for v, _ in loader]).detach().cpu().numpy()
     assert np.allclose(scores, ref, rtol=0, atol=1e-7)
+
+
+# --------------------------------------------------------------------------------------------------------- CUDA-graph step
+def test_graphed_train_step_matches_eager(dev):
+    """One CUDA graph per step (graphs.GraphedStep): building it must not advance training, replays must equal eager steps, and a
+    scheduler's LR change must reach the captured optimizer kernel through the device-side LR."""
+    from cvad_b200.ma import CausalAnomalyDetector, MATrainer
+    from cvad_b200.noise import FixedNoise
+    B, T, H, W = 2, 4, 64, 96
+
+    def make():
+        torch.manual_seed(7)
+        tr = MATrainer(CausalAnomalyDetector(), dev, precision="bf16")
+        tr.model.train()
+        g = synth.gen(11)
+        noise = {"eps": torch.randn(B, 5, 6, generator=g), "det0": synth.keep_mask((B, T, 512), 0.3, 1),
+                 "det1": synth.keep_mask((B, T, 256), 0.2, 2), "scorer0": synth.keep_mask((B, 64), 0.2, 3),
+                 "cls0": synth.keep_mask((B, 512), 0.3, 4), "cls1": synth.keep_mask((B, 256), 0.2, 5)}
+        tr.model.noise = FixedNoise({k: v.to(dev) for k, v in noise.items()})       # device-resident: replayable inside a graph
+        return tr
+
+    xs = [synth.ma_clips(B, T, H, W, 20 + i, wide=False).to(dev) for i in range(3)]
+    ys = [torch.tensor([0, 1], device=dev), torch.tensor([1, 1], device=dev), torch.tensor([0, 0], device=dev)]
+    eager, eager2, graphed = make(), make(), make()
+    p0 = graphed.optimizer.arena.p.clone()
+    gs = graphed.graphed_train_step(xs[0], ys[0])
+    assert torch.equal(graphed.optimizer.arena.p, p0), "capturing the graph must not change the parameters"
+    assert gs.launches > 50
+    for i in range(3):
+        if i == 2:                      # an LR scheduler step between replays
+            for tr in (eager, eager2, graphed):
+                tr.optimizer.param_groups[0]["lr"] = 1e-3
+        ce, _ = eager.train_step(xs[i], ys[i])
+        eager2.train_step(xs[i], ys[i])
+        cg, _ = gs(xs[i], ys[i])
+        assert rel(cg, ce, floor=1e-6) < 2e-3, (i, cg, ce)          # fp32 atomics reorder between runs; losses agree closely
+    pe, pe2, pg = eager.optimizer.arena.p, eager2.optimizer.arena.p, graphed.optimizer.arena.p
+    moved = float((pe - p0).abs().mean())
+    noise = float((pe - pe2).abs().mean())         # run-to-run spread of two EAGER runs (Adam amplifies atomics round-off)
+    diff = float((pe - pg).abs().mean())
+    print(f"[graph] mean |dp| {moved:.3e}, eager-vs-eager {noise:.3e}, graph-vs-eager {diff:.3e}")
+    assert moved > 1e-4
+    assert diff <= 3 * noise + 0.02 * moved
+    # the third step ran at lr 1e-3 in all three: had the graph kept the captured 3e-4 it would trail by ~0.7e-3 per parameter
+    last = float(((pg - p0).abs().mean()))
+    assert abs(last - moved) < 0.1 * moved
