@@ -1,9 +1,8 @@
-// Bandwidth kernels of the bf16 (tensor-core) M-A backbone path: NHWC bf16 activations, fp32 statistics.
-//   stem:      BatchNorm2d + ReLU + MaxPool2d(3,2,1) of the frozen 7x7 stem output (cad:145-148), NCHW fp32 -> NHWC bf16
+// Bandwidth kernels of the bf16 (tensor-core) M-A backbone path on the padded-flat / phase-plane layouts of flatconv_tc.cu:
 //   bn_stats:  per-channel batch mean / biased variance (fp64 accumulation) + running-stat update (cad:131,136)
-//   bn_apply:  y = relu((x-mean)*invstd*gamma+beta), bf16 -> bf16
+//   bn_apply:  y = relu((x-mean)*invstd*gamma+beta), bf16 -> bf16, zero border / phase planes for the next convolution
 //   bn_bwd:    ReLU + BatchNorm backward (two passes: per-channel reductions, then dx), dgamma/dbeta accumulated in fp32
-//   avgpool:   AdaptiveAvgPool2d((4,6)) (cad:126,155) NHWC bf16 -> fp32 features in the reference's (c,h,w) flatten order
+//   avgpool:   AdaptiveAvgPool2d((4,6)) (cad:126,155) bf16 -> fp32 features in the reference's (c,h,w) flatten order
 // All loads/stores are 16-byte vectors over the channel axis (8 bf16), coalesced across threads.
 #include "common.cuh"
 #include "cvad_b200.h"
@@ -27,86 +26,6 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return v;
 }
 
-// ------------------------------------------------------------------------------------------------ stem
-// one block per (n, ph): y (N,C,H,W) fp32 -> out (N,PH,PW,C) bf16, 3x3 stride-2 pad-1 max of relu(bn(y))
-__global__ void stem_bn_relu_maxpool_kernel(const float* __restrict__ y, int C, int H, int W, int PH, int PW, const float* __restrict__ mean,
-                                            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __nv_bfloat16 tile[];   // [PW][C]
-  const int ph = blockIdx.x % PH, n = blockIdx.x / PH;
-  for (int i = threadIdx.x; i < C * PW; i += blockDim.x) {
-    const int pw = i % PW, c = i / PW;     // pw fastest: reads run along W
-    const float sc = invstd[c] * gamma[c];
-    const float sh = beta[c] - mean[c] * sc;
-    const float* yp = y + ((long long)n * C + c) * H * W;
-    float best = 0.f;                       // relu output is >= 0 and every window holds >= 1 valid element
-    for (int a = 0; a < 3; ++a) {
-      const int h = ph * 2 - 1 + a;
-      if ((unsigned)h >= (unsigned)H) continue;
-      for (int b = 0; b < 3; ++b) {
-        const int w = pw * 2 - 1 + b;
-        if ((unsigned)w >= (unsigned)W) continue;
-        best = fmaxf(best, fmaf(__ldg(yp + (long long)h * W + w), sc, sh));
-      }
-    }
-    tile[pw * C + c] = __float2bfloat16(best);
-  }
-  __syncthreads();
-  __nv_bfloat16* op = out + ((long long)n * PH + ph) * PW * C;
-  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
-  uint4* o4 = reinterpret_cast<uint4*>(op);
-  for (int i = threadIdx.x; i < PW * C / 8; i += blockDim.x) o4[i] = t4[i];
-}
-
-// ------------------------------------------------------------------------------------------------ BN statistics
-// x (P, C) bf16.  Thread handles one 8-channel group; blockDim = 256 -> 256/(C/8) pixels per pass.
-template <bool BWD>
-__global__ void bn_reduce_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dact, long long P, int C,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, double* __restrict__ ws) {
-  // !BWD: ws[c] += sum x, ws[C+c] += sum x^2.   BWD: g = dact*(pre>0): ws[c] += sum g, ws[C+c] += sum g*xhat
-  extern __shared__ float red[];             // [256][16]
-  const int groups = C / 8;
-  const int cg = threadIdx.x % groups, prow = threadIdx.x / groups, prows = blockDim.x / groups;
-  const long long chunk = (P + gridDim.x - 1) / gridDim.x;
-  const long long beg = blockIdx.x * chunk, end = beg + chunk < P ? beg + chunk : P;
-  float s[8], q[8], mu[8], is[8], ga[8], be[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    s[i] = 0.f; q[i] = 0.f;
-    if (BWD) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; ga[i] = gamma[cg * 8 + i]; be[i] = beta[cg * 8 + i]; }
-  }
-  for (long long p = beg + prow; p < end; p += prows) {
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * C) + cg), f);
-    if (!BWD) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
-    } else {
-      float d[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dact + p * C) + cg), d);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float xh = (f[i] - mu[i]) * is[i];
-        float g = fmaf(xh, ga[i], be[i]) > 0.f ? d[i] : 0.f;
-        s[i] += g;
-        q[i] = fmaf(g, xh, q[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
-  __syncthreads();
-  // threads 0..2C-1 finish: j < C -> sum of channel j ; j >= C -> second moment
-  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
-    const int c = j % C, which = j / C;
-    const int g2 = c / 8, i = c % 8;
-    double acc = 0.0;
-    for (int r = 0; r < prows; ++r) acc += (double)red[(r * groups + g2) * 16 + which * 8 + i];
-    atomicAdd(ws + which * C + c, acc);
-  }
-}
-
 __global__ void bn_finalize_nhwc_kernel(double* __restrict__ ws, int C, double count, float eps, float momentum, float* __restrict__ mean,
                                         float* __restrict__ invstd, float* __restrict__ running_mean, float* __restrict__ running_var,
                                         long long* __restrict__ nbt) {
@@ -128,51 +47,6 @@ __global__ void bn_finalize_nhwc_kernel(double* __restrict__ ws, int C, double c
   if (c == 0 && nbt) *nbt += 1;
 }
 
-__global__ void bn_apply_relu_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long P, int C,
-                                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                          const float* __restrict__ beta) {
-  const int groups = C / 8;
-  const long long total = P * groups;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(t % groups);
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = cg * 8 + i;
-      const float sc = invstd[c] * gamma[c];
-      f[i] = fmaxf(fmaf(f[i], sc, beta[c] - mean[c] * sc), 0.f);
-    }
-    reinterpret_cast<uint4*>(y)[t] = pack8(f);
-  }
-}
-
-// dx = gamma*invstd*(g - mean_g - xhat*mean_gx) ; training==0 -> dx = gamma*invstd*g
-__global__ void bn_relu_bwd_apply_nhwc_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dact,
-                                              __nv_bfloat16* __restrict__ dx, long long P, int C, const float* __restrict__ mean,
-                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                              const float* __restrict__ beta, const double* __restrict__ ws, double count, int training) {
-  const int groups = C / 8;
-  const long long total = P * groups;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(t % groups);
-    float f[8], d[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x) + t), f);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dact) + t), d);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = cg * 8 + i;
-      const float is = invstd[c], ga = gamma[c];
-      const float xh = (f[i] - mean[c]) * is;
-      const float g = fmaf(xh, ga, beta[c]) > 0.f ? d[i] : 0.f;
-      const float mg = training ? (float)(ws[c] / count) : 0.f;
-      const float mgx = training ? (float)(ws[C + c] / count) : 0.f;
-      f[i] = ga * is * (g - mg - xh * mgx);
-    }
-    reinterpret_cast<uint4*>(dx)[t] = pack8(f);
-  }
-}
-
 __global__ void bn_bwd_params_nhwc_kernel(double* __restrict__ ws, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
@@ -186,47 +60,6 @@ __global__ void bn_bwd_params_nhwc_kernel(double* __restrict__ ws, int C, float*
 // ------------------------------------------------------------------------------------------------ adaptive average pool
 __device__ __forceinline__ int bstart(int o, int in, int out) { return (int)(((long long)o * in) / out); }
 __device__ __forceinline__ int bend(int o, int in, int out) { return (int)((((long long)(o + 1)) * in + out - 1) / out); }
-
-// x (N,H,W,C) bf16 -> out (N, C, OH, OW) fp32
-__global__ void avgpool_nhwc_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int OH, int OW,
-                                        float* __restrict__ out) {
-  const long long total = (long long)N * OH * OW * C;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % C);
-    long long r = t / C;
-    const int ow = (int)(r % OW); r /= OW;
-    const int oh = (int)(r % OH);
-    const int n = (int)(r / OH);
-    const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH), w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
-    float s = 0.f;
-    for (int h = h0; h < h1; ++h)
-      for (int w = w0; w < w1; ++w) s += __bfloat162float(x[(((long long)n * H + h) * W + w) * C + c]);
-    out[(((long long)n * C + c) * OH + oh) * OW + ow] = s / (float)((h1 - h0) * (w1 - w0));
-  }
-}
-// dout (N,C,OH,OW) fp32 -> dx (N,H,W,C) bf16
-__global__ void avgpool_nhwc_bwd_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
-                                        __nv_bfloat16* __restrict__ dx) {
-  const long long total = (long long)N * H * W * C;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(t % C);
-    long long r = t / C;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H);
-    const int n = (int)(r / H);
-    float s = 0.f;
-    for (int oh = 0; oh < OH; ++oh) {
-      const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH);
-      if (h < h0 || h >= h1) continue;
-      for (int ow = 0; ow < OW; ++ow) {
-        const int w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
-        if (w < w0 || w >= w1) continue;
-        s += __ldg(dout + (((long long)n * C + c) * OH + oh) * OW + ow) / (float)((h1 - h0) * (w1 - w0));
-      }
-    }
-    dx[t] = __float2bfloat16(s);
-  }
-}
 
 inline int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
@@ -418,42 +251,6 @@ __global__ void pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ r
   }
 }
 
-// stem: y (N,C,H,W) fp32 NCHW -> relu(bn) -> maxpool(3,2,1) -> padded-flat (N,PH+2,PW+2,C) bf16 with zero border
-__global__ void stem_bn_relu_maxpool_pad_kernel(const float* __restrict__ y, int C, int H, int W, int PH, int PW, const float* __restrict__ mean,
-                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __nv_bfloat16 tile[];   // [PW+2][C]
-  const int php = blockIdx.x % (PH + 2), n = blockIdx.x / (PH + 2);
-  const int rowlen = (PW + 2) * C;
-  uint4* o4 = reinterpret_cast<uint4*>(out + (long long)blockIdx.x * rowlen);
-  if (php == 0 || php == PH + 1) {
-    for (int i = threadIdx.x; i < rowlen / 8; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  const int ph = php - 1;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) tile[(i < C ? 0 : (PW + 1) * C) + (i % C)] = __float2bfloat16(0.f);
-  for (int i = threadIdx.x; i < C * PW; i += blockDim.x) {
-    const int pw = i % PW, c = i / PW;
-    const float sc = invstd[c] * gamma[c];
-    const float sh = beta[c] - mean[c] * sc;
-    const float* yp = y + ((long long)n * C + c) * H * W;
-    float best = 0.f;
-    for (int a = 0; a < 3; ++a) {
-      const int h = ph * 2 - 1 + a;
-      if ((unsigned)h >= (unsigned)H) continue;
-      for (int b = 0; b < 3; ++b) {
-        const int w = pw * 2 - 1 + b;
-        if ((unsigned)w >= (unsigned)W) continue;
-        best = fmaxf(best, fmaf(__ldg(yp + (long long)h * W + w), sc, sh));
-      }
-    }
-    tile[(pw + 1) * C + c] = __float2bfloat16(best);
-  }
-  __syncthreads();
-  const uint4* t4 = reinterpret_cast<const uint4*>(tile);
-  for (int i = threadIdx.x; i < rowlen / 8; i += blockDim.x) o4[i] = t4[i];
-}
-
 // AdaptiveAvgPool2d on a padded-flat input; out (N, C, OH, OW) fp32.  One thread = one output bin x 8 channels: 16-byte loads
 // over the bin, eight strided fp32 stores (the reference's (c,h,w) flatten order, cad:155).
 __global__ void avgpool_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int OH, int OW, float* __restrict__ out) {
@@ -526,92 +323,7 @@ inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
 
 }  // namespace
 
-CVAD_API int cvad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd,
-                                            const float* gamma, const float* beta, void* out, void* stream) {
-  const int PH = (H + 2 - 3) / 2 + 1, PW = (W + 2 - 3) / 2 + 1;
-  if ((PW * C) % 8) return (int)cudaErrorInvalidValue;
-  size_t smem = (size_t)PW * C * 2;
-  stem_bn_relu_maxpool_kernel<<<N * PH, 256, smem, (cudaStream_t)stream>>>(y, C, H, W, PH, PW, mean, invstd, gamma, beta,
-                                                                           (__nv_bfloat16*)out);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
-CVAD_API int cvad_bn_stats_nhwc_bf16(const void* x, long long P, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
-                                     float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
-  if (C % 8 || C > 512 || 256 % (C / 8)) return (int)cudaErrorInvalidValue;
-  cudaStream_t st = (cudaStream_t)stream;
-  int blocks = (int)((P + 2047) / 2048);
-  if (blocks > 4 * cvad_num_sms()) blocks = 4 * cvad_num_sms();
-  if (blocks < 1) blocks = 1;
-  bn_reduce_nhwc_kernel<false><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)x, nullptr, P, C, nullptr, nullptr,
-                                                                               nullptr, nullptr, ws);
-  CVAD_LAUNCH_CHECK();
-  bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, (double)P, eps, momentum, mean, invstd, running_mean, running_var,
-                                                           num_batches_tracked);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
-CVAD_API int cvad_bn_apply_relu_nhwc_bf16(const void* x, void* y, long long P, int C, const float* mean, const float* invstd,
-                                          const float* gamma, const float* beta, void* stream) {
-  if (C % 8) return (int)cudaErrorInvalidValue;
-  bn_apply_relu_nhwc_kernel<<<blocks_for(P * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, P, C, mean,
-                                                                                        invstd, gamma, beta);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
-CVAD_API int cvad_bn_relu_bwd_nhwc_bf16(const void* x, const void* dact, void* dx, long long P, int C, const float* mean,
-                                        const float* invstd, const float* gamma, const float* beta, int training, double* ws,
-                                        float* dgamma, float* dbeta, void* stream) {
-  if (C % 8 || C > 512 || 256 % (C / 8)) return (int)cudaErrorInvalidValue;
-  cudaStream_t st = (cudaStream_t)stream;
-  int blocks = (int)((P + 2047) / 2048);
-  if (blocks > 4 * cvad_num_sms()) blocks = 4 * cvad_num_sms();
-  if (blocks < 1) blocks = 1;
-  bn_reduce_nhwc_kernel<true><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dact, P, C, mean,
-                                                                              invstd, gamma, beta, ws);
-  CVAD_LAUNCH_CHECK();
-  if (dx) {
-    bn_relu_bwd_apply_nhwc_kernel<<<blocks_for(P * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dact,
-                                                                           (__nv_bfloat16*)dx, P, C, mean, invstd, gamma, beta, ws,
-                                                                           (double)P, training);
-    CVAD_LAUNCH_CHECK();
-  }
-  bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
-CVAD_API int cvad_avgpool_nhwc_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream) {
-  long long total = (long long)N * OH * OW * C;
-  if (total <= 0) return 0;
-  avgpool_nhwc_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
-CVAD_API int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream) {
-  long long total = (long long)N * H * W * C;
-  if (total <= 0) return 0;
-  avgpool_nhwc_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
 // ---------------------------------------------------------------------------------------------- padded-flat entry points
-CVAD_API int cvad_pad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd,
-                                                const float* gamma, const float* beta, void* out, void* stream) {
-  const int PH = (H + 2 - 3) / 2 + 1, PW = (W + 2 - 3) / 2 + 1;
-  if (C % 8) return (int)cudaErrorInvalidValue;
-  size_t smem = (size_t)(PW + 2) * C * 2;
-  stem_bn_relu_maxpool_pad_kernel<<<N * (PH + 2), 256, smem, (cudaStream_t)stream>>>(y, C, H, W, PH, PW, mean, invstd, gamma, beta,
-                                                                                     (__nv_bfloat16*)out);
-  CVAD_LAUNCH_CHECK();
-  return 0;
-}
-
 CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean,
                                     float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
   PadGeo g;

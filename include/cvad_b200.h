@@ -164,35 +164,9 @@ int cvad_lincomb3_f32(float* out, const float* x, float a, const float* y, float
 int cvad_softmax_rows_f32(const float* x, long long rows, int C, float* y, void* stream);
 int cvad_softmax_rows_bwd_f32(const float* y, const float* dy, long long rows, int C, float* dx, void* stream);
 
-/* ---- bf16 tensor-core path of the M-A backbone (conv_tc.cu, nhwc_bf16.cu) ---------------------------------------------
- * The eight 3x3 convolutions of cad:128-139 as tcgen05 (UMMA) implicit GEMMs: bf16 operands, fp32 accumulation in TMEM.
- * Activations are NHWC bf16 (void* = __nv_bfloat16*).  Cin % 8 == 0, Cout % 32 == 0, kernel 3x3, padding 1. */
-/* OIHW fp32 (Cout,Cin,3,3) -> w_fwd [Cout][tap][Cin] bf16 and w_dgrad [Cin][tap][Cout] bf16 (either may be NULL) */
-int cvad_pack_w3x3_bf16(const float* w, int Cout, int Cin, void* w_fwd, void* w_dgrad, void* stream);
-/* y (N,Ho,Wo,Cout) = conv3x3(x (N,H,W,Cin)) + bias (fp32, may be NULL) */
-int cvad_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int stride,
-                          void* stream);
-/* dx (N,H,W,Cin) from dy (N,Ho,Wo,Cout) */
-int cvad_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
-/* dw (OIHW fp32) += x^T dy, reduction over pixels split across CTAs, fp32 atomics into the gradient arena */
-int cvad_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
-/* cad:145-148: relu(bn1(y)) then MaxPool2d(3,2,1); y (N,C,H,W) fp32 NCHW -> out (N,PH,PW,C) bf16 NHWC */
-int cvad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd, const float* gamma,
-                                   const float* beta, void* out, void* stream);
-/* BatchNorm2d batch statistics over x (P pixels, C channels) bf16; ws = 2*C zeroed doubles (re-zeroed by the call) */
-int cvad_bn_stats_nhwc_bf16(const void* x, long long P, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
-                            float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
-int cvad_bn_apply_relu_nhwc_bf16(const void* x, void* y, long long P, int C, const float* mean, const float* invstd, const float* gamma,
-                                 const float* beta, void* stream);
-/* ReLU+BN backward: dx (bf16, may be NULL) from dact; dgamma / dbeta ADDED in fp32 (may be NULL) */
-int cvad_bn_relu_bwd_nhwc_bf16(const void* x, const void* dact, void* dx, long long P, int C, const float* mean, const float* invstd,
-                               const float* gamma, const float* beta, int training, double* ws, float* dgamma, float* dbeta, void* stream);
-/* cad:126,155: AdaptiveAvgPool2d NHWC bf16 -> fp32 (N,C,OH,OW) (the reference's flatten order) and its gradient */
-int cvad_avgpool_nhwc_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream);
-int cvad_avgpool_nhwc_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream);
-
-/* ---- "flat" bf16 tensor-core path of the M-A backbone (flatconv_tc.cu, nhwc_bf16.cu) -----------------------------------
- * Same arithmetic as the block above (cad:128-139, 145-155) on a zero-bordered layout that lets TMA feed tcgen05 directly:
+/* ---- bf16 tensor-core path of the M-A backbone (flatconv_tc.cu, nhwc_bf16.cu) ---------------------------------------------
+ * The eight 3x3 convolutions, BatchNorms and pools of cad:128-139, 145-155 as tcgen05 (UMMA) GEMMs with fp32 accumulation in
+ * TMEM, on a zero-bordered layout that lets TMA feed the tensor cores directly:
  * an activation (N,H,W,C) is stored "padded-flat" as (N,H+2,W+2,C) bf16; the input of a stride-2 convolution is stored as
  * four phase planes P_ab[n][i][j] = padded(2(i-1)+a, 2(j-1)+b), each in the geometry (N,Ho+2,Wo+2,C) of that convolution's
  * output, plane index a*2+b outermost.  Convolution outputs / data-gradients carry junk in their border rows. */
@@ -210,9 +184,6 @@ int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, 
                                  void* stream);
 /* dw (OIHW fp32) += sum over pixels; x as for the forward (padded-flat or phase planes), dy padded-flat with a ZERO border */
 int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
-/* cad:145-148 -> padded-flat (N,PH+2,PW+2,C) bf16 with zero border */
-int cvad_pad_stem_bn_relu_maxpool_bf16(const float* y, int N, int C, int H, int W, const float* mean, const float* invstd, const float* gamma,
-                                       const float* beta, void* out, void* stream);
 /* batch statistics over the interior of a padded-flat raw tensor (N,H,W,C interior geometry) */
 int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
                            float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);

@@ -278,95 +278,3 @@ def test_fused_adam_matches_torch(dev, decoupled, clip_mode):
     for a, b in zip(before, my_p):
         assert torch.equal(a, b.data)
     assert mopt.skipped_steps() == 1
-
-
-# ------------------------------------------------------------------------------------------------ bf16 tensor-core path
-TC_CASES = [(2, 12, 18, 32, 32, 1), (3, 15, 23, 32, 64, 2), (2, 9, 11, 64, 128, 2), (1, 8, 12, 128, 256, 1), (2, 30, 45, 64, 64, 1),
-            (5, 8, 12, 256, 256, 1), (2, 60, 90, 32, 32, 1)]
-
-
-def _tc_inputs(dev, N, H, W, Ci, Co, s):
-    x = torch.randn(N, H, W, Ci, generator=_g(1)).to(dev).to(torch.bfloat16)
-    w = (torch.randn(Co, Ci, 3, 3, generator=_g(2)) / (3.0 * Ci ** 0.5)).to(dev)
-    b = torch.randn(Co, generator=_g(3)).to(dev)
-    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
-    wr = w.to(torch.bfloat16).float().requires_grad_(True)
-    ref = F.conv2d(xr, wr, b, stride=s, padding=1)
-    dy = torch.randn(ref.shape, generator=_g(4)).to(dev).to(torch.bfloat16)
-    gx, gw = torch.autograd.grad(ref, (xr, wr), dy.float())
-    return x, w, b, ref.detach(), dy.permute(0, 2, 3, 1).contiguous(), gx, gw
-
-
-@pytest.mark.parametrize("case", TC_CASES)
-def test_tc_conv3x3_fwd_dgrad_wgrad(dev, case):
-    from cvad_b200.ops import _call, _ptr, _st
-    N, H, W, Ci, Co, s = case
-    x, w, b, ref, dy, gx, gw = _tc_inputs(dev, *case)
-    Ho, Wo = ref.shape[2], ref.shape[3]
-    wf = torch.empty(Co, 9 * Ci, device=dev, dtype=torch.bfloat16)
-    wd = torch.empty(Ci, 9 * Co, device=dev, dtype=torch.bfloat16)
-    _call("cvad_pack_w3x3_bf16", _ptr(w), Co, Ci, _ptr(wf), _ptr(wd), _st())
-    y = torch.empty(N, Ho, Wo, Co, device=dev, dtype=torch.bfloat16)
-    _call("cvad_conv3x3_fwd_bf16", _ptr(x), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _st())
-    torch.cuda.synchronize()
-    e_f = rel(y.float().permute(0, 3, 1, 2), ref)
-    dx = torch.empty(N, H, W, Ci, device=dev, dtype=torch.bfloat16)
-    _call("cvad_conv3x3_dgrad_bf16", _ptr(dy), _ptr(wd), _ptr(dx), N, H, W, Ci, Co, s, _st())
-    torch.cuda.synchronize()
-    e_d = rel(dx.float().permute(0, 3, 1, 2), gx)
-    dw = torch.zeros(Co, Ci, 3, 3, device=dev)
-    _call("cvad_conv3x3_wgrad_bf16", _ptr(x), _ptr(dy), _ptr(dw), N, H, W, Ci, Co, s, _st())
-    torch.cuda.synchronize()
-    e_w = rel(dw, gw)
-    print(f"[tc] {case}: fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e}")
-    assert e_f < 1e-2 and e_d < 1e-2 and e_w < 1e-3
-
-
-def test_nhwc_bn_pool_kernels(dev):
-    from cvad_b200 import ops
-    from cvad_b200.ops import _call, _ptr, _st
-    N, H, W, C = 3, 9, 14, 64
-    xr = (torch.randn(N, C, H, W, generator=_g(1)) * 2 + 1).to(dev)
-    x = xr.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
-    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
-    gam = (torch.rand(C, generator=_g(2)) + 0.5).to(dev).requires_grad_(True)
-    bet = torch.randn(C, generator=_g(3)).to(dev).requires_grad_(True)
-    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
-    rm2, rv2 = rm.clone(), rv.clone()
-    ref = F.relu(F.batch_norm(xr, rm, rv, gam, bet, True, 0.1, 1e-5))
-    mean, invstd = torch.empty(C, device=dev), torch.empty(C, device=dev)
-    nbt = torch.tensor(0, device=dev)
-    P = N * H * W
-    _call("cvad_bn_stats_nhwc_bf16", _ptr(x), P, C, _ptr(ops.bn_workspace(dev, C)), 1e-5, 0.1, _ptr(mean), _ptr(invstd), _ptr(rm2), _ptr(rv2),
-          _ptr(nbt), _st())
-    y = torch.empty_like(x)
-    _call("cvad_bn_apply_relu_nhwc_bf16", _ptr(x), _ptr(y), P, C, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), _st())
-    assert rel(rm2, rm) < 1e-4 and rel(rv2, rv) < 1e-4
-    assert rel(y.float().permute(0, 3, 1, 2), ref) < 1e-2
-    dact = torch.randn(N, H, W, C, generator=_g(5)).to(dev).to(torch.bfloat16)
-    gr = torch.autograd.grad(ref, (xr, gam, bet), dact.float().permute(0, 3, 1, 2))
-    dx = torch.empty_like(x)
-    dg, db = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
-    _call("cvad_bn_relu_bwd_nhwc_bf16", _ptr(x), _ptr(dact), _ptr(dx), P, C, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), 1,
-          _ptr(ops.bn_workspace(dev, C)), _ptr(dg), _ptr(db), _st())
-    assert rel(dx.float().permute(0, 3, 1, 2), gr[0]) < 1e-2
-    assert rel(dg, gr[1]) < 1e-3 and rel(db, gr[2]) < 1e-3
-    # adaptive average pool to (4,6) and back
-    feats = torch.empty(N, C, 4, 6, device=dev)
-    _call("cvad_avgpool_nhwc_bf16_fwd", _ptr(x), N, H, W, C, 4, 6, _ptr(feats), _st())
-    xr2 = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
-    pr = F.adaptive_avg_pool2d(xr2, (4, 6))
-    assert rel(feats, pr) < 1e-5
-    go = torch.randn(N, C, 4, 6, generator=_g(6)).to(dev)
-    (gxr,) = torch.autograd.grad(pr, xr2, go)
-    dxp = torch.empty_like(x)
-    _call("cvad_avgpool_nhwc_bf16_bwd", _ptr(go), N, H, W, C, 4, 6, _ptr(dxp), _st())
-    assert rel(dxp.float().permute(0, 3, 1, 2), gxr) < 1e-2
-    # stem: relu(bn) + maxpool(3,2,1), NCHW fp32 -> NHWC bf16
-    y1 = torch.randn(2, 32, 21, 30, generator=_g(7)).to(dev) * 3
-    m1, i1 = torch.randn(32, generator=_g(8)).to(dev), (torch.rand(32, generator=_g(9)) + 0.5).to(dev)
-    g1, b1 = (torch.rand(32, generator=_g(10)) - 0.3).to(dev), torch.randn(32, generator=_g(11)).to(dev)
-    sref = F.max_pool2d(F.relu((y1 - m1.view(1, -1, 1, 1)) * (i1 * g1).view(1, -1, 1, 1) + b1.view(1, -1, 1, 1)), 3, 2, 1)
-    so = torch.empty(2, sref.shape[2], sref.shape[3], 32, device=dev, dtype=torch.bfloat16)
-    _call("cvad_stem_bn_relu_maxpool_bf16", _ptr(y1), 2, 32, 21, 30, _ptr(m1), _ptr(i1), _ptr(g1), _ptr(b1), _ptr(so), _st())
-    assert rel(so.float().permute(0, 3, 1, 2), sref) < 1e-2
