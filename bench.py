@@ -33,6 +33,10 @@ PER_GPU_BATCH = 32
 # algorithmic FLOPs (2*MAC) per frame of the eight 3x3 convolutions: forward, and forward+dgrad+wgrad
 CONV_FWD_MFLOP = [99.53, 99.53, 49.77, 99.53, 50.87, 101.74, 56.62, 113.25]
 CONV_TRAIN_MFLOP = sum(CONV_FWD_MFLOP) * 3 - CONV_FWD_MFLOP[0]      # layer1.0 needs no data-gradient (frozen stem below it)
+# compulsory HBM bytes of the same 23 calls for 512 frames: every operand read once and every result written once in bf16 over the
+# logical (unpadded) tensors; weights and weight-gradients are negligible.  (elements per frame of each layer's input / output)
+_CONV_IO = [(172800, 172800), (172800, 172800), (172800, 86400), (86400, 86400), (86400, 44160), (44160, 44160), (44160, 24576), (24576, 24576)]
+CONV_ALG_BYTES = sum(2 * 512 * ((i + o) + (i + o) + ((i + o) if k else 0)) for k, (i, o) in enumerate(_CONV_IO))
 
 
 def peaks():
@@ -41,6 +45,24 @@ def peaks():
         d = json.load(open(p))
         return d.get("bf16_tflops_sustained", 1341.2), d.get("hbm_gbs", 6499.0), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+def conv_family_traffic():
+    """DRAM bytes the convolution family moves per 512-frame step, from the committed ncu capture (tools/conv_traffic.py)."""
+    p = os.path.join(ROOT, "profiles", "conv_family_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    return d.get("bytes_per_step"), d.get("source")
+
+
+_T0 = time.time()
+
+
+def trace(msg):
+    """Stage markers on stderr (CVAD_BENCH_TRACE=1): where every rank is, should a multi-GPU run stall."""
+    if os.environ.get("CVAD_BENCH_TRACE", "0") == "1":
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 class ClockSampler(threading.Thread):
@@ -129,7 +151,9 @@ def run_ours(args):
     from cvad_b200.ma import CausalAnomalyDetector, MATrainer
     from cvad_b200.parallel import DataParallel, init_from_env
 
+    trace("imports done")
     rank, local, world = init_from_env()
+    trace(f"process group up (world {world})")
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
     torch.manual_seed(1234 + rank)
@@ -138,6 +162,8 @@ def run_ours(args):
     tr = MATrainer(CausalAnomalyDetector(), dev, precision=args.precision, dp=dp)
     if dp is not None:
         dp.broadcast_parameters(tr.optimizer.arena)
+        torch.cuda.synchronize()
+        trace("parameters broadcast")
     tr.model.train()
     x_host, y_host = synth_batch(B, 1234 + rank)
     x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
@@ -156,7 +182,9 @@ def run_ours(args):
             return comp
     else:
         # the whole step (zero_grad, forward, loss, backward, all-reduce, clip+AdamW) is one CUDA graph
+        trace("batch resident; capturing the step")
         gs = tr.graphed_train_step(x_dev, y_dev)
+        trace("step captured")
         launches_per_step = gs.launches
         x_dev, y_dev = gs.static_inputs
 
@@ -166,6 +194,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(x_dev, y_dev)
     barrier()
+    trace("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -178,6 +207,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    trace(f"timed region done ({ms / args.steps:.3f} ms/step)")
     launches = ops.LAUNCHES[0] - n0
     # ---- end to end: pinned host batch -> H2D -> step -> D2H loss, through the public trainer API
     # Every step's batch starts in pinned host memory and its loss is read back to the host.  With the graphed trainer the
@@ -203,6 +233,7 @@ def run_ours(args):
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
+    trace(f"e2e region done ({ms_e2e / args.steps:.3f} ms/step)")
     sampler.stop_flag = True
     # ---- dominant kernel family, timed live with CUDA events around every call (eager launches of the same step)
     conv_names = {"cvad_flat_conv3x3_fwd_bf16", "cvad_flat_conv3x3_dgrad_bf16", "cvad_flat_conv3x3_wgrad_bf16"} if args.precision == "bf16" \
@@ -223,9 +254,11 @@ def run_ours(args):
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
+    trace("kernel probe done")
     if rank != 0:
         return
     tf_peak, hbm_peak, src = peaks()
+    traffic, traffic_src = conv_family_traffic() if args.precision == "bf16" else (None, None)
     ms_step = ms / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_value = world * B / (ms_e2e / args.steps / 1e3)
@@ -245,7 +278,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 8, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_step": CONV_ALG_BYTES,
                      "kernel": "flatconv / flatwgrad TMA+tcgen05 3x3 convolutions (fwd+dgrad+wgrad, 8 layers)" if args.precision == "bf16"
                      else "conv_gemm_kernel fp32",
                      "peak_source": src, "launches_per_step": conv_launches, "ms_per_step": conv_total_ms,

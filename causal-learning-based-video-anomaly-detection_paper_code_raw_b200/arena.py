@@ -135,6 +135,11 @@ class FusedAdam(torch.optim.Optimizer):
     def step(self, closure=None):
         if self.pre_step_hook is not None:
             self.pre_step_hook(self.arena)
+        return self.step_local()
+
+    @torch.no_grad()
+    def step_local(self):
+        """The fused grad-norm + clip + Adam(W) kernels alone (no data-parallel hook): what runs after the all-reduce."""
         g = self.param_groups[0]
         self.arena.step(g["lr"], g["betas"], g["eps"], g["weight_decay"], self.decoupled, self.clip_mode, self.max_norm,
                         self.clip_threshold, self.nan_mode, self.grad_scale)

@@ -133,6 +133,10 @@ __global__ void pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, 
   }
 }
 
+constexpr int PAD_REP = 16, PAD_REP_MAXC = 512;
+__device__ double g_pad_rep[PAD_REP * 2 * PAD_REP_MAXC];      // zero-initialised; every launch leaves it zero again
+__device__ unsigned int g_pad_ticket = 0u;
+
 // per-channel reductions over the INTERIOR of raw.  !BWD: sum x, sum x^2.  BWD: g = dact*(pre>0): sum g, sum g*xhat.
 // dact is plain (PHASE=0) or phase planes (PHASE=1).
 template <bool BWD, int PHASE>
@@ -199,13 +203,37 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
   __syncthreads();
+  // Cross-CTA combine.  ~1200 CTAs adding into the same 2*C addresses serialise in the L2 atomic unit (~15 us of tail per
+  // launch, profiles/r01e): each CTA adds into one of PAD_REP replicas instead, and the last CTA to finish (ticket counter)
+  // folds the replicas into ws and re-zeroes them.  Calls are stream-ordered (as for ws itself), so one scratch suffices.
+  const bool replicated = C <= PAD_REP_MAXC;
+  double* dst = replicated ? g_pad_rep + (size_t)(blockIdx.x & (PAD_REP - 1)) * (2 * PAD_REP_MAXC) : ws;
   for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
     const int c = j % C, which = j / C;
     const int g2 = c >> 3, i = c & 7;
     double acc = 0.0;
     for (int r = 0; r < slots; ++r) acc += (double)red[(r * groups + g2) * 16 + which * 8 + i];
-    atomicAdd(ws + which * C + c, acc);
+    atomicAdd(dst + which * C + c, acc);
   }
+  if (!replicated) return;
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_pad_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < PAD_REP; ++r) {
+      double* p = g_pad_rep + (size_t)r * (2 * PAD_REP_MAXC) + j;
+      acc += __ldcg(p);
+      __stcg(p, 0.0);
+    }
+    ws[j] += acc;
+  }
+  if (threadIdx.x == 0) g_pad_ticket = 0u;
 }
 
 // ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)

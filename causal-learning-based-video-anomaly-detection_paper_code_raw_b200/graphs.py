@@ -23,8 +23,12 @@ class GraphedStep:
     ``__call__(*inputs)`` copies the inputs into the static buffers (an H2D copy when they live in pinned host memory),
     replays the graph and returns the static output tensors (valid until the next replay)."""
 
-    def __init__(self, step_fn, example_inputs, mutated=(), warmup: int = 3, pre_replay=None):
+    def __init__(self, step_fn, example_inputs, mutated=(), warmup: int = 3, pre_replay=None, between=None, tail_fn=None):
+        """``between`` / ``tail_fn`` split the step in two graphs around an eagerly issued call: graph(step_fn) ->
+        between() -> graph(tail_fn).  The data-parallel trainer uses it to keep the NCCL gradient all-reduce OUT of the
+        captured graphs (``between``) while forward/backward and the fused optimizer are each one graph launch."""
         self.pre_replay = pre_replay
+        self.between, self.tail_graph = between, None
         self.static_inputs = [torch.empty_like(t, device=t.device if t.is_cuda else torch.cuda.current_device()) for t in example_inputs]
         for s, t in zip(self.static_inputs, example_inputs):
             s.copy_(t)
@@ -35,6 +39,10 @@ class GraphedStep:
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 step_fn(*self.static_inputs)
+                if between is not None:
+                    between()
+                if tail_fn is not None:
+                    tail_fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -45,8 +53,22 @@ class GraphedStep:
         n0 = ops.LAUNCHES[0]
         with torch.cuda.graph(self.graph):
             out = step_fn(*self.static_inputs)
+        if tail_fn is not None:
+            self.tail_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.tail_graph):
+                tail_fn()
         self.launches = ops.LAUNCHES[0] - n0          # cvad ABI calls inside one replay
         self.outputs = out if isinstance(out, tuple) else (out,)
+
+    def _replay(self):
+        if self.pre_replay is not None:
+            self.pre_replay()
+        self.graph.replay()
+        if self.between is not None:
+            self.between()
+        if self.tail_graph is not None:
+            self.tail_graph.replay()
+        ops.LAUNCHES[0] += self.launches
 
     # ---- input prefetch: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes
     def _init_prefetch(self):
@@ -72,18 +94,12 @@ class GraphedStep:
         for s, st in zip(self.static_inputs, self.staging):
             s.copy_(st, non_blocking=True)                      # device-to-device, ~55 us for the 177 MB batch
         self.ev_free.record(cur)
-        if self.pre_replay is not None:
-            self.pre_replay()
-        self.graph.replay()
-        ops.LAUNCHES[0] += self.launches
+        self._replay()
         return self.outputs
 
     def __call__(self, *inputs):
         for s, t in zip(self.static_inputs, inputs):
             if t is not s:
                 s.copy_(t, non_blocking=True)
-        if self.pre_replay is not None:
-            self.pre_replay()
-        self.graph.replay()
-        ops.LAUNCHES[0] += self.launches
+        self._replay()
         return self.outputs

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import collections.abc
 import math
+import os
 
 import numpy as np
 import torch
@@ -326,11 +327,15 @@ class MATrainer:
         return ops.ma_loss(outputs["direct_predictions"], outputs["anomaly_scores"], outputs["causal_anomaly_scores"], d["kl_losses"],
                            labels, self.optimizer.arena.header[0:1])
 
-    def train_step(self, videos, labels):
+    def forward_backward(self, videos, labels):
         self.optimizer.zero_grad()
         outputs = self.model(videos)
         loss, comp = self.loss_on_device(outputs, labels)
         loss.backward()
+        return comp, outputs
+
+    def train_step(self, videos, labels):
+        comp, outputs = self.forward_backward(videos, labels)
         self.optimizer.step()
         return comp, outputs
 
@@ -344,11 +349,21 @@ class MATrainer:
         Returns a callable ``(videos, labels) -> (loss components (5,), anomaly_scores (B,))``."""
         from .graphs import GraphedStep
 
+        opt = self.optimizer
+        opt.sync_lr_to_device()
+        if opt.pre_step_hook is not None and os.environ.get("CVAD_NCCL_IN_GRAPH", "0") != "1":
+            # data parallel: graph(zero_grad..backward) -> eager NCCL all-reduce of the gradient arena -> graph(clip+AdamW).
+            # The collective stays outside the captured graphs (NCCL's graph-mode buffer registration stalled an 8-rank run).
+            def fwd_bwd(x, y):
+                comp, out = self.forward_backward(x, y)
+                return comp, out["anomaly_scores"]
+            return GraphedStep(fwd_bwd, (videos, labels), self.mutated_tensors(), pre_replay=opt.sync_lr_to_device,
+                               between=lambda: opt.pre_step_hook(opt.arena), tail_fn=opt.step_local)
+
         def step(x, y):
             comp, out = self.train_step(x, y)
             return comp, out["anomaly_scores"]
-        self.optimizer.sync_lr_to_device()
-        return GraphedStep(step, (videos, labels), self.mutated_tensors(), pre_replay=self.optimizer.sync_lr_to_device)
+        return GraphedStep(step, (videos, labels), self.mutated_tensors(), pre_replay=opt.sync_lr_to_device)
 
     @torch.no_grad()
     def eval_step(self, videos, labels):

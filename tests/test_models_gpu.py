@@ -485,9 +485,11 @@ def test_create_unsupervised_labels(dev, gold):
 
 
 # --------------------------------------------------------------------------------------------------------- CUDA-graph step
-def test_graphed_train_step_matches_eager(dev):
+@pytest.mark.parametrize("split", [False, True])
+def test_graphed_train_step_matches_eager(dev, split):
     """One CUDA graph per step (graphs.GraphedStep): building it must not advance training, replays must equal eager steps, and a
-    scheduler's LR change must reach the captured optimizer kernel through the device-side LR."""
+    scheduler's LR change must reach the captured optimizer kernel through the device-side LR.  ``split`` = the data-parallel
+    form: graph(zero_grad..backward) -> eager hook (the NCCL all-reduce; here an identity op on the arena) -> graph(clip+AdamW)."""
     from cvad_b200.ma import CausalAnomalyDetector, MATrainer
     from cvad_b200.noise import FixedNoise
     B, T, H, W = 2, 4, 64, 96
@@ -507,7 +509,15 @@ def test_graphed_train_step_matches_eager(dev):
     ys = [torch.tensor([0, 1], device=dev), torch.tensor([1, 1], device=dev), torch.tensor([0, 0], device=dev)]
     eager, eager2, graphed = make(), make(), make()
     p0 = graphed.optimizer.arena.p.clone()
+    if split:
+        hook_calls = [0]
+
+        def hook(arena):
+            hook_calls[0] += 1
+            arena.g.mul_(1.0)
+        graphed.optimizer.pre_step_hook = hook
     gs = graphed.graphed_train_step(xs[0], ys[0])
+    assert (gs.tail_graph is not None) == split
     assert torch.equal(graphed.optimizer.arena.p, p0), "capturing the graph must not change the parameters"
     assert gs.launches > 50
     for i in range(3):
@@ -518,6 +528,8 @@ def test_graphed_train_step_matches_eager(dev):
         eager2.train_step(xs[i], ys[i])
         cg, _ = gs(xs[i], ys[i])
         assert rel(cg, ce, floor=1e-6) < 2e-3, (i, cg, ce)          # fp32 atomics reorder between runs; losses agree closely
+    if split:
+        assert hook_calls[0] == 3 + 3, hook_calls       # 3 warm-up executions + one eager call per replay, none at capture
     pe, pe2, pg = eager.optimizer.arena.p, eager2.optimizer.arena.p, graphed.optimizer.arena.p
     moved = float((pe - p0).abs().mean())
     noise = float((pe - pe2).abs().mean())         # run-to-run spread of two EAGER runs (Adam amplifies atomics round-off)
