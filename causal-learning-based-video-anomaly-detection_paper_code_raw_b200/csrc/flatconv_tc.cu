@@ -40,8 +40,15 @@ constexpr int FC_BOX = 256;          // rows per big TMA box
 constexpr size_t FC_SMEM_BUDGET = 226 * 1024;
 
 // optional profiling hook (tools/conv_probe.py): when set, the MMA-issuing warp of every CTA records the cycles it spent
-// waiting on each barrier class: dbg[cta*8 + {0 total, 1 src_full, 2 w_full, 3 acc_empty, 4 work items}]
+// waiting on each barrier class: dbg[cta*8 + {0 total, 1 src_full, 2 w_full, 3 acc_empty, 4 work items, 5 entry ns, 6 loop start ns, 7 loop end ns}]
 __device__ long long* g_fc_debug = nullptr;
+constexpr int FC_DBG_CTAS = 148;     // buffer: FC_DBG_CTAS x 8 per-CTA records + {min entry ns (preset to max), max exit ns}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct FcUnit {
   int row_off;          // first segment row relative to the tile's first output row (may be negative)
@@ -76,6 +83,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
       bar_acc_empty[FC_MAX_SLOTS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float s_bias[N];
+  const long long t_entry = g_fc_debug ? (long long)globaltimer_ns() : 0;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t seg_bytes = (uint32_t)p.seg_rows * ROWB;
@@ -153,6 +161,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     long long* dbg = g_fc_debug;
     long long t_src = 0, t_w = 0, t_acc = 0, n_items = 0;
     const long long t_begin = dbg ? clock64() : 0;
+    const long long t_loop_ns = dbg ? (long long)globaltimer_ns() : 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       ++n_items;
       for (int u = 0; u < n_units; ++u) {
@@ -223,6 +232,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     if (dbg && lane == 0) {
       long long* d = dbg + (long long)blockIdx.x * 8;
       d[0] = clock64() - t_begin; d[1] = t_src; d[2] = t_w; d[3] = t_acc; d[4] = n_items;
+      d[5] = t_entry; d[6] = t_loop_ns; d[7] = (long long)globaltimer_ns();      // kernel entry / MMA loop start / MMA loop end (ns)
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (TMEM lanes 32*(warp-4) ..)
@@ -273,11 +283,17 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (g_fc_debug && tid == 0) {      // grid-wide first entry / last exit (ns) behind the per-CTA records
+    atomicMin((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8, (unsigned long long)t_entry);
+    atomicMax((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8 + 1, globaltimer_ns());
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-inline int n_block_of(int nout) { return nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32); }
+// Output-channel block = the MMA's N.  One M128 x N x K16 MMA streams 4 KB of A plus N*32 B of B from shared memory at ~80-90 B/cycle
+// (profiles/r01g_flatconv_L0_ncu_full.md), so it is operand-bound below N = 256: take the widest N the layer allows.
+inline int n_block_of(int nout) { return nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32)); }
 
 template <int ROWB, int N>
 int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk, long long w_rows, FcParams& p, const float* bias,
@@ -291,7 +307,7 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   }
   // rows per work item: as many 128-row sub-tiles as TMEM and shared memory allow while the machine stays filled
   static const int cand[] = {8, 6, 4, 3, 2, 1};
-  const int sub_max = N == 32 ? 8 : 4;
+  const int sub_max = N == 32 ? 8 : (N == 256 ? 2 : 4);     // TMEM: 512 columns = sub x N accumulators (x2 when they double-buffer)
   p.sub = 0;
   for (int sub : cand) {
     if (sub > sub_max) continue;
@@ -345,10 +361,12 @@ int run_flat(const void* src, long long src_rows, int K, const void* wpk, int No
   if (rowb == 64) {
     if (n == 32) return launch_flatconv<64, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
     if (n == 64) return launch_flatconv<64, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+    if (n == 256) return launch_flatconv<64, 256>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
     return launch_flatconv<64, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
   }
   if (n == 32) return launch_flatconv<128, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
   if (n == 64) return launch_flatconv<128, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+  if (n == 256) return launch_flatconv<128, 256>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
   return launch_flatconv<128, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
 }
 

@@ -77,7 +77,19 @@ struct PadGeo {
   int N, H, W, C;       // interior geometry of the raw / plain tensor
   int Hq, Wq;           // phase-plane geometry (Ho+2, Wo+2) when a phase layout is involved
   int lg;               // log2(C/8)
+  unsigned mulW, shrW, mulH, shrH;     // x / W and x / H as umulhi(x, mul) >> shr for 0 <= x < 2^31 (mul = 0: divisor 1)
 };
+
+// division by a launch constant without the ~20-instruction emulated divide: mul = ceil(2^(31+ceil(log2 d)) / d)
+inline void fast_div_init(unsigned d, unsigned& mul, unsigned& shr) {
+  if (d <= 1) { mul = 0; shr = 0; return; }
+  unsigned lg = 0;
+  while ((1u << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  mul = (unsigned)(((1ull << p) + d - 1) / d);
+  shr = p - 32;
+}
+__device__ __forceinline__ int fast_div(int x, unsigned mul, unsigned shr) { return mul ? (int)(__umulhi((unsigned)x, mul) >> shr) : x; }
 
 __device__ __forceinline__ long long plain_row(const PadGeo& g, int n, int hp, int wp) { return ((long long)n * (g.H + 2) + hp) * (g.W + 2) + wp; }
 __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, int wp) {
@@ -86,10 +98,13 @@ __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, i
 }
 
 // relu(bn(raw)) -> act.  PHASE=0: plain padded act, zero border.  PHASE=1: four phase planes (zeros where no pixel maps).
+// Block = 256 threads, two 16-byte vectors per thread and pass (v = tid, tid + 256): every padded row of the backbone
+// (368..448 vectors) is one pass with all loads issued before the first use.  PHASE=1 handles the two column-phase planes
+// (a,0) and (a,1) of one plane row in the same block, so the raw row both of them sample is fetched from HBM once.
 template <int PHASE>
-__global__ void pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ act, PadGeo g,
-                                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta) {
+__global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ act, PadGeo g,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta) {
   const int groups = 1 << g.lg;
   const int cg = threadIdx.x & (groups - 1);
   float sc[8], sh[8];
@@ -100,35 +115,55 @@ __global__ void pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, 
     sh[i] = beta[c] - mean[c] * sc[i];
   }
   const int Hp = g.H + 2, Wp = g.W + 2;
-  const int rows = PHASE ? 4 * g.N * g.Hq : g.N * Hp;
+  const int items = PHASE ? 2 * g.N * g.Hq : g.N * Hp;          // PHASE: (a, n, i) with both b planes per item
   const int rowlen = (PHASE ? g.Wq : Wp) << g.lg;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    int n, hp, a = 0, b = 0;
+  const int span = PHASE ? 2 * rowlen : rowlen;
+  for (int r = blockIdx.x; r < items; r += gridDim.x) {
+    int n, hp, a = 0;
+    long long row0, row1 = 0;                                      // first vector of the output row(s)
     if (PHASE) {
       const int i = r % g.Hq;
       const int t = r / g.Hq;
       n = t % g.N;
-      const int pl = t / g.N;
-      a = pl >> 1; b = pl & 1;
+      a = t / g.N;
       hp = 2 * (i - 1) + a;
+      row0 = ((((long long)(2 * a) * g.N + n) * g.Hq) + i) * rowlen;
+      row1 = ((((long long)(2 * a + 1) * g.N + n) * g.Hq) + i) * rowlen;
     } else {
       hp = r % Hp;
       n = r / Hp;
+      row0 = (long long)r * rowlen;
     }
     const bool row_ok = hp >= 1 && hp <= g.H;
-    uint4* dst = reinterpret_cast<uint4*>(act) + (long long)r * rowlen;
-    for (int v = threadIdx.x; v < rowlen; v += blockDim.x) {
-      const int j = v >> g.lg;
-      const int wp = PHASE ? 2 * (j - 1) + b : j;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (row_ok && wp >= 1 && wp <= g.W) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + ((plain_row(g, n, hp, wp) << g.lg) + cg)), f);
+    for (int v0 = threadIdx.x; v0 < span; v0 += 512) {
+      uint4 x[2];
+      bool in[2], ok[2];
+      long long dst[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
-        o = pack8(f);
+      for (int u = 0; u < 2; ++u) {
+        const int v = v0 + u * 256;
+        in[u] = v < span;
+        const int b = PHASE && v >= rowlen ? 1 : 0;
+        const int vv = v - b * rowlen;
+        const int j = vv >> g.lg;
+        const int wp = PHASE ? 2 * (j - 1) + b : j;
+        ok[u] = in[u] && row_ok && wp >= 1 && wp <= g.W;
+        dst[u] = (b ? row1 : row0) + vv;
+        if (ok[u]) x[u] = __ldg(reinterpret_cast<const uint4*>(raw) + ((plain_row(g, n, hp, wp) << g.lg) + cg));
       }
-      dst[v] = o;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!in[u]) continue;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          float f[8];
+          unpack8(x[u], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
+          o = pack8(f);
+        }
+        reinterpret_cast<uint4*>(act)[dst[u]] = o;
+      }
     }
   }
 }
@@ -140,25 +175,31 @@ __device__ unsigned int g_pad_ticket = 0u;
 // per-channel reductions over the INTERIOR of raw.  !BWD: sum x, sum x^2.  BWD: g = dact*(pre>0): sum g, sum g*xhat.
 // dact is plain (PHASE=0) or phase planes (PHASE=1).
 template <bool BWD, int PHASE>
-__global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact, PadGeo g,
-                                  const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                  const float* __restrict__ beta, double* __restrict__ ws) {
+__global__ void __launch_bounds__(256, 4) pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact, PadGeo g,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            double* __restrict__ ws) {
   extern __shared__ float red[];             // [blockDim][16]
   const int groups = 1 << g.lg;
   const int cg = threadIdx.x & (groups - 1), slot = threadIdx.x >> g.lg, slots = blockDim.x >> g.lg;
   const int C = g.C;
-  float s[8], q[8], mu[8], is[8], ga[8], be[8];
+  // BWD: the ReLU gate is (x*a + b > 0) with a = gamma*invstd, b = beta - mean*a; the sums are taken over g and g*x and turned into
+  // sum g*xhat = invstd * (sum g*x - mean * sum g) in the fp64 combine below (half the per-thread state of carrying xhat).
+  float s[8], q[8], ga[8], gb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     s[i] = 0.f; q[i] = 0.f;
-    if (BWD) { mu[i] = mean[cg * 8 + i]; is[i] = invstd[cg * 8 + i]; ga[i] = gamma[cg * 8 + i]; be[i] = beta[cg * 8 + i]; }
+    if (BWD) {
+      ga[i] = gamma[cg * 8 + i] * invstd[cg * 8 + i];
+      gb[i] = beta[cg * 8 + i] - mean[cg * 8 + i] * ga[i];
+    }
   }
   // Interior pixels as one flat index space p = (n*H + h)*W + w, strided over the block's pixel slots; four independent
-  // 16-byte loads (eight in the backward) are in flight per thread before any is consumed.
+  // 16-byte loads are in flight per thread before any is consumed.
   const int P = g.N * g.H * g.W;               // < 2^31 (checked by the launcher)
   const int chunk = (P + gridDim.x - 1) / gridDim.x;
   const int p_end = min(P, (int)(blockIdx.x + 1) * chunk);
-  constexpr int U = 4;
+  constexpr int U = BWD ? 2 : 4;     // 16-byte loads in flight per thread and tensor (the backward reads two tensors)
   for (int p0 = blockIdx.x * chunk + slot; p0 < p_end; p0 += U * slots) {
     uint4 xv[U], dv[U];
     bool ok[U];
@@ -167,9 +208,9 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
       const int pp = p0 + u * slots;
       ok[u] = pp < p_end;
       if (ok[u]) {
-        const int t = pp / g.W;
+        const int t = fast_div(pp, g.mulW, g.shrW);
         const int w = pp - t * g.W;
-        const int n = t / g.H;
+        const int n = fast_div(t, g.mulH, g.shrH);
         const int h = t - n * g.H;
         const long long row = plain_row(g, n, h + 1, w + 1);
         xv[u] = __ldg(reinterpret_cast<const uint4*>(raw) + ((row << g.lg) + cg));
@@ -192,10 +233,9 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
         unpack8(dv[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] - mu[i]) * is[i];
-          const float gg = fmaf(xh, ga[i], be[i]) > 0.f ? d[i] : 0.f;
+          const float gg = fmaf(f[i], ga[i], gb[i]) > 0.f ? d[i] : 0.f;
           s[i] += gg;
-          q[i] = fmaf(gg, xh, q[i]);
+          q[i] = fmaf(gg, f[i], q[i]);
         }
       }
     }
@@ -203,17 +243,21 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
 #pragma unroll
   for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s[i]; red[threadIdx.x * 16 + 8 + i] = q[i]; }
   __syncthreads();
-  // Cross-CTA combine.  ~1200 CTAs adding into the same 2*C addresses serialise in the L2 atomic unit (~15 us of tail per
-  // launch, profiles/r01e): each CTA adds into one of PAD_REP replicas instead, and the last CTA to finish (ticket counter)
-  // folds the replicas into ws and re-zeroes them.  Calls are stream-ordered (as for ws itself), so one scratch suffices.
+  // Cross-CTA combine.  Hundreds of CTAs adding into the same 2*C addresses serialise in the L2 atomic unit: each CTA adds into one
+  // of PAD_REP replicas instead, and the last CTA to finish (ticket counter) folds the replicas into ws and re-zeroes them.  Calls
+  // are stream-ordered (as for ws itself), so one scratch suffices.
   const bool replicated = C <= PAD_REP_MAXC;
   double* dst = replicated ? g_pad_rep + (size_t)(blockIdx.x & (PAD_REP - 1)) * (2 * PAD_REP_MAXC) : ws;
-  for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) {
-    const int c = j % C, which = j / C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g2 = c >> 3, i = c & 7;
-    double acc = 0.0;
-    for (int r = 0; r < slots; ++r) acc += (double)red[(r * groups + g2) * 16 + which * 8 + i];
-    atomicAdd(dst + which * C + c, acc);
+    double a0 = 0.0, a1 = 0.0;
+    for (int r = 0; r < slots; ++r) {
+      a0 += (double)red[(r * groups + g2) * 16 + i];
+      a1 += (double)red[(r * groups + g2) * 16 + 8 + i];
+    }
+    if (BWD) a1 = (a1 - (double)mean[c] * a0) * (double)invstd[c];
+    atomicAdd(dst + c, a0);
+    atomicAdd(dst + C + c, a1);
   }
   if (!replicated) return;
   __shared__ int s_last;
@@ -238,19 +282,26 @@ __global__ void pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const _
 
 // ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)
 template <int PHASE>
-__global__ void pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
-                                             __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
-                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                             const float* __restrict__ beta, const double* __restrict__ ws, double count, int training) {
+__global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
+                                                                    __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
+                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, const double* __restrict__ ws, double count,
+                                                                    int training) {
   const int groups = 1 << g.lg;
   const int cg = threadIdx.x & (groups - 1);
-  float mu[8], is[8], ga[8], be[8], mg[8], mgx[8];
+  // With a = gamma*invstd, b = beta - mean*a (the forward's scale/shift), g = dact*(x*a + b > 0), mg = mean(g), mgx = mean(g*xhat):
+  //   draw = a*(g - mg - xhat*mgx) = a*g - k0 - k1*x,   k1 = a*mgx*invstd,  k0 = a*mg - k1*mean     (eval mode: k0 = k1 = 0)
+  float ca[8], cb[8], k0[8], k1[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cg * 8 + i;
-    mu[i] = mean[c]; is[i] = invstd[c]; ga[i] = gamma[c]; be[i] = beta[c];
-    mg[i] = training ? (float)(ws[c] / count) : 0.f;
-    mgx[i] = training ? (float)(ws[g.C + c] / count) : 0.f;
+    const float is = invstd[c], mu = mean[c];
+    ca[i] = gamma[c] * is;
+    cb[i] = beta[c] - mu * ca[i];
+    const float mg = training ? (float)(ws[c] / count) : 0.f;
+    const float mgx = training ? (float)(ws[g.C + c] / count) : 0.f;
+    k1[i] = ca[i] * mgx * is;
+    k0[i] = ca[i] * mg - k1[i] * mu;
   }
   const int Hp = g.H + 2, Wp = g.W + 2;
   const int rows = g.N * Hp, rowlen = Wp << g.lg;
@@ -258,23 +309,38 @@ __global__ void pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ r
     const int hp = r % Hp, n = r / Hp;
     const bool row_ok = hp >= 1 && hp <= g.H;
     const long long vbase = (long long)r * rowlen;
-    for (int v = threadIdx.x; v < rowlen; v += blockDim.x) {
-      const int wp = v >> g.lg;
-      uint4 o = make_uint4(0, 0, 0, 0);
-      if (row_ok && wp >= 1 && wp <= g.W) {
-        float f[8], d[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(raw) + vbase + v), f);
-        const long long dv = PHASE ? ((phase_row(g, n, hp, wp) << g.lg) + cg) : vbase + v;
-        unpack8(__ldg(reinterpret_cast<const uint4*>(dact) + dv), d);
+    for (int v0 = threadIdx.x; v0 < rowlen; v0 += 512) {
+      uint4 x[2], dd[2];
+      bool in[2], ok[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = (f[i] - mu[i]) * is[i];
-          const float gg = fmaf(xh, ga[i], be[i]) > 0.f ? d[i] : 0.f;
-          f[i] = ga[i] * is[i] * (gg - mg[i] - xh * mgx[i]);
+      for (int u = 0; u < 2; ++u) {
+        const int v = v0 + u * 256;
+        const int wp = v >> g.lg;
+        in[u] = v < rowlen;
+        ok[u] = in[u] && row_ok && wp >= 1 && wp <= g.W;
+        if (ok[u]) {
+          x[u] = __ldg(reinterpret_cast<const uint4*>(raw) + vbase + v);
+          const long long dv = PHASE ? ((phase_row(g, n, hp, wp) << g.lg) + cg) : vbase + v;
+          dd[u] = __ldg(reinterpret_cast<const uint4*>(dact) + dv);
         }
-        o = pack8(f);
       }
-      reinterpret_cast<uint4*>(draw)[vbase + v] = o;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!in[u]) continue;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+          float f[8], d[8];
+          unpack8(x[u], f);
+          unpack8(dd[u], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float gg = fmaf(f[i], ca[i], cb[i]) > 0.f ? d[i] : 0.f;
+            f[i] = fmaf(-k1[i], f[i], fmaf(ca[i], gg, -k0[i]));
+          }
+          o = pack8(f);
+        }
+        reinterpret_cast<uint4*>(draw)[vbase + v0 + u * 256] = o;
+      }
     }
   }
 }
@@ -339,6 +405,44 @@ __global__ void avgpool_pad_bwd_kernel(const float* __restrict__ dout, int N, in
   }
 }
 
+// Same result, one CTA per frame: the frame's (C, OH, OW) gradient is staged in shared memory transposed to [bin][channel], so the
+// strided fp32 reads of the kernel above (32 sectors per warp load) become one coalesced pass, and all index math is 32-bit.
+__global__ void avgpool_pad_bwd_frame_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
+                                             __nv_bfloat16* __restrict__ dx) {
+  extern __shared__ float sd[];              // [OH*OW][C]
+  const int bins = OH * OW, groups = C >> 3, Wp = W + 2, Hp = H + 2;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float* src = dout + ((long long)n * C + c) * bins;
+      for (int b = 0; b < bins; ++b) sd[b * C + c] = __ldg(src + b);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < H * W * groups; t += blockDim.x) {
+      const int cg = t % groups, pix = t / groups;
+      const int w = pix % W, h = pix / W;
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      const int ohc = (h * OH) / H, owc = (w * OW) / W;
+      for (int oh = max(0, ohc - 1); oh <= min(OH - 1, ((h + 1) * OH) / H + 1); ++oh) {
+        const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH);
+        if (h < h0 || h >= h1) continue;
+        for (int ow = max(0, owc - 1); ow <= min(OW - 1, ((w + 1) * OW) / W + 1); ++ow) {
+          const int w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
+          if (w < w0 || w >= w1) continue;
+          const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+          const float4 lo = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * C + cg * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * C + cg * 8 + 4);
+          s[0] = fmaf(lo.x, inv, s[0]); s[1] = fmaf(lo.y, inv, s[1]); s[2] = fmaf(lo.z, inv, s[2]); s[3] = fmaf(lo.w, inv, s[3]);
+          s[4] = fmaf(hi.x, inv, s[4]); s[5] = fmaf(hi.y, inv, s[5]); s[6] = fmaf(hi.z, inv, s[6]); s[7] = fmaf(hi.w, inv, s[7]);
+        }
+      }
+      reinterpret_cast<uint4*>(dx)[(((long long)n * Hp + h + 1) * Wp + w + 1) * groups + cg] = pack8(s);
+    }
+    __syncthreads();
+  }
+}
+
 inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   if (C % 8 || C > 256 || (C / 8) & (C / 8 - 1) || (long long)N * (H + 2) * (W + 2) * 4 > 0x7fffffffLL) return 1;
   g.N = N; g.H = H; g.W = W; g.C = C;
@@ -346,6 +450,8 @@ inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   g.Wq = phase ? (W - 1) / 2 + 3 : 0;
   g.lg = 0;
   while ((8 << g.lg) < C) ++g.lg;
+  fast_div_init((unsigned)W, g.mulW, g.shrW);
+  fast_div_init((unsigned)H, g.mulH, g.shrH);
   return 0;
 }
 
@@ -357,7 +463,7 @@ CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C,
   PadGeo g;
   if (make_geo(g, N, H, W, C, 0)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  int blocks = N * H < 8 * cvad_num_sms() ? N * H : 8 * cvad_num_sms();
+  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();      // one wave (launch bounds: 4 CTAs per SM)
   pad_reduce_kernel<false, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)raw, nullptr, g, nullptr, nullptr, nullptr,
                                                                               nullptr, ws);
   CVAD_LAUNCH_CHECK();
@@ -372,12 +478,12 @@ CVAD_API int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int 
   PadGeo g;
   if (make_geo(g, N, H, W, C, phase_out)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rows = phase_out ? 4 * N * g.Hq : N * (H + 2);
-  const int blocks = rows < 16 * cvad_num_sms() ? rows : 16 * cvad_num_sms();
+  const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
+  const int blocks = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
   if (phase_out)
-    pad_bn_apply_relu_kernel<1><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
+    pad_bn_apply_relu_kernel<1><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
   else
-    pad_bn_apply_relu_kernel<0><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
+    pad_bn_apply_relu_kernel<0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -389,7 +495,7 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   if (make_geo(g, N, H, W, C, phase_in)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  int blocks = N * H < 8 * cvad_num_sms() ? N * H : 8 * cvad_num_sms();
+  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
   if (phase_in)
     pad_reduce_kernel<true, 1><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
   else
@@ -397,12 +503,12 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   CVAD_LAUNCH_CHECK();
   if (draw) {
     const int rows = N * (H + 2);
-    const int ab = rows < 16 * cvad_num_sms() ? rows : 16 * cvad_num_sms();
+    const int ab = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
     if (phase_in)
-      pad_bn_relu_bwd_apply_kernel<1><<<ab, 128, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
+      pad_bn_relu_bwd_apply_kernel<1><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
                                                           training);
     else
-      pad_bn_relu_bwd_apply_kernel<0><<<ab, 128, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
+      pad_bn_relu_bwd_apply_kernel<0><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
                                                           training);
     CVAD_LAUNCH_CHECK();
   }
@@ -422,7 +528,12 @@ CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C
 CVAD_API int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream) {
   long long total = (long long)N * H * W * (C / 8);
   if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;
-  avgpool_pad_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
+  const size_t frame_smem = (size_t)OH * OW * C * sizeof(float);
+  if (frame_smem <= 48 * 1024)
+    avgpool_pad_bwd_frame_kernel<<<N < 8 * cvad_num_sms() ? N : 8 * cvad_num_sms(), 256, frame_smem, (cudaStream_t)stream>>>(
+        dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
+  else
+    avgpool_pad_bwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

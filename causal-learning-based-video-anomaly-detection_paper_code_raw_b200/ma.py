@@ -331,7 +331,8 @@ class MATrainer:
         self.optimizer.zero_grad()
         outputs = self.model(videos)
         loss, comp = self.loss_on_device(outputs, labels)
-        loss.backward()
+        with ops.param_grad_overlap():          # weight/bias-gradient kernels of the dense tail run beside the data-gradient chain
+            loss.backward()
         return comp, outputs
 
     def train_step(self, videos, labels):

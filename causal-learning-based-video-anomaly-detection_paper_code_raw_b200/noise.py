@@ -15,7 +15,8 @@ class DeviceNoise:
         self.generator = generator
 
     def keep_mask(self, name: str, shape, p: float, device) -> torch.Tensor:
-        return (torch.rand(shape, device=device, generator=self.generator) >= p).float()
+        # one launch: Bernoulli(1 - p) keep flags as fp32 (torch.rand(...) >= p followed by .float() is three)
+        return torch.empty(shape, device=device, dtype=torch.float32).bernoulli_(1.0 - p, generator=self.generator)
 
     def uniform(self, name: str, shape, device) -> torch.Tensor:
         return torch.rand(shape, device=device, generator=self.generator)

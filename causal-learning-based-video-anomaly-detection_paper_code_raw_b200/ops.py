@@ -8,7 +8,9 @@ and the fused optimizer see one contiguous buffer); the autograd Functions retur
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
+import os
 
 import torch
 
@@ -40,19 +42,74 @@ def _ptr(t):
 
 TIMED = {}        # bench.py: ABI name -> list of (start_event, end_event); set TIMED_NAMES to enable
 TIMED_NAMES = set()
+TIMED_CAPTURE_ONLY = [False]     # True: bracket the named calls only while a CUDA graph is being captured
 
 
 def _call(name, *args):
     LAUNCHES[0] += 1
-    if name in TIMED_NAMES:
-        s = torch.cuda.Event(enable_timing=True)
-        e = torch.cuda.Event(enable_timing=True)
+    if name in TIMED_NAMES and (not TIMED_CAPTURE_ONLY[0] or torch.cuda.is_current_stream_capturing()):
+        # inside a capture the events become event-record nodes of the graph ("external" events): every replay re-records
+        # them, so elapsed_time() measures the call as it runs inside the replayed step
+        ext = torch.cuda.is_current_stream_capturing()
+        s = torch.cuda.Event(enable_timing=True, external=ext)
+        e = torch.cuda.Event(enable_timing=True, external=ext)
         s.record()
         check(getattr(L(), name)(*args), name)
         e.record()
         TIMED.setdefault(name, []).append((s, e))
         return
     check(getattr(L(), name)(*args), name)
+
+
+class _ParamGradOverlap:
+    """Side stream for the parameter-gradient kernels of the dense layers (weight-gradient GEMM, bias column sums).
+
+    In a backward pass only the data-gradient chain is on the critical path; the ~70 small weight/bias-gradient launches of the
+    M-A tail merely have to finish before the optimizer (or the gradient all-reduce) reads the arena.  Inside
+    ``param_grad_overlap()`` they are issued on a second stream that forks from the current stream at every layer and joins when the
+    context exits; in a captured step the fork/join become graph edges, so the two chains run concurrently on replay.  Their
+    operands are kept alive until the join (the caching allocator only tracks the stream a block was allocated on)."""
+    active = False
+    streams = {}
+    keep = []
+
+
+_AUX_STREAMS = {}
+
+
+def aux_stream(device):
+    """A second stream per device for work that is independent of the critical chain (callers fork and join explicitly)."""
+    st = _AUX_STREAMS.get(device.index)
+    if st is None:
+        st = _AUX_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _pg_stream(device):
+    if not _ParamGradOverlap.active:
+        return None
+    st = _ParamGradOverlap.streams.get(device.index)
+    if st is None:
+        st = _ParamGradOverlap.streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+@contextlib.contextmanager
+def param_grad_overlap(enabled: bool = True):
+    if not enabled or os.environ.get("CVAD_PG_OVERLAP", "1") == "0" or _ParamGradOverlap.active:
+        yield
+        return
+    _ParamGradOverlap.active = True
+    try:
+        yield
+    finally:
+        _ParamGradOverlap.active = False
+        if _ParamGradOverlap.keep:
+            cur = torch.cuda.current_stream()
+            for st in _ParamGradOverlap.streams.values():
+                if st.device == cur.device:
+                    cur.wait_stream(st)
+            _ParamGradOverlap.keep.clear()
 
 
 def grad_buffer(p: torch.Tensor) -> torch.Tensor:
@@ -207,10 +264,17 @@ class _LinearAct(torch.autograd.Function):
             out = torch.empty_like(dz)
             _call("cvad_act_mask_bwd_f32", _ptr(dz), _ptr(y), _ptr(mask), float(mask_scale), act, _ptr(out), dz.numel(), _st())
             dz = out
-        if _wants_grad(weight):      # dW[o][i] += sum_m dz[m][o] x[m][i]
-            _sgemm(O, K, M, dz, O, False, x2, K, False, grad_buffer(weight), K, accumulate=1, splits=_splits_for(O, K, M), gate=gate)
-        if _wants_grad(bias):
-            _call("cvad_colsum_f32", _ptr(dz), M, O, O, _ptr(grad_buffer(bias)), 1, _st())
+        gw = grad_buffer(weight) if _wants_grad(weight) else None
+        gb = grad_buffer(bias) if _wants_grad(bias) else None
+        side = _pg_stream(dz.device) if (gw is not None or gb is not None) else None
+        if side is not None:         # off the critical path: fork here, join when param_grad_overlap() exits
+            side.wait_stream(torch.cuda.current_stream())
+            _ParamGradOverlap.keep.append((dz, x2))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            if gw is not None:       # dW[o][i] += sum_m dz[m][o] x[m][i]
+                _sgemm(O, K, M, dz, O, False, x2, K, False, gw, K, accumulate=1, splits=_splits_for(O, K, M), gate=gate)
+            if gb is not None:
+                _call("cvad_colsum_f32", _ptr(dz), M, O, O, _ptr(gb), 1, _st())
         dx = None
         if ctx.needs_input_grad[0]:  # dx[m][i] = sum_o dz[m][o] W[o][i]
             splits = _splits_for(M, K, O)

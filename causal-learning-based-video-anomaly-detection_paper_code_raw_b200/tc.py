@@ -56,6 +56,27 @@ class _BackboneBF16(torch.autograd.Function):
         if C1 != 32 or conv1.in_channels != 1 or conv1.kernel_size != (7, 7) or conv1.stride != (2, 2):
             raise RuntimeError("the tensor-core stem implements the reference's 7x7 stride-2 1->32 convolution (cad:115)")
         x = x.contiguous()
+        need_bwd = any(ctx.needs_input_grad)
+        layers = _layers(bb)
+        strides = [conv.stride[0] for conv, _ in layers]
+        if strides[0] == 2:
+            raise RuntimeError("the first 3x3 convolution after the stem is stride 1 in the reference (cad:150)")
+        # bf16 weight packs of the eight 3x3 layers: independent of the activations, so they are issued on a side stream beside the
+        # stem and joined before the first 3x3 convolution (allocated here, on the compute stream, which also consumes them)
+        packs, cin = [], C1
+        for i, (conv, _) in enumerate(layers):
+            cout = conv.out_channels
+            wf = torch.empty((9 * cout, cin), device=dev, dtype=BF16)
+            wd = torch.empty((9 * cin, cout), device=dev, dtype=BF16) if need_bwd and i > 0 else None
+            packs.append((wf, wd))
+            cin = cout
+        cur, side = torch.cuda.current_stream(), ops.aux_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            cin = C1
+            for (conv, _), (wf, wd), stride in zip(layers, packs, strides):
+                _call("cvad_flat_pack_w3x3_bf16", _ptr(conv.weight), conv.out_channels, cin, stride, _ptr(wf), _ptr(wd), _st())
+                cin = conv.out_channels
         H1, W1 = out_hw(H, W, 2)
         mean = torch.empty(C1, device=dev, dtype=torch.float32)
         invstd = torch.empty_like(mean)
@@ -75,21 +96,15 @@ class _BackboneBF16(torch.autograd.Function):
         _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
               _ptr(y1), st)
         h, w = out_hw(H1, W1, 2)
-        layers = _layers(bb)
-        strides = [conv.stride[0] for conv, _ in layers]
-        if strides[0] == 2:
-            raise RuntimeError("the first 3x3 convolution after the stem is stride 1 in the reference (cad:150)")
         a = torch.empty(act_shape(N, h, w, C1, False), device=dev, dtype=BF16)
         _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
         del y1, x4, x
-        need_bwd = any(ctx.needs_input_grad)
+        cur.wait_stream(side)
         saved = []
         cin = C1
         for i, (conv, bn) in enumerate(layers):
             cout, stride = conv.out_channels, strides[i]
-            wf = torch.empty((9 * cout, cin), device=dev, dtype=BF16)
-            wd = torch.empty((9 * cin, cout), device=dev, dtype=BF16) if need_bwd and i > 0 else None
-            _call("cvad_flat_pack_w3x3_bf16", _ptr(conv.weight), cout, cin, stride, _ptr(wf), _ptr(wd), st)
+            wf, wd = packs[i]
             ho, wo = out_hw(h, w, stride)
             raw = torch.empty((N, ho + 2, wo + 2, cout), device=dev, dtype=BF16)
             _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)

@@ -49,14 +49,20 @@ def main():
             fn()
             torch.cuda.synchronize()
             if os.environ.get("FC_DEBUG") and name != "wgrad":
-                dbg = torch.zeros(148 * 8, device=dev, dtype=torch.int64)
+                dbg = torch.zeros(148 * 8 + 2, device=dev, dtype=torch.int64)
+                dbg[148 * 8] = torch.iinfo(torch.int64).max
                 cvad_b200.ops.L().cvad_flat_debug_buffer(dbg.data_ptr())
                 fn()
                 torch.cuda.synchronize()
                 cvad_b200.ops.L().cvad_flat_debug_buffer(None)
-                d = dbg.view(148, 8).double()
-                m = d.mean(0)
-                line += f"[{name} MMA-warp cycles/CTA: total {m[0]:.0f} wait src {m[1]:.0f} w {m[2]:.0f} acc {m[3]:.0f} items {m[4]:.1f}] "
+                t_in, t_out = int(dbg[148 * 8]), int(dbg[148 * 8 + 1])
+                d = dbg[:148 * 8].view(148, 8)
+                live = d[:, 5] > 0
+                m = d[live].double().mean(0)
+                entry, l0, l1 = d[live, 5] - t_in, d[live, 6] - t_in, d[live, 7] - t_in
+                line += (f"[{name} MMA-warp cycles/CTA: total {m[0]:.0f} wait src {m[1]:.0f} w {m[2]:.0f} acc {m[3]:.0f} items {m[4]:.1f}; "
+                         f"ns from first CTA entry: last entry {int(entry.max())}, loop start mean {int(l0.double().mean())}, loop end mean "
+                         f"{int(l1.double().mean())} max {int(l1.max())}, last exit {t_out - t_in}] ")
             ms = 0.0
             for _ in range(reps):
                 flush.fill_(1)
