@@ -141,6 +141,39 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def profile_calls(tr, x_dev, y_dev, path, reps=5):
+    """Per-ABI-call time inside the replayed step graph (external CUDA events around EVERY call of libcvad_b200.so), written as a
+    markdown table: where the step's milliseconds go, including what is not ours (torch fills / RNG) as the unbracketed rest."""
+    from cvad_b200 import ops
+    ops.TIMED.clear()
+    ops.TIMED_NAMES.add("*")
+    ops.TIMED_CAPTURE_ONLY[0] = True
+    gp = tr.graphed_train_step(x_dev, y_dev)
+    ops.TIMED_CAPTURE_ONLY[0] = False
+    ops.TIMED_NAMES.clear()
+    acc = {k: 0.0 for k in ops.TIMED}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    total = 0.0
+    for i in range(reps + 1):
+        e0.record()
+        gp(x_dev, y_dev)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            total += e0.elapsed_time(e1) / reps
+            for k, v in ops.TIMED.items():
+                acc[k] += sum(s.elapsed_time(e) for s, e in v) / reps
+    lines = [f"# per-call time inside the replayed M-A train-step graph (batch 32, external CUDA events, mean of {reps} replays)\n",
+             f"step (instrumented graph) {total * 1e3:.0f} us; sum of bracketed calls {sum(acc.values()) * 1e3:.0f} us "
+             "(calls on the side streams overlap the main chain, so the sum may exceed the step)\n",
+             "| ABI call | calls | us | share of step |", "|---|---:|---:|---:|"]
+    for k, v in sorted(acc.items(), key=lambda kv: -kv[1]):
+        lines.append(f"| `{k}` | {len(ops.TIMED[k])} | {v * 1e3:.1f} | {100 * v / total:.1f}% |")
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    ops.TIMED.clear()
+
+
 def run_ours(args):
     # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION is set in the image; stdout carries exactly one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
@@ -236,7 +269,8 @@ def run_ours(args):
     trace(f"e2e region done ({ms_e2e / args.steps:.3f} ms/step)")
     sampler.stop_flag = True
     # ---- dominant kernel family, timed live with CUDA events around every call (eager launches of the same step)
-    conv_names = {"cvad_flat_conv3x3_fwd_bf16", "cvad_flat_conv3x3_dgrad_bf16", "cvad_flat_conv3x3_wgrad_bf16"} if args.precision == "bf16" \
+    conv_names = {"cvad_flat_conv3x3_fwd_bf16", "cvad_flat_conv3x3_fwd_stats_bf16", "cvad_flat_conv3x3_dgrad_bf16",
+                  "cvad_flat_conv3x3_wgrad_bf16"} if args.precision == "bf16" \
         else {"cvad_conv_fwd_f32", "cvad_conv_dgrad_f32", "cvad_conv_wgrad_f32"}
     probe_steps = 5
     ops.TIMED.clear()
@@ -268,6 +302,8 @@ def run_ours(args):
         how = f"external CUDA events around each ABI call inside the replayed step graph, mean of {probe_steps} replays after the timed region"
     ops.TIMED_NAMES.clear()
     conv_launches = sum(len(v) for v in ops.TIMED.values()) // (probe_steps if args.no_graph else 1)
+    if args.profile_calls and not args.no_graph and rank == 0:
+        profile_calls(tr, x_dev, y_dev, args.profile_calls)
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -323,6 +359,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying one CUDA graph")
+    ap.add_argument("--profile-calls", default="", help="write a per-ABI-call timing table of the replayed step graph to this file")
     ap.add_argument("--watchdog", type=int, default=300, help="seconds after which a stuck run dumps its stack and exits non-zero")
     args = ap.parse_args()
     import faulthandler

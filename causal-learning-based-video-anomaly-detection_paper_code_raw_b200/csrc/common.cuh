@@ -76,6 +76,18 @@ __device__ __forceinline__ double block_sum_d(double v, double* sh /* >=32 doubl
   return r;
 }
 
+// x / d for a launch constant d and 0 <= x < 2^31 as umulhi(x, mul) >> shr (mul = 0 encodes d = 1), instead of the ~20-instruction
+// emulated divide: mul = ceil(2^(31 + ceil(log2 d)) / d), shr = ceil(log2 d) - 1
+static inline void fast_div_init(unsigned d, unsigned& mul, unsigned& shr) {
+  if (d <= 1) { mul = 0; shr = 0; return; }
+  unsigned lg = 0;
+  while ((1u << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  mul = (unsigned)(((1ull << p) + d - 1) / d);
+  shr = p - 32;
+}
+__device__ __forceinline__ int fast_div(int x, unsigned mul, unsigned shr) { return mul ? (int)(__umulhi((unsigned)x, mul) >> shr) : x; }
+
 static inline int cvad_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int cvad_num_sms() {
   static int sms = 0;

@@ -37,7 +37,7 @@ constexpr int FC_MAX_UNITS = 16;
 constexpr int FC_WST_MAX = 8;        // maximum weight ring depth
 constexpr int FC_MAX_SLOTS = 16;     // TMEM accumulator ring
 constexpr int FC_BOX = 256;          // rows per big TMA box
-constexpr size_t FC_SMEM_BUDGET = 226 * 1024;
+constexpr size_t FC_SMEM_BUDGET = 222 * 1024;   // dynamic; the static part (barriers, bias, statistics) stays below 5 KB of the 227 KB
 
 // optional profiling hook (tools/conv_probe.py): when set, the MMA-issuing warp of every CTA records the cycles it spent
 // waiting on each barrier class: dbg[cta*8 + {0 total, 1 src_full, 2 w_full, 3 acc_empty, 4 work items, 5 entry ns, 6 loop start ns, 7 loop end ns}]
@@ -63,8 +63,41 @@ struct FcParams {
   long long out_row_base;
   int n_units, seg_rows, sub, n_blocks, ld_out, wst, w_resident;
   int big_boxes, tail_rows;      // segment = big_boxes x 256 rows + one exact tail box (0 = none)
+  // fused BatchNorm statistics (forward only, n_blocks == 1): per-channel sum / sum of squares of the bf16-rounded outputs over the
+  // interior pixels (1..st_h, 1..st_w of every (st_h+2) x (st_w+2) image), added to st_out[0..N) / st_out[N..2N) (fp64, zeroed by the caller)
+  int st_h, st_w;
+  unsigned st_mul_img, st_shr_img, st_mul_row, st_shr_row;
+  double* st_out;
   FcUnit units[FC_MAX_UNITS];
 };
+
+// Column sums of a 32-row x 16-column register tile held one row per lane, for the values and their squares at once (two independent
+// shuffle chains): a butterfly that halves the number of columns a lane carries at every exchange (8 + 4 + 2 + 1 shuffles) and a final
+// pair exchange; afterwards every lane holds the 32-row sums of column 8*bit4 + 4*bit3 + 2*bit2 + bit1 of its lane index.
+__device__ __forceinline__ void warp_colsum16_sq(const float (&x)[16], int lane, float& sum, float& sumsq) {
+  float y[8], z[4], w[2], yy[8], zz[4], ww[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = b4 ? x[i + 8] : x[i], send = b4 ? x[i] : x[i + 8];
+    y[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    yy[i] = fmaf(keep, keep, __shfl_xor_sync(0xffffffffu, send * send, 16));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    z[i] = (b3 ? y[i + 4] : y[i]) + __shfl_xor_sync(0xffffffffu, b3 ? y[i] : y[i + 4], 8);
+    zz[i] = (b3 ? yy[i + 4] : yy[i]) + __shfl_xor_sync(0xffffffffu, b3 ? yy[i] : yy[i + 4], 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    w[i] = (b2 ? z[i + 2] : z[i]) + __shfl_xor_sync(0xffffffffu, b2 ? z[i] : z[i + 2], 4);
+    ww[i] = (b2 ? zz[i + 2] : zz[i]) + __shfl_xor_sync(0xffffffffu, b2 ? zz[i] : zz[i + 2], 4);
+  }
+  const float v = (b1 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w[0] : w[1], 2);
+  const float vv = (b1 ? ww[1] : ww[0]) + __shfl_xor_sync(0xffffffffu, b1 ? ww[0] : ww[1], 2);
+  sum = v + __shfl_xor_sync(0xffffffffu, v, 1);
+  sumsq = vv + __shfl_xor_sync(0xffffffffu, vv, 1);
+}
 
 template <int ROWB, int N>
 __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
@@ -83,6 +116,8 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
       bar_acc_empty[FC_MAX_SLOTS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float s_bias[N];
+  __shared__ float s_stat[2 * N];          // fused BatchNorm statistics of this CTA's rows (fp32 partial sums, flushed once at the end)
+  for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stat[i] = 0.f;
   const long long t_entry = g_fc_debug ? (long long)globaltimer_ns() : 0;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -240,6 +275,9 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
     uint32_t acc_cnt = 0;
     int cur_nb = -1;
+    float st_s[N / 16], st_q[N / 16];          // fused statistics: this lane's column of every 16-column chunk, over all its tiles
+#pragma unroll
+    for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       const long long q0 = (wi / n_blocks) * MT;
       const int nb = (int)(wi % n_blocks);
@@ -257,21 +295,40 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         const long long q = q0 + s * 128 + ew * 32 + lane;
         const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
         __nv_bfloat16* orow = out + (p.out_row_base + q) * (long long)p.ld_out + nb * N;
+        bool keep = false;                    // interior pixel (the only ones BatchNorm statistics run over)
+        if (p.st_out && q < p.rows) {
+          const int qi = (int)q;
+          const int r = qi - fast_div(qi, p.st_mul_img, p.st_shr_img) * ((p.st_h + 2) * (p.st_w + 2));
+          const int i = fast_div(r, p.st_mul_row, p.st_shr_row), j = r - i * (p.st_w + 2);
+          keep = i >= 1 && i <= p.st_h && j >= 1 && j <= p.st_w;
+        }
 #pragma unroll
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
-          if (q < p.rows) {
-            uint32_t pk[8];
+          uint32_t pk[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (q < p.rows) {
             *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (p.st_out) {                     // warp-uniform: statistics of exactly the values the BatchNorm kernels will read back
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[2 * i] = keep ? __uint_as_float(pk[i] << 16) : 0.f;
+              x[2 * i + 1] = keep ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
+            }
+            float cs, cq;
+            warp_colsum16_sq(x, lane, cs, cq);
+            st_s[c0 / 16] += cs;
+            st_q[c0 / 16] += cq;
           }
         }
         tc_fence_before();
@@ -279,10 +336,20 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
       }
       acc_cnt += sub;
     }
+    if (p.st_out && !(lane & 1)) {            // one shared-memory add per warp and column, once per kernel
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+#pragma unroll
+      for (int i = 0; i < N / 16; ++i) {
+        atomicAdd(&s_stat[i * 16 + col], st_s[i]);
+        atomicAdd(&s_stat[N + i * 16 + col], st_q[i]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (p.st_out)
+    for (int i = tid; i < 2 * N; i += blockDim.x) atomicAdd(p.st_out + i, (double)s_stat[i]);
   if (g_fc_debug && tid == 0) {      // grid-wide first entry / last exit (ns) behind the per-CTA records
     atomicMin((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8, (unsigned long long)t_entry);
     atomicMax((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8 + 1, globaltimer_ns());
@@ -411,8 +478,25 @@ CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int str
   return 0;
 }
 
+namespace {
+int flat_fwd(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int stride, double* stats,
+             void* stream);
+}
+
 CVAD_API int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                                         int stride, void* stream) {
+  return flat_fwd(x, w_fwd, bias, y, N, H, W, Cin, Cout, stride, nullptr, stream);
+}
+
+CVAD_API int cvad_flat_conv3x3_fwd_stats_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin,
+                                              int Cout, int stride, double* stats, void* stream) {
+  if (!stats || Cout != n_block_of(Cout)) return (int)cudaErrorInvalidValue;      // one output-channel block per CTA row tile
+  return flat_fwd(x, w_fwd, bias, y, N, H, W, Cin, Cout, stride, stats, stream);
+}
+
+namespace {
+int flat_fwd(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout, int stride, double* stats,
+             void* stream) {
   if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
   const int slab = Cin >= 64 ? 64 : 32;
   const int nslab = Cin / slab;
@@ -455,8 +539,17 @@ CVAD_API int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const 
         }
       }
   }
+  if (stats) {
+    if (p.rows > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    p.st_out = stats;
+    p.st_h = stride == 1 ? H : (H - 1) / 2 + 1;
+    p.st_w = stride == 1 ? W : (W - 1) / 2 + 1;
+    fast_div_init((unsigned)((p.st_h + 2) * (p.st_w + 2)), p.st_mul_img, p.st_shr_img);
+    fast_div_init((unsigned)(p.st_w + 2), p.st_mul_row, p.st_shr_row);
+  }
   return run_flat(x, src_rows, Cin, w_fwd, Cout, bias, y, p, (cudaStream_t)stream);
 }
+}  // namespace
 
 CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
                                           void* stream) {

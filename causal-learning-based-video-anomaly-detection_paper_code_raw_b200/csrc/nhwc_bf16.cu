@@ -80,16 +80,6 @@ struct PadGeo {
   unsigned mulW, shrW, mulH, shrH;     // x / W and x / H as umulhi(x, mul) >> shr for 0 <= x < 2^31 (mul = 0: divisor 1)
 };
 
-// division by a launch constant without the ~20-instruction emulated divide: mul = ceil(2^(31+ceil(log2 d)) / d)
-inline void fast_div_init(unsigned d, unsigned& mul, unsigned& shr) {
-  if (d <= 1) { mul = 0; shr = 0; return; }
-  unsigned lg = 0;
-  while ((1u << lg) < d) ++lg;
-  const unsigned p = 31 + lg;
-  mul = (unsigned)(((1ull << p) + d - 1) / d);
-  shr = p - 32;
-}
-__device__ __forceinline__ int fast_div(int x, unsigned mul, unsigned shr) { return mul ? (int)(__umulhi((unsigned)x, mul) >> shr) : x; }
 
 __device__ __forceinline__ long long plain_row(const PadGeo& g, int n, int hp, int wp) { return ((long long)n * (g.H + 2) + hp) * (g.W + 2) + wp; }
 __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, int wp) {
@@ -469,6 +459,15 @@ CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C,
   CVAD_LAUNCH_CHECK();
   bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, (double)N * H * W, eps, momentum, mean, invstd, running_mean, running_var,
                                                            num_batches_tracked);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_bn_finalize_f64(double* ws, int C, double count, float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                                  float* running_var, long long* num_batches_tracked, void* stream) {
+  if (C <= 0 || count <= 0) return (int)cudaErrorInvalidValue;
+  bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ws, C, count, eps, momentum, mean, invstd, running_mean, running_var,
+                                                                            num_batches_tracked);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

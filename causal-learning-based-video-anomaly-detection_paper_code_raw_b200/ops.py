@@ -47,7 +47,7 @@ TIMED_CAPTURE_ONLY = [False]     # True: bracket the named calls only while a CU
 
 def _call(name, *args):
     LAUNCHES[0] += 1
-    if name in TIMED_NAMES and (not TIMED_CAPTURE_ONLY[0] or torch.cuda.is_current_stream_capturing()):
+    if (name in TIMED_NAMES or "*" in TIMED_NAMES) and (not TIMED_CAPTURE_ONLY[0] or torch.cuda.is_current_stream_capturing()):
         # inside a capture the events become event-record nodes of the graph ("external" events): every replay re-records
         # them, so elapsed_time() measures the call as it runs inside the replayed step
         ext = torch.cuda.is_current_stream_capturing()
@@ -77,11 +77,11 @@ class _ParamGradOverlap:
 _AUX_STREAMS = {}
 
 
-def aux_stream(device):
-    """A second stream per device for work that is independent of the critical chain (callers fork and join explicitly)."""
-    st = _AUX_STREAMS.get(device.index)
+def aux_stream(device, which: int = 0):
+    """Extra streams per device for work that is independent of the critical chain (callers fork and join explicitly)."""
+    st = _AUX_STREAMS.get((device.index, which))
     if st is None:
-        st = _AUX_STREAMS[device.index] = torch.cuda.Stream(device=device)
+        st = _AUX_STREAMS[(device.index, which)] = torch.cuda.Stream(device=device)
     return st
 
 

@@ -16,12 +16,15 @@ gradient (the reference only accumulates round-off there); they receive exactly 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
 from .ops import _call, _ptr, _st, grad_buffer, _wants_grad
 
 BF16 = torch.bfloat16
+FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm batch statistics from the convolution epilogue
 
 
 def _layers(bb):
@@ -107,13 +110,20 @@ class _BackboneBF16(torch.autograd.Function):
             wf, wd = packs[i]
             ho, wo = out_hw(h, w, stride)
             raw = torch.empty((N, ho + 2, wo + 2, cout), device=dev, dtype=BF16)
-            _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
             mean = torch.empty(cout, device=dev, dtype=torch.float32)
             invstd = torch.empty_like(mean)
-            if bn.training:
+            if bn.training and FUSED_STATS and cout in (32, 64, 128, 256):
+                # batch statistics straight from the convolution's epilogue (no second pass over raw), then the tiny finalize
+                ws = ops.bn_workspace(dev, cout)
+                _call("cvad_flat_conv3x3_fwd_stats_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, _ptr(ws), st)
+                _call("cvad_bn_finalize_f64", _ptr(ws), cout, float(N * ho * wo), float(bn.eps), float(bn.momentum), _ptr(mean), _ptr(invstd),
+                      _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(bn.num_batches_tracked), st)
+            elif bn.training:
+                _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
                 _call("cvad_pad_bn_stats_bf16", _ptr(raw), N, ho, wo, cout, _ptr(ops.bn_workspace(dev, cout)), float(bn.eps), float(bn.momentum),
                       _ptr(mean), _ptr(invstd), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(bn.num_batches_tracked), st)
             else:
+                _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
                 _call("cvad_bn_eval_prepare_f32", cout, float(bn.eps), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(mean), _ptr(invstd), st)
             phase_out = i + 1 < len(layers) and strides[i + 1] == 2
             act = torch.empty(act_shape(N, ho, wo, cout, phase_out), device=dev, dtype=BF16)

@@ -179,6 +179,16 @@ int cvad_flat_debug_buffer(long long* buf);
 /* (N,H,W,Cin) = input geometry.  stride 1: x, y padded-flat.  stride 2: x = phase planes, y padded-flat (N,Ho+2,Wo+2,Cout). */
 int cvad_flat_conv3x3_fwd_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                                int stride, void* stream);
+/* The same convolution with the BatchNorm batch statistics of its output (cad:131,136 in train mode) taken in the epilogue: per-channel
+ * sum and sum of squares of the bf16-rounded outputs over the interior pixels are ADDED to stats[0..Cout) / stats[Cout..2*Cout) (fp64,
+ * zeroed by the caller; cvad_bn_finalize_f64 turns them into mean / invstd / running statistics and re-zeroes them).
+ * Cout must be 32, 64, 128 or 256. */
+int cvad_flat_conv3x3_fwd_stats_bf16(const void* x, const void* w_fwd, const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                                     int stride, double* stats, void* stream);
+/* mean = ws[c]/count, var = ws[C+c]/count - mean^2 (biased) -> invstd; running stats with momentum and the unbiased variance
+ * (nn.BatchNorm2d train mode); running_mean / running_var / num_batches_tracked may be NULL.  Re-zeroes ws. */
+int cvad_bn_finalize_f64(double* ws, int C, double count, float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                         float* running_var, long long* num_batches_tracked, void* stream);
 /* stride 1: dy, dx padded-flat.  stride 2: dy padded-flat (N,Ho+2,Wo+2,Cout), dx = phase planes. */
 int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
                                  void* stream);

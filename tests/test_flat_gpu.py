@@ -42,6 +42,41 @@ def _inputs(dev, N, H, W, Ci, Co, s):
 
 
 @pytest.mark.parametrize("case", FLAT_CASES)
+def test_flat_conv3x3_fwd_fused_bn_statistics(dev, case):
+    """cvad_flat_conv3x3_fwd_stats_bf16: same output as the plain forward, and the epilogue's per-channel sum / sum of squares over the
+    interior pixels equal those of the bf16 output it wrote (what the separate statistics pass would read back)."""
+    from cvad_b200 import tc
+    from cvad_b200.ops import _call, _ptr, _st
+    N, H, W, Ci, Co, s = case
+    x, w, b, ref, _, _, _ = _inputs(dev, *case)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    wf = torch.empty(9 * Co, Ci, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_pack_w3x3_bf16", _ptr(w), Co, Ci, s, _ptr(wf), None, _st())
+    xin = tc.to_padded(x) if s == 1 else tc.to_phase(x)
+    y0 = torch.full((N, Ho + 2, Wo + 2, Co), 7.0, device=dev, dtype=torch.bfloat16)
+    y1 = torch.full_like(y0, 7.0)
+    _call("cvad_flat_conv3x3_fwd_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y0), N, H, W, Ci, Co, s, _st())
+    ws = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+    _call("cvad_flat_conv3x3_fwd_stats_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y1), N, H, W, Ci, Co, s, _ptr(ws), _st())
+    torch.cuda.synchronize()
+    assert torch.equal(tc.from_padded(y0, Ho, Wo), tc.from_padded(y1, Ho, Wo))
+    inner = y1[:, 1:Ho + 1, 1:Wo + 1, :].double()
+    s1, s2 = inner.sum(dim=(0, 1, 2)), (inner * inner).sum(dim=(0, 1, 2))
+    assert rel(ws[:Co], s1, floor=1.0) < 2e-5 and rel(ws[Co:], s2) < 2e-5
+    # finalize -> mean / invstd / running statistics as nn.BatchNorm2d computes them from that tensor; ws comes back zeroed
+    mean, invstd = torch.empty(Co, device=dev), torch.empty(Co, device=dev)
+    rm, rv, nbt = torch.zeros(Co, device=dev), torch.ones(Co, device=dev), torch.tensor(0, device=dev)
+    cnt = N * Ho * Wo
+    _call("cvad_bn_finalize_f64", _ptr(ws), Co, float(cnt), 1e-5, 0.1, _ptr(mean), _ptr(invstd), _ptr(rm), _ptr(rv), _ptr(nbt), _st())
+    torch.cuda.synchronize()
+    flat = inner.reshape(-1, Co)
+    var = flat.var(dim=0, unbiased=False)
+    assert rel(mean.double(), flat.mean(dim=0), floor=1e-2) < 1e-4 and rel(invstd.double(), (var + 1e-5).rsqrt()) < 1e-4
+    assert rel(rv.double(), 0.9 + 0.1 * flat.var(dim=0, unbiased=True)) < 1e-4 and int(nbt) == 1
+    assert float(ws.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", FLAT_CASES)
 def test_flat_conv3x3_fwd_dgrad_wgrad(dev, case):
     from cvad_b200 import tc
     from cvad_b200.ops import _call, _ptr, _st

@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
     bf = torch.bfloat16
-    tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    tot = {"fwd+stats": 0.0, "fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
     for li, (H, W, Ci, Co, s) in enumerate(LAYERS):
         Ho, Wo = tc.out_hw(H, W, s)
         xin = torch.randn(tc.act_shape(N, H, W, Ci, s == 2), device=dev).to(bf)
@@ -36,7 +36,9 @@ def main():
         dy = torch.randn(N, Ho + 2, Wo + 2, Co, device=dev).to(bf)
         dx = torch.empty_like(xin)
         dw = torch.zeros(Co, Ci, 3, 3, device=dev)
+        ws = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
         calls = {
+            "fwd+stats": lambda: _call("cvad_flat_conv3x3_fwd_stats_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _ptr(ws), _st()),
             "fwd": lambda: _call("cvad_flat_conv3x3_fwd_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _st()),
             "dgrad": lambda: _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(dy), _ptr(wd), _ptr(dx), N, H, W, Ci, Co, s, _st()),
             "wgrad": lambda: _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(xin), _ptr(dy), _ptr(dw), N, H, W, Ci, Co, s, _st()),
@@ -48,7 +50,7 @@ def main():
                 continue
             fn()
             torch.cuda.synchronize()
-            if os.environ.get("FC_DEBUG") and name != "wgrad":
+            if os.environ.get("FC_DEBUG") and name in ("fwd", "dgrad"):
                 dbg = torch.zeros(148 * 8 + 2, device=dev, dtype=torch.int64)
                 dbg[148 * 8] = torch.iinfo(torch.int64).max
                 cvad_b200.ops.L().cvad_flat_debug_buffer(dbg.data_ptr())
