@@ -270,7 +270,7 @@ def run_ours(args):
     sampler.stop_flag = True
     # ---- dominant kernel family, timed live with CUDA events around every call (eager launches of the same step)
     conv_names = {"cvad_flat_conv3x3_fwd_bf16", "cvad_flat_conv3x3_fwd_stats_bf16", "cvad_flat_conv3x3_dgrad_bf16",
-                  "cvad_flat_conv3x3_wgrad_bf16"} if args.precision == "bf16" \
+                  "cvad_flat_conv3x3_wgrad_bf16", "cvad_flat_conv3x3_wgrad_staged_bf16"} if args.precision == "bf16" \
         else {"cvad_conv_fwd_f32", "cvad_conv_dgrad_f32", "cvad_conv_wgrad_f32"}
     probe_steps = 5
     ops.TIMED.clear()
@@ -334,7 +334,7 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": traffic,
                      "traffic_source": traffic_src, "algorithmic_bytes_per_step": CONV_ALG_BYTES,
-                     "kernel": "flatconv / flatwgrad TMA+tcgen05 3x3 convolutions (fwd+dgrad+wgrad, 8 layers)" if args.precision == "bf16"
+                     "kernel": "flatconv / flatwgrad TMA+tcgen05 3x3 convolutions (fwd incl. BatchNorm statistics + dgrad + wgrad incl. its fold pass, 8 layers)" if args.precision == "bf16"
                      else "conv_gemm_kernel fp32",
                      "peak_source": src, "launches_per_step": conv_launches, "ms_per_step": conv_total_ms,
                      "share_of_step": conv_total_ms / ms_step, "per_kernel_ms": conv_ms,

@@ -618,6 +618,7 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
 namespace {
 
 constexpr int WG_MAX_STAGES = 4;
+bool g_wgrad_kh_stack = true;          // cvad_flat_wgrad_mode(0) selects the one-kernel-row-per-MMA form (A/B measurements)
 
 struct WgGroup {
   int seg, delta;
@@ -634,13 +635,23 @@ struct WgParams {
   int seg_rows, qs, n_stages, n_variants;
   int Cin, Cout, ci_blocks, co_blocks;
   int a_big, a_tail, b_box, max_seg;
+  // KH-stacked mode (stride 1, 32/64 channels): the dy tile carries a halo of b_halo = W+2 rows on either side and the MMA's N is three
+  // 32/64-channel atoms b_halo rows apart (kernel rows kh = 2, 1, 0), so one MMA covers a whole 3 x {kw} block of taps
+  int b_rows, b_big, b_tail, b_halo;
+  // optional staging buffer [tap][Cout][Cin] fp32 (zero on entry): the epilogue's atomics then run along Cin, i.e. along the lanes of a
+  // warp (128 contiguous bytes per instruction instead of 32 addresses 36 bytes apart in the OIHW gradient); wgrad_fold_kernel adds it
+  // into dw and re-zeroes it
+  float* scratch;
   WgVariant v[4];
 };
 
-template <int ROWB_A, int ROWB_B, int NB, int A_SLABS>
+template <int ROWB_A, int ROWB_B, int NB, int A_SLABS, int KH>
 __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_at,
-                                                           const __grid_constant__ CUtensorMap map_b, const WgParams p, float* __restrict__ dw) {
+                                                           const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_bt,
+                                                           const WgParams p, float* __restrict__ dw) {
   constexpr int B_SLABS = (NB * 2 + ROWB_B - 1) / ROWB_B;
+  constexpr int NMMA = NB * KH;                            // the MMA's N: KH row-shifted copies of the NB-channel dy tile
+  static_assert(KH == 1 || (KH == 3 && B_SLABS == 1 && NMMA <= 256), "KH stacking needs a single-slab dy tile");
   constexpr int LAY_A = ROWB_A == 128 ? UMMA_SW128 : UMMA_SW64;
   constexpr int LAY_B = ROWB_B == 128 ? UMMA_SW128 : UMMA_SW64;
   constexpr int AW = A_SLABS == 2 ? 128 : ROWB_A / 2;      // channels per M atom group that share a tap
@@ -654,7 +665,7 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   const uint32_t seg1 = (uint32_t)p.seg_rows * ROWB_A;            // one slab of one segment
   const uint32_t a_bytes = (uint32_t)var.n_seg * A_SLABS * seg1;
   const uint32_t a_bytes_max = (uint32_t)p.max_seg * A_SLABS * seg1;
-  const uint32_t b1 = (uint32_t)p.qs * ROWB_B;
+  const uint32_t b1 = (uint32_t)(KH == 3 ? p.b_rows : p.qs) * ROWB_B;
   const uint32_t stage_bytes = a_bytes_max + B_SLABS * b1;
   const uint32_t tx_bytes = a_bytes + B_SLABS * b1;
 
@@ -695,18 +706,26 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
             for (int b = 0; b < p.a_big; ++b) tma_load_2d(dst + b * (FC_BOX * ROWB_A), &map_a, col, r0 + b * FC_BOX, &bar_full[st]);
             if (p.a_tail) tma_load_2d(dst + p.a_big * (FC_BOX * ROWB_A), &map_at, col, r0 + p.a_big * FC_BOX, &bar_full[st]);
           }
-        for (int sl = 0; sl < B_SLABS; ++sl) {
-          const uint32_t dst = base + a_bytes_max + sl * b1;
-          for (int r = 0; r < qs; r += p.b_box) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
+        if (KH == 3) {                    // dy rows [q - halo, q - halo + b_rows): big boxes + one exact tail box
+          const uint32_t dst = base + a_bytes_max;
+          const int r0 = (int)q - p.b_halo;
+          for (int b = 0; b < p.b_big; ++b) tma_load_2d(dst + b * (FC_BOX * ROWB_B), &map_b, cob * NB, r0 + b * FC_BOX, &bar_full[st]);
+          if (p.b_tail) tma_load_2d(dst + p.b_big * (FC_BOX * ROWB_B), &map_bt, cob * NB, r0 + p.b_big * FC_BOX, &bar_full[st]);
+        } else {
+          for (int sl = 0; sl < B_SLABS; ++sl) {
+            const uint32_t dst = base + a_bytes_max + sl * b1;
+            for (int r = 0; r < qs; r += p.b_box) tma_load_2d(dst + r * ROWB_B, &map_b, cob * NB + sl * 64, (int)q + r, &bar_full[st]);
+          }
         }
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, NB, 1, 1);
+    const uint32_t idesc = make_idesc_bf16(128, NMMA, 1, 1);
     const uint32_t lbo_a = A_SLABS == 2 ? seg1 : ROWB_A;
     const uint64_t da_hi = make_smem_desc(0, lbo_a, 8 * ROWB_A, LAY_A);
-    const uint64_t db_hi = make_smem_desc(0, b1, 8 * ROWB_B, LAY_B);
+    // KH == 3: the N atoms are the same channels b_halo pixel rows apart (atom i = dy[q + (i-1)*halo] <-> kernel row kh = 2 - i)
+    const uint64_t db_hi = make_smem_desc(0, KH == 3 ? (uint32_t)p.b_halo * ROWB_B : b1, 8 * ROWB_B, LAY_B);
     const int n_groups = var.n_groups;
     const int ksteps = qs / 16;
     for (int it = 0; it < n_iter; ++it) {
@@ -717,7 +736,7 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
       if (elect_one()) {
         for (int g = 0; g < n_groups; ++g) {
           const uint32_t a0 = base + var.groups[g].seg * A_SLABS * seg1 + (uint32_t)var.groups[g].delta * ROWB_A;
-          const uint32_t tacc = tmem_base + g * NB;
+          const uint32_t tacc = tmem_base + g * NMMA;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = da_hi | (uint64_t)(((a0 + k * 16 * ROWB_A) >> 4) & 0x3FFF);
             const uint64_t db = db_hi | (uint64_t)(((base + a_bytes_max + k * 16 * ROWB_B) >> 4) & 0x3FFF);
@@ -741,18 +760,25 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
     const int ci = cib * CI_BLK + (m % AW);
     const uint32_t tlane = tmem_base + ((uint32_t)(lq * 32) << 16);
     for (int g = 0; g < var.n_groups; ++g) {
-      const int tap = var.groups[g].tap[j];
+      const int tap0 = var.groups[g].tap[j];           // KH == 3: the kw of this M atom (the kernel row comes from the N atom)
 #pragma unroll
-      for (int c0 = 0; c0 < NB; c0 += 16) {
+      for (int c0 = 0; c0 < NMMA; c0 += 16) {
         if ((((c0 >> 4) + g) & 1) != half) continue;
         uint32_t v[16];
-        tmem_ld16(tlane + g * NB + c0, v);
+        tmem_ld16(tlane + g * NMMA + c0, v);
         tmem_ld_wait();
-        if (tap >= 0 && ci < p.Cin) {
+        if (tap0 >= 0 && ci < p.Cin) {
+          const int tap = KH == 3 ? (2 - c0 / NB) * 3 + tap0 : tap0;
+          if (p.scratch) {
+            float* dst = p.scratch + ((long long)tap * p.Cout + cob * NB + (c0 % NB)) * p.Cin + ci;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int co = cob * NB + c0 + i;
-            atomicAdd(dw + ((long long)co * p.Cin + ci) * 9 + tap, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)i * p.Cin, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int co = cob * NB + (c0 % NB) + i;
+              atomicAdd(dw + ((long long)co * p.Cin + ci) * 9 + tap, __uint_as_float(v[i]));
+            }
           }
         }
       }
@@ -763,16 +789,28 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-template <int ROWB_A, int ROWB_B, int NB, int A_SLABS>
+// dw (OIHW) += scratch ([tap][Cout][Cin]); scratch = 0
+__global__ void wgrad_fold_kernel(float* __restrict__ scratch, float* __restrict__ dw, int Cin, int Cout) {
+  const int total = Cout * Cin * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ci = (i / 9) % Cin, co = i / (9 * Cin);
+    float* s = scratch + ((long long)tap * Cout + co) * Cin + ci;
+    dw[i] += *s;
+    *s = 0.f;
+  }
+}
+
+template <int ROWB_A, int ROWB_B, int NB, int A_SLABS, int KH>
 int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& p, float* dw, cudaStream_t st) {
   constexpr int B_SLABS = (NB * 2 + ROWB_B - 1) / ROWB_B;
+  constexpr int NMMA = NB * KH;
   constexpr int CI_BLK = A_SLABS == 2 ? 128 : ROWB_A / 2;
   p.ci_blocks = (p.Cin + CI_BLK - 1) / CI_BLK;
   p.co_blocks = p.Cout / NB;
   int max_delta = 0;
   p.max_seg = 0;
   for (int v = 0; v < p.n_variants; ++v) {
-    if (p.v[v].n_groups * NB > 512) return (int)cudaErrorInvalidValue;
+    if (p.v[v].n_groups * NMMA > 512) return (int)cudaErrorInvalidValue;
     p.max_seg = p.v[v].n_seg > p.max_seg ? p.v[v].n_seg : p.max_seg;
     for (int g = 0; g < p.v[v].n_groups; ++g) max_delta = p.v[v].groups[g].delta > max_delta ? p.v[v].groups[g].delta : max_delta;
   }
@@ -782,7 +820,8 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
   size_t stage = 0;
   for (;; qs >>= 1) {
     p.seg_rows = round_up(qs + max_delta + shifts, 32);
-    stage = (size_t)p.max_seg * A_SLABS * p.seg_rows * ROWB_A + (size_t)B_SLABS * qs * ROWB_B;
+    p.b_rows = KH == 3 ? round_up(qs + 2 * p.b_halo, 32) : qs;
+    stage = (size_t)p.max_seg * A_SLABS * p.seg_rows * ROWB_A + (size_t)B_SLABS * p.b_rows * ROWB_B;
     if (2 * stage + 1024 <= FC_SMEM_BUDGET || qs == 64) break;
   }
   if (2 * stage + 1024 > FC_SMEM_BUDGET) return (int)cudaErrorInvalidValue;
@@ -792,6 +831,8 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
   p.a_big = p.seg_rows / FC_BOX;
   p.a_tail = p.seg_rows % FC_BOX;
   p.b_box = qs < FC_BOX ? qs : FC_BOX;
+  p.b_big = p.b_rows / FC_BOX;
+  p.b_tail = p.b_rows % FC_BOX;
   const size_t smem = p.n_stages * stage + 1024;
   const int yz = p.ci_blocks * p.co_blocks * p.n_variants;
   long long chunks = cvad_num_sms() / yz;                         // one wave of CTAs
@@ -805,37 +846,90 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
   if (e) return e;
   e = make_tmap_2d(&mat, src, src_rows, p.Cin, p.a_tail ? p.a_tail : 32, ROWB_A / 2, ROWB_A);
   if (e) return e;
-  e = make_tmap_2d(&mb, dy, p.rows, p.Cout, p.b_box, ROWB_B / 2, ROWB_B);
+  CUtensorMap mbt;
+  e = make_tmap_2d(&mb, dy, p.rows, p.Cout, KH == 3 ? FC_BOX : p.b_box, ROWB_B / 2, ROWB_B);
+  if (e) return e;
+  e = make_tmap_2d(&mbt, dy, p.rows, p.Cout, p.b_tail ? p.b_tail : 32, ROWB_B / 2, ROWB_B);
   if (e) return e;
   static size_t configured = 0;
   if (smem > configured) {
-    cudaError_t ce = cudaFuncSetAttribute(flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute(flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return (int)ce;
     configured = smem;
   }
-  flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS><<<dim3((unsigned)chunks, p.ci_blocks * p.co_blocks, p.n_variants), 256, smem, st>>>(ma, mat, mb, p, dw);
+  flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS, KH><<<dim3((unsigned)chunks, p.ci_blocks * p.co_blocks, p.n_variants), 256, smem, st>>>(ma, mat, mb, mbt, p, dw);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 int dispatch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& p, float* dw, cudaStream_t st) {
-  if (p.Cin == 32 && p.Cout == 32) return launch_wgrad<64, 64, 32, 1>(src, src_rows, dy, p, dw, st);
-  if (p.Cin == 32 && p.Cout % 64 == 0) return launch_wgrad<64, 128, 64, 1>(src, src_rows, dy, p, dw, st);
-  if (p.Cin == 64 && p.Cout % 64 == 0) return launch_wgrad<128, 128, 64, 1>(src, src_rows, dy, p, dw, st);
-  if (p.Cin % 128 == 0 && p.Cout % 128 == 0) return launch_wgrad<128, 128, 128, 2>(src, src_rows, dy, p, dw, st);
+  if (p.b_halo) {                       // KH-stacked: stride 1, 32->32 or 64->64
+    if (p.Cin == 32 && p.Cout == 32) return launch_wgrad<64, 64, 32, 1, 3>(src, src_rows, dy, p, dw, st);
+    if (p.Cin == 64 && p.Cout == 64) return launch_wgrad<128, 128, 64, 1, 3>(src, src_rows, dy, p, dw, st);
+    return (int)cudaErrorInvalidValue;
+  }
+  if (p.Cin == 32 && p.Cout == 32) return launch_wgrad<64, 64, 32, 1, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin == 32 && p.Cout % 64 == 0) return launch_wgrad<64, 128, 64, 1, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin == 64 && p.Cout % 64 == 0) return launch_wgrad<128, 128, 64, 1, 1>(src, src_rows, dy, p, dw, st);
+  if (p.Cin % 128 == 0 && p.Cout % 128 == 0) return launch_wgrad<128, 128, 128, 2, 1>(src, src_rows, dy, p, dw, st);
   return (int)cudaErrorInvalidValue;
 }
 
 }  // namespace
 
+CVAD_API int cvad_flat_wgrad_mode(int kh_stack) {
+  g_wgrad_kh_stack = kh_stack != 0;
+  return 0;
+}
+
+namespace {
+int flat_wgrad(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
+}
+
 CVAD_API int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride,
                                           void* stream) {
+  return flat_wgrad(x, dy, dw, nullptr, N, H, W, Cin, Cout, stride, stream);
+}
+
+CVAD_API int cvad_flat_conv3x3_wgrad_staged_bf16(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin,
+                                                 int Cout, int stride, void* stream) {
+  if (!scratch) return (int)cudaErrorInvalidValue;
+  int e = flat_wgrad(x, dy, dw, scratch, N, H, W, Cin, Cout, stride, stream);
+  if (e) return e;
+  const int total = Cout * Cin * 9;
+  wgrad_fold_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch, dw, Cin, Cout);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace {
+int flat_wgrad(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin, int Cout, int stride, void* stream) {
   if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int apm = Cin == 32 ? 4 : (Cin == 64 ? 2 : 1);     // taps one MMA can cover through pixel-shift atoms
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.Cin = Cin; p.Cout = Cout;
+  p.scratch = scratch;
+  if (stride == 1 && g_wgrad_kh_stack && ((Cin == 32 && Cout == 32) || (Cin == 64 && Cout == 64))) {
+    // dW[kh][kw] = sum_q' x[q' + kw - 1] * dy[q' - (kh - 1)*Wp]: the kw taps are pixel-shift atoms of M (as below), the kh taps are
+    // atoms of N one padded image row apart, so one M128 x N(3*Cout) MMA per 16 pixels covers a 3 x apm block of taps.  The operand
+    // stream per 16 pixels drops from 3 x 5 KB to 7 KB (32 channels) and from 6 x 6 KB to 2 x 10 KB (64 channels).
+    const int Wp = W + 2;
+    p.rows = (long long)N * (H + 2) * Wp;
+    p.b_halo = Wp;
+    p.n_variants = 1;
+    WgVariant& v = p.v[0];
+    v.n_seg = 1;
+    v.seg_row_off[0] = -1;
+    for (int kw = 0; kw < 3; kw += apm) {
+      WgGroup& g = v.groups[v.n_groups++];
+      g.seg = 0;
+      g.delta = kw;
+      for (int j = 0; j < 4; ++j) g.tap[j] = (j < apm && kw + j < 3) ? kw + j : -1;
+    }
+    return dispatch_wgrad(x, p.rows, dy, p, dw, st);
+  }
   if (stride == 1) {
     const int Wp = W + 2;
     p.rows = (long long)N * (H + 2) * Wp;
@@ -878,3 +972,4 @@ CVAD_API int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* 
   }
   return dispatch_wgrad(x, 4 * p.rows, dy, p, dw, st);
 }
+}  // namespace

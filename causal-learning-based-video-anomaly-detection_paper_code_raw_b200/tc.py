@@ -24,6 +24,19 @@ from . import ops
 from .ops import _call, _ptr, _st, grad_buffer, _wants_grad
 
 BF16 = torch.bfloat16
+STAGED_WGRAD = os.environ.get("CVAD_STAGED_WGRAD", "1") != "0"      # weight-gradient atomics through a [tap][Cout][Cin] staging buffer
+_WG_SCRATCH = {}
+
+
+def _wgrad_scratch(device, cin, cout):
+    """Zeroed staging buffer of a layer shape (stream-ordered reuse: every call leaves it zero again)."""
+    key = (str(device), int(cin), int(cout))
+    buf = _WG_SCRATCH.get(key)
+    if buf is None:
+        buf = _WG_SCRATCH[key] = torch.zeros(9 * cin * cout, device=device, dtype=torch.float32)
+    return buf
+
+
 FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm batch statistics from the convolution epilogue
 
 
@@ -156,7 +169,11 @@ class _BackboneBF16(torch.autograd.Function):
             _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
                   _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
             if _wants_grad(conv.weight):
-                _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, st)
+                if STAGED_WGRAD:
+                    _call("cvad_flat_conv3x3_wgrad_staged_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)),
+                          _ptr(_wgrad_scratch(dev, cin, cout)), N, hi, wi, cin, cout, stride, st)
+                else:
+                    _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, st)
             if _wants_grad(conv.bias):
                 grad_buffer(conv.bias)          # analytically zero (BatchNorm removes the mean); keep the tensor "with grad"
             if idx > 0:

@@ -194,6 +194,13 @@ int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, 
                                  void* stream);
 /* dw (OIHW fp32) += sum over pixels; x as for the forward (padded-flat or phase planes), dy padded-flat with a ZERO border */
 int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int stride, void* stream);
+/* The same weight gradient with its atomics staged through scratch (9*Cout*Cin floats, [tap][Cout][Cin], ZERO on entry and again on
+ * return): coalesced reductions along Cin, then one pass adds the staging buffer into dw (OIHW). */
+int cvad_flat_conv3x3_wgrad_staged_bf16(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin, int Cout,
+                                        int stride, void* stream);
+/* development switch: 1 (default) = stride-1 32->32 / 64->64 weight gradients stack the three kernel rows in the MMA's N dimension,
+ * 0 = one kernel row per MMA */
+int cvad_flat_wgrad_mode(int kh_stack);
 /* batch statistics over the interior of a padded-flat raw tensor (N,H,W,C interior geometry) */
 int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
                            float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);

@@ -102,8 +102,15 @@ def test_flat_conv3x3_fwd_dgrad_wgrad(dev, case):
     _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(xin), _ptr(dyp), _ptr(dw), N, H, W, Ci, Co, s, _st())
     torch.cuda.synchronize()
     e_w = rel(dw, gw)
-    print(f"[flat] {case}: fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e}")
-    assert e_f < 1e-2 and e_d < 1e-2 and e_w < 2e-3
+    # staged variant: accumulates on top of what dw already holds and hands the staging buffer back zeroed
+    dw2 = dw.clone()
+    scratch = torch.zeros(9 * Co * Ci, device=dev)
+    _call("cvad_flat_conv3x3_wgrad_staged_bf16", _ptr(xin), _ptr(dyp), _ptr(dw2), _ptr(scratch), N, H, W, Ci, Co, s, _st())
+    torch.cuda.synchronize()
+    e_w2 = rel(dw2, 2 * gw)
+    assert float(scratch.abs().max()) == 0.0
+    print(f"[flat] {case}: fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e} staged {e_w2:.2e}")
+    assert e_f < 1e-2 and e_d < 1e-2 and e_w < 2e-3 and e_w2 < 2e-3
 
 
 def test_layout_helpers_roundtrip(dev):

@@ -484,6 +484,43 @@ def test_create_unsupervised_labels(dev, gold):
     assert np.allclose(scores, ref, rtol=0, atol=1e-7)
 
 
+# --------------------------------------------------------------------------------------------------------- long-sequence sweep
+@pytest.mark.parametrize("T", [64, 128, 256])
+def test_long_sequence_inference_sweep_sharded(dev, gold, T):
+    """BASELINE config 5: clip scoring at 64-256 frames per clip, clips sharded over 2/4/8 ranks with no communication.  The CUDA
+    path must equal the CPU oracle on the whole batch (fp32, 1e-5), and every rank's shard (DataParallel.shard) must reproduce its
+    slice of the unsharded result bit for bit -- eval-mode BatchNorm, no cross-clip coupling."""
+    from oracle import mb as o_mb, mc as o_mc
+    from cvad_b200.mb import CausalAnomalyDetector as MB
+    from cvad_b200.mc import SimpleVideoAnomalyDetector
+    from cvad_b200.parallel import DataParallel
+    B = 8
+    g = gold("mc.pt")
+    mc = SimpleVideoAnomalyDetector().to(dev).eval()
+    mc.load_state_dict(_mc_synth(g), strict=True)
+    P = {k: v.detach().cpu() for k, v in mc.state_dict().items()}
+    x = synth.mc_clips(B, T, 64, 64, 900 + T)
+    with torch.no_grad():
+        full = mc(x.to(dev))
+    assert rel(full, o_mc.mc_forward(P, x), floor=1e-6) < 1e-5
+    mbm = MB().to(dev).eval()
+    Pb = {k: v.detach().cpu() for k, v in mbm.state_dict().items()}
+    xb = synth.mb_clips(B, T, 64, 64, 700 + T)
+    with torch.no_grad():
+        sb, ab, fb = mbm(xb.to(dev))
+    so, ao, fo = o_mb.mb_forward(Pb, xb)
+    assert rel(sb, so, floor=1e-6) < 1e-5 and rel(ab, ao) < 1e-5 and rel(fb, fo) < 1e-5
+    for world in (2, 4, 8):
+        parts = []
+        for rank in range(world):
+            dp = DataParallel.__new__(DataParallel)          # shard arithmetic only: no process group on a single GPU
+            dp.world, dp.rank = world, rank
+            lo, hi = dp.shard(B)
+            with torch.no_grad():
+                parts.append(mc(x[lo:hi].to(dev)))
+        assert rel(torch.cat(parts), full, floor=1e-6) < 1e-6          # split-K of the dense layers depends on the batch size
+
+
 # --------------------------------------------------------------------------------------------------------- CUDA-graph step
 @pytest.mark.parametrize("split", [False, True])
 def test_graphed_train_step_matches_eager(dev, split):

@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
     bf = torch.bfloat16
-    tot = {"fwd+stats": 0.0, "fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
+    tot = {"fwd+stats": 0.0, "fwd": 0.0, "dgrad": 0.0, "wgrad-staged": 0.0, "wgrad": 0.0}
     for li, (H, W, Ci, Co, s) in enumerate(LAYERS):
         Ho, Wo = tc.out_hw(H, W, s)
         xin = torch.randn(tc.act_shape(N, H, W, Ci, s == 2), device=dev).to(bf)
@@ -37,12 +37,21 @@ def main():
         dx = torch.empty_like(xin)
         dw = torch.zeros(Co, Ci, 3, 3, device=dev)
         ws = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+        scr = torch.zeros(9 * Co * Ci, device=dev)
         calls = {
             "fwd+stats": lambda: _call("cvad_flat_conv3x3_fwd_stats_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _ptr(ws), _st()),
             "fwd": lambda: _call("cvad_flat_conv3x3_fwd_bf16", _ptr(xin), _ptr(wf), _ptr(b), _ptr(y), N, H, W, Ci, Co, s, _st()),
             "dgrad": lambda: _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(dy), _ptr(wd), _ptr(dx), N, H, W, Ci, Co, s, _st()),
+            "wgrad-staged": lambda: _call("cvad_flat_conv3x3_wgrad_staged_bf16", _ptr(xin), _ptr(dy), _ptr(dw), _ptr(scr), N, H, W, Ci, Co, s, _st()),
             "wgrad": lambda: _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(xin), _ptr(dy), _ptr(dw), N, H, W, Ci, Co, s, _st()),
         }
+        if os.environ.get("STEP_ONLY"):           # exactly the convolution launches of one train step, once each (for an ncu metrics pass)
+            calls["fwd+stats"]()
+            if li > 0:
+                calls["dgrad"]()
+            calls["wgrad-staged"]()
+            torch.cuda.synchronize()
+            continue
         gflop = 2.0 * N * Ho * Wo * 9 * Ci * Co / 1e9
         line = f"L{li} {H}x{W} {Ci}->{Co} s{s} ({gflop:5.1f} GFLOP): "
         for name, fn in calls.items():

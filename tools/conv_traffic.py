@@ -1,37 +1,50 @@
 #!/usr/bin/env python
-"""DRAM traffic of the convolution family per train step, from the ncu metrics pass over tools/conv_probe.py
-(profiles/r01f_conv_kernels_ncu_metrics.md: dram__bytes_read.sum / dram__bytes_write.sum per launch, REPS=1, cold cache).
+"""DRAM traffic of the convolution family per train step from an ncu metrics pass over `STEP_ONLY=1 python tools/conv_probe.py 512`
+(which launches exactly the convolution kernels of one 512-frame step, once each):
 
-conv_probe launches, per layer, forward x2, data-gradient x2 (four phase launches each for the stride-2 layers) and
-weight-gradient x2; the second (timed) set of each is taken.  A train step runs forward + weight-gradient of all eight layers
-and the data-gradient of layers 1..7 (layer1.0 sits on the frozen stem).  Usage: python tools/conv_traffic.py > profiles/conv_family_traffic.json"""
+    STEP_ONLY=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \\
+        --log-file gpurun_out/conv_step_metrics.csv python tools/conv_probe.py 512
+    python tools/conv_traffic.py gpurun_out/conv_step_metrics.csv profiles/rXX_conv_step_metrics.md > profiles/conv_family_traffic.json
+"""
+import collections
+import csv
 import json
-import os
 import re
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = "profiles/r01f_conv_kernels_ncu_metrics.md"
-STRIDES = [1, 1, 2, 1, 2, 1, 2, 1]
-
 
 def main():
-    rows = [l.strip().split("|") for l in open(os.path.join(ROOT, SRC)) if re.match(r"\| \d+ \|", l)]
-    R = [(float(r[4]), float(r[5]), float(r[6])) for r in rows]          # us, read MB, write MB
-    idx, per_layer, total_mb, launches = 0, [], 0.0, 0
-    for li, s in enumerate(STRIDES):
-        nd = 1 if s == 1 else 4
-        f = R[idx + 1: idx + 2]; idx += 2
-        d = R[idx + nd: idx + 2 * nd]; idx += 2 * nd
-        w = R[idx + 1: idx + 2]; idx += 2
-        mb = lambda xs: sum(x[1] + x[2] for x in xs)
-        use = mb(f) + mb(w) + (mb(d) if li > 0 else 0.0)
-        launches += 2 + (nd if li > 0 else 0)
-        total_mb += use
-        per_layer.append({"layer": li, "fwd_mb": round(mb(f), 1), "dgrad_mb": round(mb(d), 1), "wgrad_mb": round(mb(w), 1)})
-    assert idx == len(R), (idx, len(R))
-    json.dump({"source": SRC, "what": "dram__bytes_read.sum + dram__bytes_write.sum summed over the convolution launches of one 512-frame train step",
-               "launches_per_step": launches, "bytes_per_step": int(total_mb * 1e6), "per_layer": per_layer}, sys.stdout, indent=1)
+    path, md = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else None)
+    with open(path) as f:
+        lines = [l for l in f if l.startswith('"')]
+    per = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        k = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", r["Kernel Name"]).split("(")[0]
+        if not any(t in k for t in ("flatconv_kernel", "flatwgrad_kernel", "wgrad_fold_kernel")):
+            continue
+        d = per.setdefault(r["ID"], {"kernel": k, "grid": r["Grid Size"]})
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r["Metric Unit"].lower()
+        if "byte" in unit:
+            v *= {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+        elif unit in ("us", "usecond"):
+            v *= 1e3
+        elif unit in ("ms", "msecond"):
+            v *= 1e6
+        d[r["Metric Name"]] = v
+    rows = list(per.values())
+    total = sum(r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"] for r in rows)
+    t = sum(r["gpu__time_duration.sum"] for r in rows)
+    if md:
+        with open(md, "w") as f:
+            f.write("# convolution launches of one 512-frame train step: ncu metrics pass (cold cache, serialised)\n\n")
+            f.write("| # | kernel | grid | us | DRAM read MB | DRAM write MB |\n|---|---|---|---:|---:|---:|\n")
+            for i, r in enumerate(rows):
+                f.write(f"| {i} | `{r['kernel']}` | {r['grid']} | {r['gpu__time_duration.sum'] / 1e3:.1f} | {r['dram__bytes_read.sum'] / 1e6:.1f} | "
+                        f"{r['dram__bytes_write.sum'] / 1e6:.1f} |\n")
+            f.write(f"\n{len(rows)} launches, {t / 1e3:.0f} us, {total / 1e9:.3f} GB\n")
+    json.dump({"source": md or path, "what": "dram__bytes_read.sum + dram__bytes_write.sum summed over the convolution launches of one 512-frame train step",
+               "launches_per_step": len(rows), "bytes_per_step": int(total), "ncu_us_per_step": t / 1e3}, sys.stdout, indent=1)
     print()
 
 
