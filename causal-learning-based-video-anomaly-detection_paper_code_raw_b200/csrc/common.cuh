@@ -1,5 +1,6 @@
 // Shared device helpers for the cvad_b200 kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -87,6 +88,41 @@ static inline void fast_div_init(unsigned d, unsigned& mul, unsigned& shr) {
   shr = p - 32;
 }
 __device__ __forceinline__ int fast_div(int x, unsigned mul, unsigned shr) { return mul ? (int)(__umulhi((unsigned)x, mul) >> shr) : x; }
+
+static inline bool cvad_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CVAD_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// ---- programmatic dependent launch (PDL) for the chains of small, latency-bound kernels of the dense tail.
+// A kernel launched through cvad_launch_pdl may be scheduled while its stream predecessor is still running; cvad_pdl_enter() -- the
+// FIRST statement of such a kernel, before any global-memory access -- (1) lets the kernel's own successor be scheduled as soon as
+// every CTA of this grid has started, and (2) blocks until all prerequisite grids have completed and their writes are visible.
+// The data dependence is unchanged; what disappears is the ~2 us scheduling gap between dependent launches (also inside a captured
+// CUDA graph, where the launches become programmatic edges).  Predecessors that never trigger simply release at completion.
+__device__ __forceinline__ void cvad_pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t cvad_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = cvad_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 static inline int cvad_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int cvad_num_sms() {

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(int M, int N, int K, const fl
                                                    const float* __restrict__ bias, int act, const float* __restrict__ mask,
                                                    float mask_scale, int accumulate, int k_per_split, int atomic_out,
                                                    const float* __restrict__ gate) {
+  cvad_pdl_enter();
   if (gate && !(*gate > 0.f)) return;     // device-side "this branch received no gradient" switch
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(int M, int N, int K, const fl
 
 __global__ void bias_act_mask_kernel(float* __restrict__ y, long long rows, int cols, const float* __restrict__ bias, int act,
                                      const float* __restrict__ mask, float mask_scale) {
+  cvad_pdl_enter();
   long long n = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int j = (int)(i % cols);
@@ -125,6 +127,7 @@ __global__ void bias_act_mask_kernel(float* __restrict__ y, long long rows, int 
 // dz = dy * act'(y) * mask*scale ; also (optionally) column sums db[j] = sum_i dz[i][j]
 __global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ mask,
                                     float mask_scale, int act, float* __restrict__ dz, long long n) {
+  cvad_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float g = dy[i];
     float yy = y ? y[i] : 0.f;
@@ -142,6 +145,7 @@ __global__ void act_mask_bwd_kernel(const float* __restrict__ dy, const float* _
 // threads of a warp read 32 consecutive columns of one row (coalesced), row lanes are reduced through shared memory.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int cols, long long ld, float* __restrict__ out,
                                                      int accumulate) {
+  cvad_pdl_enter();
   __shared__ float sh[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + cx;
@@ -175,12 +179,15 @@ CVAD_API int cvad_sgemm_f32(int M, int N, int K, const float* A, long long lda, 
   if (splits < 1) splits = 1;
   int atomic_out = splits > 1;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-#define GO(AK, BKM) sgemm_kernel<AK, BKM><<<grid, NT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, act, mask, mask_scale, accumulate, kps, atomic_out, gate)
+  cudaError_t le;
+#define GO(AK, BKM) le = cvad_launch_pdl(sgemm_kernel<AK, BKM>, grid, dim3(NT), 0, st, M, N, K, A, lda, B, ldb, C, ldc, bias, act, mask, mask_scale, \
+                                         accumulate, kps, atomic_out, gate)
   if (a_kmajor && b_kmajor) GO(true, true);
   else if (a_kmajor) GO(true, false);
   else if (b_kmajor) GO(false, true);
   else GO(false, false);
 #undef GO
+  if (le != cudaSuccess) return (int)le;
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -191,7 +198,8 @@ CVAD_API int cvad_bias_act_mask_f32(float* y, long long rows, int cols, const fl
   if (n <= 0) return 0;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 4 * cvad_num_sms()) blocks = 4 * cvad_num_sms();
-  bias_act_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, rows, cols, bias, act, mask, mask_scale);
+  cudaError_t le = cvad_launch_pdl(bias_act_mask_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, y, rows, cols, bias, act, mask, mask_scale);
+  if (le != cudaSuccess) return (int)le;
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -201,7 +209,8 @@ CVAD_API int cvad_act_mask_bwd_f32(const float* dy, const float* y, const float*
   if (n <= 0) return 0;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * cvad_num_sms()) blocks = 8 * cvad_num_sms();
-  act_mask_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dy, y, mask, mask_scale, act, dz, n);
+  cudaError_t le = cvad_launch_pdl(act_mask_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, dy, y, mask, mask_scale, act, dz, n);
+  if (le != cudaSuccess) return (int)le;
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -217,7 +226,8 @@ CVAD_API int cvad_colsum_f32(const float* x, long long rows, int cols, long long
     if (by > cap) by = cap;
     if (by < 1) by = 1;
   }
-  colsum_kernel<<<dim3(bx, by), 256, 0, st>>>(x, rows, cols, ld, out, accumulate);
+  cudaError_t le = cvad_launch_pdl(colsum_kernel, dim3(bx, by), dim3(256), 0, st, x, rows, cols, ld, out, accumulate);
+  if (le != cudaSuccess) return (int)le;
   CVAD_LAUNCH_CHECK();
   return 0;
 }
