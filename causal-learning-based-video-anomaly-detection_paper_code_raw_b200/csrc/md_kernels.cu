@@ -133,38 +133,80 @@ __global__ void __launch_bounds__(128) memory_score_kernel(const float* __restri
 
 // recon (B, ., E) with t-stride rts (0 = one reconstruction broadcast over T), frames (B,T,E).
 // clip_err[b] += sum_{t,e} (recon - x)^2 / (T*E)   (pre-zeroed);  drecon (may be NULL): d(mean over B,T,E)/d recon
-__global__ void recon_mse_kernel(const float* __restrict__ recon, long long rts, const float* __restrict__ x, int B, int T, long long E,
-                                 double* __restrict__ clip_acc, float* __restrict__ drecon) {
+// VEC = 4: 16-byte accesses (E % 4 == 0, 16-byte aligned tensors), four time steps in flight per thread; VEC = 1: any E / alignment.
+template <int VEC>
+__global__ void __launch_bounds__(256) recon_mse_kernel(const float* __restrict__ recon, long long rts, const float* __restrict__ x, int B, int T,
+                                                        long long E, double* __restrict__ clip_acc, float* __restrict__ drecon) {
   __shared__ double shd[32];
   const int b = blockIdx.y;
   const float scale = 2.f / ((float)B * (float)T * (float)E);
+  const long long EV = E / VEC;
+  const float* rb = recon + (long long)b * (rts ? T : 1) * E;
+  const float* xb = x + (long long)b * T * E;
+  float* db = drecon ? drecon + (long long)b * (rts ? T : 1) * E : nullptr;
   double acc = 0.0;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
-    float gsum = 0.f, part = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float r = recon[((long long)b * (rts ? T : 1)) * E + (long long)t * rts + e];
-      const float d = r - x[((long long)b * T + t) * E + e];
-      part = fmaf(d, d, part);
-      if (rts) { if (drecon) drecon[((long long)b * T + t) * E + e] = d * scale; }
-      else gsum += d;
+  for (long long ev = blockIdx.x * (long long)blockDim.x + threadIdx.x; ev < EV; ev += (long long)gridDim.x * blockDim.x) {
+    const long long e = ev * VEC;
+    float gsum[VEC], part = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) gsum[i] = 0.f;
+    constexpr int U = 4;
+    for (int t0 = 0; t0 < T; t0 += U) {
+      float r[U][VEC], v[U][VEC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t0 + u >= T) continue;
+        const float* rp = rb + (long long)(t0 + u) * rts + e;
+        const float* xp = xb + (long long)(t0 + u) * E + e;
+        if (VEC == 4) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(rp)), c = __ldg(reinterpret_cast<const float4*>(xp));
+          r[u][0] = a.x; r[u][1 % VEC] = a.y; r[u][2 % VEC] = a.z; r[u][3 % VEC] = a.w;
+          v[u][0] = c.x; v[u][1 % VEC] = c.y; v[u][2 % VEC] = c.z; v[u][3 % VEC] = c.w;
+        } else {
+          r[u][0] = __ldg(rp);
+          v[u][0] = __ldg(xp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t0 + u >= T) continue;
+        float d[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          d[i] = r[u][i] - v[u][i];
+          part = fmaf(d[i], d[i], part);
+          gsum[i] += d[i];
+        }
+        if (rts && db) {
+          float* dp = db + (long long)(t0 + u) * E + e;
+          if (VEC == 4) *reinterpret_cast<float4*>(dp) = make_float4(d[0] * scale, d[1 % VEC] * scale, d[2 % VEC] * scale, d[3 % VEC] * scale);
+          else *dp = d[0] * scale;
+        }
+      }
     }
-    if (!rts && drecon) drecon[(long long)b * E + e] = gsum * scale;
+    if (!rts && db) {
+      if (VEC == 4) *reinterpret_cast<float4*>(db + e) = make_float4(gsum[0] * scale, gsum[1 % VEC] * scale, gsum[2 % VEC] * scale, gsum[3 % VEC] * scale);
+      else db[e] = gsum[0] * scale;
+    }
     acc += (double)part;
   }
   acc = block_sum_d(acc, shd);
   if (threadIdx.x == 0) atomicAdd(clip_acc + b, acc);
 }
 
-__global__ void recon_finish_kernel(double* __restrict__ clip_acc, int B, double per_clip, float* __restrict__ clip_err, float* __restrict__ loss,
-                                    float* __restrict__ nonfinite_flag) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int b = 0; b < B; ++b) {
-      const double v = clip_acc[b] / per_clip;
-      if (clip_err) clip_err[b] = (float)v;
-      tot += v;
-      clip_acc[b] = 0.0;
-    }
+// one block: clip_err[b] = acc[b] / per_clip, loss = mean_b clip_err, acc re-zeroed
+__global__ void __launch_bounds__(256) recon_finish_kernel(double* __restrict__ clip_acc, int B, double per_clip, float* __restrict__ clip_err,
+                                                           float* __restrict__ loss, float* __restrict__ nonfinite_flag) {
+  __shared__ double shd[32];
+  double tot = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const double v = clip_acc[b] / per_clip;
+    if (clip_err) clip_err[b] = (float)v;
+    tot += v;
+    clip_acc[b] = 0.0;
+  }
+  tot = block_sum_d(tot, shd);
+  if (threadIdx.x == 0) {
     const float l = (float)(tot / B);
     if (loss) *loss = l;
     if (nonfinite_flag && !isfinite(l)) *nonfinite_flag = 1.f;
@@ -205,11 +247,16 @@ CVAD_API int cvad_recon_mse_f32(const float* recon, long long recon_t_stride, co
                                 float* clip_err, float* loss, float* drecon, float* nonfinite_flag, void* stream) {
   if (B <= 0 || T <= 0 || E <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int bx = (int)((E + 255) / 256);
-  if (bx > 64) bx = 64;
-  recon_mse_kernel<<<dim3(bx, B), 256, 0, st>>>(recon, recon_t_stride, frames, B, T, E, ws, drecon);
+  const bool vec = E % 4 == 0 && recon_t_stride % 4 == 0 && (((uintptr_t)recon | (uintptr_t)frames | (uintptr_t)drecon) & 15) == 0;
+  const long long ev = vec ? E / 4 : E;
+  int bx = (int)((ev + 255) / 256);
+  const int cap = (16 * cvad_num_sms() + B - 1) / B;        // enough CTAs to fill the machine, no more than the work
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  if (vec) recon_mse_kernel<4><<<dim3(bx, B), 256, 0, st>>>(recon, recon_t_stride, frames, B, T, E, ws, drecon);
+  else recon_mse_kernel<1><<<dim3(bx, B), 256, 0, st>>>(recon, recon_t_stride, frames, B, T, E, ws, drecon);
   CVAD_LAUNCH_CHECK();
-  recon_finish_kernel<<<1, 32, 0, st>>>(ws, B, (double)T * (double)E, clip_err, loss, nonfinite_flag);
+  recon_finish_kernel<<<1, 256, 0, st>>>(ws, B, (double)T * (double)E, clip_err, loss, nonfinite_flag);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
