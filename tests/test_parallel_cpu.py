@@ -4,6 +4,7 @@ import os
 import socket
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -94,3 +95,37 @@ def test_dataset_dropin_synthetic():
     assert x.shape == (4, 3, 8, 64, 64) and x.dtype == torch.float32 and y.shape == (4,)
     assert 0.0 <= float(x.min()) and float(x.max()) <= 1.0
     assert sum(b[0].shape[0] for b in tr) == 10 and len(te.dataset) >= 4
+
+
+def test_numa_binding_reads_sysfs_topology(tmp_path, monkeypatch):
+    """bind_to_gpu_numa_node: the GPU's PCI address -> numa_node -> that node's CPU list (intersected with what the process may use);
+    unreadable topology or a single-node box leaves the process unbound."""
+    import types
+
+    import torch
+    from cvad_b200 import parallel
+
+    assert parallel._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 2:
+        pytest.skip("needs two usable CPUs")
+    half = allowed[len(allowed) // 2:]
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    for n, cpus in ((0, allowed[:len(allowed) // 2]), (1, half)):
+        d = tmp_path / f"devices/system/node/node{n}"
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(",".join(str(c) for c in cpus) + "\n")
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0))
+    try:
+        assert parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) == 1
+        assert sorted(os.sched_getaffinity(0)) == half
+    finally:
+        os.sched_setaffinity(0, allowed)
+    (dev / "numa_node").write_text("-1\n")                       # no NUMA information for the device
+    assert parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    monkeypatch.setenv("CVAD_NUMA_BIND", "0")
+    (dev / "numa_node").write_text("1\n")
+    assert parallel.bind_to_gpu_numa_node(0, sysfs=str(tmp_path)) is None
+    assert sorted(os.sched_getaffinity(0)) == allowed
