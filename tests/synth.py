@@ -89,3 +89,17 @@ def summarize(t: torch.Tensor, n: int = 16) -> dict:
     f = t.detach().double().flatten()
     return {"norm": float(f.norm()), "sum": float(f.sum()), "absmax": float(f.abs().max()) if f.numel() else 0.0,
             "head": t.detach().flatten()[:n].clone(), "numel": t.numel()}
+
+
+def is_bn_fed_conv_bias(key: str) -> bool:
+    """M-A backbone convolution biases (layerX.0.bias / layerX.3.bias): BatchNorm subtracts the batch mean right after them, so their
+    gradient is analytically zero; the reference accumulates pure round-off there (and Adam amplifies it to +-lr steps)."""
+    parts = key.split(".")
+    return len(parts) == 4 and parts[0] == "backbone" and parts[1].startswith("layer") and parts[2] in ("0", "3") and parts[3] == "bias"
+
+
+def strided_sample(t: torch.Tensor, cap: int = 16384) -> torch.Tensor:
+    """Every k-th element of a tensor (k chosen so that at most ``cap`` remain): a compact stand-in for large parameter tensors."""
+    f = t.detach().flatten()
+    k = max(1, (f.numel() + cap - 1) // cap)
+    return f[::k].clone()

@@ -27,6 +27,11 @@ def _g(seed):
 FLAT_CASES = [(3, 12, 17, 32, 32, 1), (2, 9, 11, 64, 64, 1), (2, 8, 12, 128, 128, 1), (1, 8, 12, 256, 256, 1),
               (2, 12, 18, 32, 64, 2), (3, 15, 23, 64, 128, 2), (2, 15, 23, 128, 256, 2), (1, 7, 9, 32, 32, 1),
               (40, 60, 90, 32, 32, 1), (24, 30, 45, 64, 64, 1), (9, 60, 90, 32, 64, 2)]
+# the seven distinct layer shapes of the BENCHMARKED step (512 frames of 240x360, cad:150-153): every template instance bench.py
+# launches gets here the same number of work items per CTA (2-3 for Cin >= 128, 10-19 for the 32/64-channel layers), so accumulator-
+# ring wrap-around, weight-ring parity across items and the multi-CTA weight-gradient grids are checked where the benchmark runs them
+FLAT_CASES += [(512, 60, 90, 32, 32, 1), (512, 60, 90, 32, 64, 2), (512, 30, 45, 64, 64, 1), (512, 30, 45, 64, 128, 2),
+               (512, 15, 23, 128, 128, 1), (512, 15, 23, 128, 256, 2), (512, 8, 12, 256, 256, 1)]
 
 
 def _inputs(dev, N, H, W, Ci, Co, s):

@@ -306,6 +306,26 @@ def test_ma_train_step_parity_fp32(dev, gold, idx):
             assert moved, k
 
 
+# bf16 gradient bound: per-tensor gradient-norm error of the bf16 path against the fp32 reference.  Observed on a B200 (printed by the
+# tests below): <= 4 % at 8-9 frames, <= 1 % at 512 frames; the bounds are ~2x the observation.
+BF16_GRAD_BOUND_SMALL, BF16_GRAD_BOUND_C2 = 0.08, 0.02
+
+
+def _bf16_grad_check(tr, c, bound):
+    gnorm = max(v["norm"] for v in c["grad_summary"].values())
+    worst, worst_k = 0.0, None
+    for k, p in tr.model.named_parameters():
+        sm = c["grad_summary"].get(k)
+        # skipped: tensors whose reference gradient is round-off (conv biases feeding a BatchNorm: analytically zero) or < 1e-3 of the largest
+        if sm is None or sm["norm"] < 1e-3 * gnorm or synth.is_bn_fed_conv_bias(k):
+            continue
+        e = abs(float(p.grad.double().norm()) - sm["norm"]) / sm["norm"]
+        if e > worst:
+            worst, worst_k = e, k
+    print(f"[bf16] case {c['name']}: worst grad-norm rel err {worst:.2e} ({worst_k})")
+    assert worst < bound, (worst_k, worst)
+
+
 @pytest.mark.parametrize("idx", [0, 1, 2, 3])
 def test_ma_bf16_tensor_core_path(dev, gold, idx):
     """bf16 operands / fp32 accumulation (tcgen05) backbone: scores and loss within 1e-3 relative of the fp32 reference
@@ -330,15 +350,150 @@ def test_ma_bf16_tensor_core_path(dev, gold, idx):
     assert torch.equal(out["dense"]["det_counts"].cpu().long(), c["det_counts"])
     if c["train"]:
         loss.backward()
-        gnorm = max(v["norm"] for v in c["grad_summary"].values())
-        worst = 0.0
-        for k, p in tr.model.named_parameters():
-            sm = c["grad_summary"].get(k)
-            if sm is None or sm["norm"] < 1e-3 * gnorm or k.endswith(".bias") and "backbone" in k:
-                continue
-            worst = max(worst, abs(float(p.grad.double().norm()) - sm["norm"]) / sm["norm"])
-        print(f"[bf16] case {c['name']}: worst grad-norm rel err {worst:.2e}")
-        assert worst < 0.15   # bf16 activations + 8-9 frame batches: per-tensor gradient norms carry a few % of rounding noise
+        _bf16_grad_check(tr, c, BF16_GRAD_BOUND_SMALL)
+
+
+# ---- the BENCHMARKED shape: 32 clips x 16 frames x 240 x 360 (BASELINE.json configs[1]); every tcgen05 template instance sees the
+# same number of work items per CTA as in bench.py (tests/golden/ma_c2.pt comes from the unmodified reference, tools/make_golden.py)
+RANK_TIE_EPS = 2e-3      # relative to the largest score: two clips closer than this may swap ranks under the 1e-3 score tolerance
+
+
+def _same_ranking(got, want, tie_eps):
+    """Every pair of clips that the reference separates by more than tie_eps * max|score| is ordered identically."""
+    got, want = got.double().cpu(), want.double().cpu()
+    dw = want.unsqueeze(0) - want.unsqueeze(1)
+    dg = got.unsqueeze(0) - got.unsqueeze(1)
+    decided = dw.abs() > tie_eps * float(want.abs().max())
+    return bool((torch.sign(dw)[decided] == torch.sign(dg)[decided]).all()), int(decided.sum()) // 2
+
+
+def _c2_step(dev, c, precision):
+    from cvad_b200.ma import MATrainer
+    m, noise = _ma_model(dev, c)
+    tr = MATrainer(m, dev, precision=precision)
+    tr.model.train()
+    tr.model.noise = noise
+    x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"]).to(dev)
+    labels = c["labels"].to(dev)
+    tr.optimizer.zero_grad()
+    out = tr.model(x)
+    loss, comp = tr.loss_on_device(out, labels)
+    loss.backward()
+    torch.cuda.synchronize()
+    return tr, out, loss, comp
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_ma_c2_benchmarked_shape_fp32(dev, gold, idx):
+    """cad:637-688 at 512 frames, fp32 mode: loss + 4 components, scores, per-tensor gradients, BN running statistics (5e-5 / 5e-3)."""
+    c = gold("ma_c2.pt")["cases"][idx]
+    tr, out, loss, comp = _c2_step(dev, c, "fp32")
+    assert rel(loss, c["loss"]) < 5e-5
+    for i, k in enumerate(("classification", "anomaly", "causal", "kl")):
+        assert abs(float(comp[i + 1]) - c["comps"][k]) < 5e-5 * max(1.0, abs(c["comps"][k])), k
+    assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 5e-5
+    assert rel(out["direct_predictions"], c["direct_predictions"]) < 5e-5
+    assert rel(out["dense"]["kl_losses"], c["kl_losses"]) < 5e-5
+    assert torch.equal(out["dense"]["n_tracks"].cpu().long(), c["n_tracks"])
+    gnorm = max(v["norm"] for v in c["grad_summary"].values())
+    for k, p in tr.model.named_parameters():
+        sm = c["grad_summary"].get(k)
+        if sm is None or sm["norm"] < 1e-5 * gnorm:
+            continue
+        got = float(p.grad.double().norm())
+        assert abs(got - sm["norm"]) <= 5e-3 * sm["norm"], (k, got, sm["norm"])
+        if "full" in sm:
+            assert float((p.grad.cpu() - sm["full"]).double().norm()) <= 5e-3 * sm["norm"], k
+    sd = tr.model.state_dict()
+    for k, v in c["new_stats"].items():
+        assert rel(sd[k].float(), v.float()) < 2e-5, k
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_ma_c2_benchmarked_shape_bf16(dev, gold, idx):
+    """The benchmarked configuration itself (bf16 operands, tcgen05, 512 frames): scores and loss within 1e-3 of the fp32 reference,
+    identical thresholded labels (0.5 and the p95 threshold of s1:60) and identical ranking up to the stated tie epsilon."""
+    import numpy as np
+    c = gold("ma_c2.pt")["cases"][idx]
+    tr, out, loss, comp = _c2_step(dev, c, "bf16")
+    got, want = out["anomaly_scores"].detach().cpu(), c["anomaly_scores"]
+    e_s, e_l = rel(got, want, floor=1e-6), rel(loss, c["loss"], floor=1e-6)
+    same, pairs = _same_ranking(got, want, RANK_TIE_EPS)
+    print(f"[bf16 C2] case {c['name']}: score rel err {e_s:.2e}, loss rel err {e_l:.2e}, {pairs} decided pairs ranked identically: {same}")
+    assert e_s < 1e-3 and e_l < 1e-3
+    for i, k in enumerate(("classification", "anomaly", "causal", "kl")):
+        assert abs(float(comp[i + 1]) - c["comps"][k]) < 1e-3 * max(1.0, abs(c["comps"][k])), k
+    assert rel(out["direct_predictions"], c["direct_predictions"]) < 1e-3
+    assert torch.equal(got > 0.5, want > 0.5)
+    thr = float(np.percentile(want.numpy(), 95))
+    clear = (want - thr).abs() > RANK_TIE_EPS * float(want.abs().max())
+    assert torch.equal((got > thr)[clear], (want > thr)[clear])
+    assert same
+    assert torch.equal(out["dense"]["det_counts"].cpu().long(), c["det_counts"])
+    assert torch.equal(out["dense"]["n_tracks"].cpu().long(), c["n_tracks"])
+    _bf16_grad_check(tr, c, BF16_GRAD_BOUND_C2)
+    sd = tr.model.state_dict()
+    for k, v in c["new_stats"].items():
+        if "bn1" not in k:          # the frozen stem's statistics come from the tf32 stem (tested in test_flat_gpu.py)
+            assert rel(sd[k].float(), v.float()) < 5e-3, k
+
+
+# 3 optimizer steps against the reference's own train_model loop (cad:609-709: AdamW 3e-4 / 1e-5, clip_grad_norm_ 1.0, frozen stem).
+# Distance measure: |ours - ref|_2 / |ref - start|_2 per tensor on a strided sample.  Adam's first steps move every element by ~lr
+# whatever its gradient's size, so elements whose gradient is round-off-sized differ by O(lr) between ANY two summation orders: the
+# oracle (fp32, CPU) is already 0.10 away from the reference by this measure (tools/make_golden.py prints it).
+TRAJ_BOUND = {"fp32": 0.25, "bf16": 0.5}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["traj_sat", "traj_live"])
+def test_ma_trajectory_vs_reference_train_model(dev, gold, name, precision):
+    from test_oracle_golden import ma_synth_state
+    from cvad_b200.ma import CausalAnomalyDetector, MATrainer
+    from cvad_b200.noise import FixedNoise
+    g = gold("ma_traj.pt")[name]
+    B, T = g["B"], g["T"]
+    P0 = ma_synth_state(g["seed"], g["live"])
+    m = CausalAnomalyDetector()
+    m.load_state_dict(P0, strict=True)
+    tr = MATrainer(m, dev, num_epochs=1, lr=3e-4, precision=precision)
+    tr.model.train()
+    losses = []
+    for xs in g["xseeds"]:
+        x = synth.ma_clips(B, T, g["H"], g["W"], xs, g["wide"]).to(dev)
+        y = (torch.rand(B, generator=synth.gen(xs + 9)) < 0.5).long().to(dev)
+        eps = torch.randn(B, 5, 6, generator=synth.gen(xs + 1))
+        keep = {"det0": synth.keep_mask((B, T, 512), 0.3, xs + 2), "det1": synth.keep_mask((B, T, 256), 0.2, xs + 3),
+                "scorer0": synth.keep_mask((B, 64), 0.2, xs + 4), "cls0": synth.keep_mask((B, 512), 0.3, xs + 5),
+                "cls1": synth.keep_mask((B, 256), 0.2, xs + 6)}
+        tr.model.noise = FixedNoise({"eps": eps, **keep})
+        comp, _ = tr.train_step(x, y)
+        losses.append(float(comp[0]))
+    mean = sum(losses) / len(losses)
+    tol = 5e-5 if precision == "fp32" else 1e-3
+    print(f"[traj {name} {precision}] losses {losses} mean {mean:.6f} (reference {g['mean_loss']:.6f})")
+    assert abs(mean - g["mean_loss"]) <= tol * abs(g["mean_loss"])
+    for a, b in zip(losses, g["oracle_losses"]):
+        assert abs(a - b) <= 2 * tol * abs(b)
+    sd = tr.model.state_dict()
+    worst, worst_k = 0.0, None
+    for k, ref in g["final_sample"].items():
+        got = synth.strided_sample(sd[k].float().cpu())
+        start = synth.strided_sample(P0[k].float())
+        moved = float((ref - start).double().norm())
+        d = float((got - ref).double().norm())
+        if "running" in k:
+            assert d <= (2e-5 if precision == "fp32" else 5e-3) * float(ref.double().norm()) or "bn1" in k and precision == "bf16", k
+            continue
+        if synth.is_bn_fed_conv_bias(k):
+            continue            # reference: Adam-amplified round-off (analytically zero gradient); here: exactly zero gradient
+        if moved == 0.0:
+            assert d == 0.0, k   # frozen stem, saturated detector / structure learner: untouched (not even weight decay)
+            continue
+        if d / moved > worst:
+            worst, worst_k = d / moved, k
+    print(f"[traj {name} {precision}] worst |ours - ref| / |ref - start| = {worst:.3f} ({worst_k})")
+    assert worst < TRAJ_BOUND[precision], (worst_k, worst)
 
 
 # --------------------------------------------------------------------------------------------------------- M-D

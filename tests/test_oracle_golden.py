@@ -204,6 +204,47 @@ def ma_noise(c):
     return eps, keep
 
 
+
+def test_ma_c2_benchmarked_shape_forward_matches_reference(gold):
+    """The oracle at the benchmarked shape (32 x 16 x 240 x 360, train-mode BatchNorm, injected dropout / eps): scores and the 4-term
+    loss of the unmodified reference (tests/golden/ma_c2.pt).  Forward only here (the backward is asserted when the fixture is made)."""
+    c = gold("ma_c2.pt")["cases"][0]
+    P = ma_synth_state(c["seed"], c["live"])
+    x = synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"])
+    eps, keep = ma_noise(c)
+    with torch.no_grad():
+        out = o_ma.ma_forward(P, x, eps, True, keep, {})
+        loss, comps = o_ma.ma_loss(out, c["labels"])
+    assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 1e-5
+    assert rel(loss, c["loss"]) < 1e-5
+    for k, v in c["comps"].items():
+        assert abs(comps[k] - v) <= 1e-5 * max(1.0, abs(v)), k
+
+
+def test_ma_trajectory_oracle_vs_reference_train_model(gold):
+    """oracle.train.ma_train_step (the CPU stand-in bench.py times when the reference copy is absent) against three iterations of
+    the reference's own train_model loop (cad:637-693): per-step losses and the final parameters."""
+    from oracle import train as o_train
+    g = gold("ma_traj.pt")["traj_live"]
+    B, T = g["B"], g["T"]
+    P0 = ma_synth_state(g["seed"], g["live"])
+    P = {k: v.clone() for k, v in P0.items()}
+    opt = o_train.OracleAdam(o_train.ma_trainable(P), 3e-4, 1e-5, True, 1.0)
+    losses = []
+    for xs in g["xseeds"]:
+        x = synth.ma_clips(B, T, g["H"], g["W"], xs, g["wide"])
+        y = (torch.rand(B, generator=synth.gen(xs + 9)) < 0.5).long()
+        eps, keep = ma_noise({"B": B, "T": T, "xseed": xs})
+        losses.append(o_train.ma_train_step(P, opt, x, y, eps, keep)[0])
+    assert abs(sum(losses) / 3 - g["mean_loss"]) < 1e-5 * g["mean_loss"]
+    for k, ref in g["final_sample"].items():
+        if "running" in k or synth.is_bn_fed_conv_bias(k):
+            continue
+        moved = float((ref - synth.strided_sample(P0[k])).double().norm())
+        d = float((synth.strided_sample(P[k]) - ref).double().norm())
+        assert d <= 0.25 * moved + 1e-12, (k, d, moved)
+
+
 # --------------------------------------------------------------------------------------------------------- M-D
 def md_synth_state(seed):
     """The state tools/make_golden.py gave the reference VideoAutoEncoder (rebuilt from seeds, no reference needed)."""

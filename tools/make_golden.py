@@ -358,6 +358,149 @@ def make_ma():
 
 
 
+def _ma_noise_for(B, T, xseed):
+    eps = torch.randn(B, 5, 6, generator=synth.gen(xseed + 1))
+    keep = {"det0": synth.keep_mask((B, T, 512), 0.3, xseed + 2), "det1": synth.keep_mask((B, T, 256), 0.2, xseed + 3),
+            "scorer0": synth.keep_mask((B, 64), 0.2, xseed + 4), "cls0": synth.keep_mask((B, 512), 0.3, xseed + 5),
+            "cls1": synth.keep_mask((B, 256), 0.2, xseed + 6)}
+    return eps, keep
+
+
+def make_ma_c2():
+    """M-A at the BENCHMARKED shape (BASELINE.json configs[1]: 32 clips x 16 frames x 240x360 = 512 frames per step): one training
+    forward / 4-term loss / backward of the unmodified reference (cad:671-688), saturated detector (the stock init) and a
+    live-detector variant.  The inputs are the ones bench.py uses on rank 0 (synth.ma_clips(32,16,240,360,1234,wide) and
+    bernoulli(0.3) labels from seed 1243), so bench.py can check its own first step against this fixture."""
+    print("== M-A at the benchmarked shape (32 x 16 x 240 x 360) ==")
+    cad = import_ref("causal_anomaly_detection")
+    out = {"cases": []}
+    for c in (dict(name="c2_sat_train", seed=3, live=False, B=32, T=16, H=240, W=360, wide=True, train=True, xseed=1234, label_p=0.3),
+              dict(name="c2_live_train", seed=4, live=True, B=32, T=16, H=240, W=360, wide=False, train=True, xseed=2234, label_p=0.5)):
+        model, P = ma_state(cad, c["seed"], c["live"])
+        B, T = c["B"], c["T"]
+        x = synth.ma_clips(B, T, c["H"], c["W"], c["xseed"], c["wide"])
+        labels = (torch.rand(B, generator=synth.gen(c["xseed"] + 9)) < c["label_p"]).long()
+        eps, keep = _ma_noise_for(B, T, c["xseed"])
+        Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+        ns = {}
+        oo = o_ma.ma_forward(Pg, x, eps, True, keep, ns)
+        lo, co = o_ma.ma_loss(oo, labels)
+        lo.backward()
+        ograd = {k: (v.grad.clone() if torch.is_tensor(v) and v.grad is not None else None) for k, v in Pg.items()}
+        ntr = oo["n_tracks"].clone()
+        oo = {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in oo.items()}
+        del Pg
+        ro, rl, rc = ref_ma_run(cad, model, P, x, labels, eps, ntr, True, keep)
+        print(f" case {c['name']}: loss {float(rl):.6f} tracks/clip {ntr.tolist()}")
+        close(oo["anomaly_scores"], ro["anomaly_scores"], 1e-5, "anomaly_scores")
+        close(oo["causal_anomaly_scores"], ro["causal_anomaly_scores"], 1e-5, "causal_anomaly_scores")
+        close(oo["direct_predictions"], ro["direct_predictions"], 1e-5, "direct_predictions")
+        close(oo["kl_losses"], torch.stack(ro["kl_losses"]), 1e-5, "kl_losses")
+        close(oo["adjacency_matrices"], torch.stack(ro["adjacency_matrices"]), 1e-5, "adjacency")
+        close(lo, rl, 1e-5, "total loss")
+        rec = {**c, "labels": labels, "loss": rl.detach().clone(), "comps": rc,
+               "anomaly_scores": ro["anomaly_scores"].detach().clone(),
+               "causal_anomaly_scores": ro["causal_anomaly_scores"].detach().clone(),
+               "direct_predictions": ro["direct_predictions"].detach().clone(),
+               "kl_losses": torch.stack(ro["kl_losses"]).detach().clone(),
+               "adjacency": torch.stack(ro["adjacency_matrices"]).detach().clone(),
+               "causal_factors": oo["causal_factors"], "n_tracks": ntr, "det_counts": oo["det_counts"].clone(),
+               "features_summary": synth.summarize(oo["features"])}
+        gs, has = {}, {}
+        gnorm = max(float(p.grad.norm()) for p in model.parameters() if p.grad is not None)
+        for k, p in model.named_parameters():
+            has[k] = p.grad is not None
+            if p.grad is not None:
+                og = ograd[k]
+                if float(p.grad.norm()) > 1e-5 * gnorm:
+                    r = float((og - p.grad).double().norm() / p.grad.double().norm())
+                    print(f"   {'ok ' if r < 5e-3 else 'BAD'} grad {k}: rel-L2 {r:.2e} |g| {float(p.grad.norm()):.3e}")
+                    assert r < 5e-3, k
+                gs[k] = synth.summarize(p.grad)
+                if p.grad.numel() <= 4096:
+                    gs[k]["full"] = p.grad.clone()
+        rec["grad_summary"], rec["has_grad"] = gs, has
+        rec["new_stats"] = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+        for k, v in rec["new_stats"].items():
+            close(ns[k], v, 1e-5, f"stat {k}") if "conv" not in k else None
+        out["cases"].append(rec)
+        del ro, oo, ograd
+
+    torch.save(out, os.path.join(GOLD, "ma_c2.pt"))
+    print("   wrote ma_c2.pt", os.path.getsize(os.path.join(GOLD, "ma_c2.pt")) // 1024, "KiB")
+
+
+
+def make_ma_traj():
+    """3-step M-A trajectories through the reference's OWN train_model loop (cad:609-709)."""
+    print("== M-A 3-step trajectories through cad.train_model ==")
+    cad = import_ref("causal_anomaly_detection")
+    out = {}
+    # ---- 3-step trajectory through the reference's OWN train_model loop (cad:609-709, fp32 branch on CPU: AdamW lr 3e-4 wd 1e-5,
+    # clip_grad_norm_ 1.0, frozen stem), and the oracle's ma_train_step (what bench.py --impl reference falls back to) against it
+    from oracle import train as o_train
+    for name, live, seed, (B, T, H, W), wide in (("traj_sat", False, 3, (8, 8, 240, 360), True), ("traj_live", True, 4, (6, 5, 120, 180), False)):
+        model, P0 = ma_state(cad, seed, live)
+        model.load_state_dict(P0, strict=True)
+        xseeds = [3100 + 10 * i + (500 if live else 0) for i in range(3)]
+        batches, noises = [], []
+        for xs in xseeds:
+            x = synth.ma_clips(B, T, H, W, xs, wide)
+            y = (torch.rand(B, generator=synth.gen(xs + 9)) < 0.5).long()
+            batches.append((x, y))
+            noises.append(_ma_noise_for(B, T, xs))
+        # the oracle first: it yields the per-clip track counts that size the injected eps of each step
+        P = {k: v.clone() for k, v in P0.items()}
+        opt = o_train.OracleAdam(o_train.ma_trainable(P), 3e-4, 1e-5, True, 1.0)
+        o_losses, ntrs = [], []
+        for (x, y), (eps, keep) in zip(batches, noises):
+            with torch.no_grad():
+                ntrs.append(o_ma.ma_forward(P, x, eps, True, keep, {})["n_tracks"].clone())
+            l, _ = o_train.ma_train_step(P, opt, x, y, eps, keep)
+            o_losses.append(l)
+        cad.device = torch.device("cpu")
+        with NoiseInjector() as inj:
+            for (eps, keep), ntr in zip(noises, ntrs):
+                inj.randn += [eps[b, : int(ntr[b])].clone() for b in range(B)]
+                inj.dropout.setdefault(id(model.detector.detector_net[2]), []).append(keep["det0"])
+                inj.dropout.setdefault(id(model.detector.detector_net[5]), []).append(keep["det1"])
+                inj.dropout.setdefault(id(model.anomaly_scorer.causal_scorer[2]), []).extend(keep["scorer0"][b:b + 1] for b in range(B))
+                inj.dropout.setdefault(id(model.direct_classifier[2]), []).append(keep["cls0"])
+                inj.dropout.setdefault(id(model.direct_classifier[5]), []).append(keep["cls1"])
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                model, tl, vl = cad.train_model(model, batches, [], num_epochs=1, lr=3e-4)
+            assert not inj.randn, "the reference consumed a different number of eps draws than the oracle predicted"
+        print(f" {name}: reference mean train loss {tl[0]:.6f}; oracle per-step losses {o_losses}")
+        close(sum(o_losses) / 3, tl[0], 1e-5, f"{name} mean loss over 3 steps (oracle ma_train_step vs reference train_model)")
+        final = model.state_dict()
+        pmax = 0.0
+        for k, v in final.items():
+            if v.is_floating_point():
+                # Adam's first steps move every weight by ~lr whatever the size of its gradient, and an element whose gradient is
+                # round-off-sized flips direction with the summation order: compare the L2 distance with the L2 distance moved
+                d = float((P[k] - v).double().norm())
+                moved = float((v - P0[k]).double().norm())
+                if synth.is_bn_fed_conv_bias(k):
+                    # a convolution bias that feeds a BatchNorm has an analytically zero gradient; the reference's autograd leaves
+                    # round-off there and Adam turns round-off into +-lr steps of random sign: nothing to compare (DESIGN.md 2)
+                    continue
+                if moved > 0:
+                    r = d / moved
+                    pmax = max(pmax, r)
+                else:
+                    assert d == 0.0, k
+        print(f"   final parameters: oracle vs reference, worst L2 distance / L2 distance moved = {pmax:.2e}")
+        assert pmax < 0.25
+        out[name] = {"B": B, "T": T, "H": H, "W": W, "wide": wide, "seed": seed, "live": live, "xseeds": xseeds, "mean_loss": tl[0],
+                     "oracle_losses": o_losses, "n_tracks": [n.clone() for n in ntrs],
+                     "final_summary": {k: synth.summarize(v) for k, v in final.items()},
+                     "moved_l2": {k: float((v - P0[k]).double().norm()) for k, v in final.items() if v.is_floating_point()},
+                     "final_sample": {k: synth.strided_sample(v) for k, v in final.items() if v.is_floating_point()}}
+    torch.save(out, os.path.join(GOLD, "ma_traj.pt"))
+    print("   wrote ma_traj.pt", os.path.getsize(os.path.join(GOLD, "ma_traj.pt")) // 1024, "KiB")
+
+
 def md_state(cad1, seed):
     """Reference VideoAutoEncoder with reproducible, trained-like weights and a partly filled memory bank."""
     torch.manual_seed(seed)
@@ -454,7 +597,7 @@ def make_me():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mb", "mc", "ma", "md", "me"]
+    which = sys.argv[1:] or ["mb", "mc", "ma", "ma_c2", "ma_traj", "md", "me"]
     os.makedirs(GOLD, exist_ok=True)
     if "mb" in which:
         make_mb()
@@ -462,6 +605,10 @@ if __name__ == "__main__":
         make_mc()
     if "ma" in which:
         make_ma()
+    if "ma_c2" in which:
+        make_ma_c2()
+    if "ma_traj" in which:
+        make_ma_traj()
     if "md" in which:
         make_md()
     if "me" in which:
