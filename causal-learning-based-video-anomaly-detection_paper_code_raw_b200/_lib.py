@@ -16,6 +16,8 @@ ROOT = os.path.dirname(PKG_DIR)
 HEADER = os.path.join(ROOT, "include", "cvad_b200.h")
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcvad_b200.so")
+# development only: A/B a library built from another branch (tools/build_variant.sh) without touching the in-tree one
+LOAD_PATH = os.environ.get("CVAD_B200_LIB", LIB_PATH)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
@@ -66,7 +68,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
-    cmd = ["nvcc", "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    cmd = ["nvcc", "-shared", "--cudart", "shared", "-o", LIB_PATH] + objs
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
@@ -99,11 +101,11 @@ def parse_header(path: str = HEADER):
 
 
 def load():
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LOAD_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: the CUDA extension must be built first (python -c 'import __graft_entry__ as g; g.build()'). "
+            f"{LOAD_PATH} is missing: the CUDA extension must be built first (python -c 'import __graft_entry__ as g; g.build()'). "
             "There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(LOAD_PATH)
     for name, (ret, argtypes) in parse_header().items():
         try:
             fn = getattr(lib, name)

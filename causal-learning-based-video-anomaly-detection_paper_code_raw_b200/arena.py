@@ -141,6 +141,10 @@ class FusedAdam(torch.optim.Optimizer):
     def step_local(self):
         """The fused grad-norm + clip + Adam(W) kernels alone (no data-parallel hook): what runs after the all-reduce."""
         g = self.param_groups[0]
+        if getattr(self.arena, "_device_lr", None) is not None and not torch.cuda.is_current_stream_capturing():
+            # a captured step published the learning rate to the device (lr_device overrides the argument from then on): keep it in
+            # step with the scheduler for eager steps as well (cached: a copy only when the value changed)
+            self.arena.set_device_lr(float(g["lr"]))
         self.arena.step(g["lr"], g["betas"], g["eps"], g["weight_decay"], self.decoupled, self.clip_mode, self.max_norm,
                         self.clip_threshold, self.nan_mode, self.grad_scale)
         return None

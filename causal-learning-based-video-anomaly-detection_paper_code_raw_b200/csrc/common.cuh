@@ -125,13 +125,30 @@ static inline cudaError_t cvad_launch_pdl(void (*kernel)(KArgs...), dim3 grid, d
 }
 
 static inline int cvad_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+// Per-DEVICE host-side caches: function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize) and the SM count belong to the current
+// device, and one process may drive several GPUs (tests on cuda:1, single-process inference sharding), so nothing is cached per process.
+constexpr int CVAD_MAX_DEVICES = 64;
+static inline int cvad_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < CVAD_MAX_DEVICES ? dev : 0;
+}
 static inline int cvad_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[CVAD_MAX_DEVICES] = {};
+  const int dev = cvad_current_device();
+  if (!sms[dev]) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = n > 0 ? n : 148;
   }
-  return sms;
+  return sms[dev];
+}
+// Raise a kernel's dynamic shared-memory limit on the current device when `smem` exceeds what was configured there before.
+template <typename Kernel>
+static inline cudaError_t cvad_ensure_dyn_smem(Kernel kernel, size_t smem, size_t (&configured)[CVAD_MAX_DEVICES]) {
+  const int dev = cvad_current_device();
+  if (smem <= configured[dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) configured[dev] = smem;
+  return e;
 }

@@ -401,12 +401,9 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   if (e) return e;
   e = make_tmap_2d(&mw, wpk, w_rows, K, FC_BOX, ROWB / 2, ROWB);
   if (e) return e;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t ce = cudaFuncSetAttribute(flatconv_kernel<ROWB, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return (int)ce;
-    configured = smem;
-  }
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(flatconv_kernel<ROWB, N>, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
   const long long MT = 128LL * p.sub;
   const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
@@ -851,12 +848,9 @@ int launch_wgrad(const void* src, long long src_rows, const void* dy, WgParams& 
   if (e) return e;
   e = make_tmap_2d(&mbt, dy, p.rows, p.Cout, p.b_tail ? p.b_tail : 32, ROWB_B / 2, ROWB_B);
   if (e) return e;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t ce = cudaFuncSetAttribute(flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ce != cudaSuccess) return (int)ce;
-    configured = smem;
-  }
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS, KH>, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
   flatwgrad_kernel<ROWB_A, ROWB_B, NB, A_SLABS, KH><<<dim3((unsigned)chunks, p.ci_blocks * p.co_blocks, p.n_variants), 256, smem, st>>>(ma, mat, mb, mbt, p, dw);
   CVAD_LAUNCH_CHECK();
   return 0;

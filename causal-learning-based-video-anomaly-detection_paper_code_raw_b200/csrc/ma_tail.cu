@@ -451,11 +451,9 @@ CVAD_API int cvad_gru_bwd_f32(const float* dhT, const float* saved, const float*
                               float* dw_hh, float* db_hh, void* stream) {
   if (B <= 0) return 0;
   size_t smem = (size_t)(HID * (3 * HID + 1) + HID + 3 * HID + HID) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(gru_bwd_kernel, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
   gru_bwd_kernel<<<B * MAXDET, 192, smem, (cudaStream_t)stream>>>(dhT, saved, w_hh, ntr, T, dgi, dw_hh, db_hh);
   CVAD_LAUNCH_CHECK();
   return 0;

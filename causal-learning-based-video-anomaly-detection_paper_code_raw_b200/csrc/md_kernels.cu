@@ -226,11 +226,9 @@ CVAD_API int cvad_lstm_bwd_f32(const float* dhT, const float* saved, const float
                                void* stream) {
   if (N <= 0) return 0;
   const size_t smem = (size_t)(LH * (LG + 1) + LH + LH + LG + LH) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_set = true;
-  }
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(lstm_bwd_kernel, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
   lstm_bwd_kernel<<<N, LG, smem, (cudaStream_t)stream>>>(dhT, saved, w_hh, T, dgi, dw_hh, db_hh);
   CVAD_LAUNCH_CHECK();
   return 0;

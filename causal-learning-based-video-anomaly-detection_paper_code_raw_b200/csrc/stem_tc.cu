@@ -69,6 +69,43 @@ __global__ void stem_s2d_kernel(const float* __restrict__ x, StemGeo g, float4* 
   }
 }
 
+// The same from uint8 frames (what cv2.imread hands the reference's dataset, cad:89-96): the Normalize(mean, std) of cad:1177-1179 is applied on the
+// fly, x = (float(v) - mean) / std -- exactly torchvision's sub_().div_() on the FloatTensor, so the result is bit-identical to the fp32
+// path while the frames cross PCIe and are read from HBM at 1 byte per pixel.  Conv padding stays 0 (it pads the NORMALISED tensor).
+__global__ void stem_s2d_u8_kernel(const uint8_t* __restrict__ x, StemGeo g, float mean, float stdv, float4* __restrict__ x4) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.np4; t += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % g.Wq);
+    const long long r = t / g.Wq;
+    const int i = (int)(r % g.Hq), n = (int)(r / g.Hq);
+    const int h0 = 2 * (i - 2), w0 = 2 * (j - 2);
+    const uint8_t* xn = x + (long long)n * g.H * g.W;
+    float v[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int h = h0 + a, w = w0 + b;
+        v[a * 2 + b] = ((unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W) ? ((float)__ldg(xn + (long long)h * g.W + w) - mean) / stdv : 0.f;
+      }
+    x4[t] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// y = (float(v) - mean) / std over a flat uint8 buffer, 16 bytes in / 64 bytes out per thread iteration (fp32 mode of the same input path)
+__global__ void u8_normalize_kernel(const uint8_t* __restrict__ x, long long n, float mean, float stdv, float* __restrict__ y) {
+  const long long n16 = n / 16;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n16; t += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x) + t);
+    const unsigned w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      reinterpret_cast<float4*>(y)[t * 4 + k] = make_float4(((float)(w[k] & 255u) - mean) / stdv, ((float)((w[k] >> 8) & 255u) - mean) / stdv,
+                                                             ((float)((w[k] >> 16) & 255u) - mean) / stdv, ((float)(w[k] >> 24) - mean) / stdv);
+  }
+  for (long long t = n16 * 16 + blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    y[t] = ((float)__ldg(x + t) - mean) / stdv;
+}
+
 // MODE 0: statistics of the raw accumulator (ws[c] += sum acc, ws[32+c] += sum acc^2 over valid rows; the bias is folded in by
 // the finalize kernel).  MODE 1: out = relu((acc + bias - mean) * invstd * gamma + beta) bf16 NHWC (N,Ho,Wo,32).
 template <int MODE>
@@ -337,13 +374,10 @@ int stem_launch(int mode, const float* x4, const float* w, const float* bias, co
   }
   const size_t smem = ST_W_BYTES + 2 * (size_t)g.seg_rows * 128 + 1024 + (mode == 0 ? 0 : 0);
   const size_t need = smem < (size_t)(ST_W_BYTES + 256 * 65 * 4 + 1024) ? (size_t)(ST_W_BYTES + 256 * 65 * 4 + 1024) : smem;
-  static size_t configured = 0;
-  if (need > configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
-    if (e != cudaSuccess) return (int)e;
-    configured = need;
-  }
+  static size_t configured0[CVAD_MAX_DEVICES] = {}, configured1[CVAD_MAX_DEVICES] = {};
+  cudaError_t ce = cvad_ensure_dyn_smem(stem_tf32_kernel<0>, need, configured0);
+  if (ce == cudaSuccess) ce = cvad_ensure_dyn_smem(stem_tf32_kernel<1>, need, configured1);
+  if (ce != cudaSuccess) return (int)ce;
   long long grid = cvad_num_sms();
   if (grid > g.n_tiles) grid = g.n_tiles;
   if (mode == 0)
@@ -368,6 +402,26 @@ CVAD_API int cvad_stem_space_to_depth_f32(const float* x, int N, int H, int W, f
   long long blocks = (g.np4 + 255) / 256;
   if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
   stem_s2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, g, reinterpret_cast<float4*>(x4));
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_stem_space_to_depth_u8(const void* x, int N, int H, int W, float mean, float stdv, float* x4, void* stream) {
+  StemGeo g;
+  if (stem_geo(g, N, H, W) || stdv == 0.f) return (int)cudaErrorInvalidValue;
+  long long blocks = (g.np4 + 255) / 256;
+  if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
+  stem_s2d_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, g, mean, stdv, reinterpret_cast<float4*>(x4));
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_u8_normalize_f32(const void* x, long long n, float mean, float stdv, float* y, void* stream) {
+  if (n <= 0) return 0;
+  if (stdv == 0.f || ((uintptr_t)x & 15) || ((uintptr_t)y & 15)) return (int)cudaErrorInvalidValue;
+  long long blocks = (n / 16 + 255) / 256 + 1;
+  if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
+  u8_normalize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, n, mean, stdv, y);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

@@ -103,3 +103,22 @@ class GraphedStep:
                 s.copy_(t, non_blocking=True)
         self._replay()
         return self.outputs
+
+
+def graphed_optimizer_step(opt, fwd_bwd, example_inputs, mutated):
+    """Capture ``fwd_bwd(*inputs) -> tuple`` (zero_grad + forward + loss + backward) followed by ``opt``'s fused step.
+
+    Single GPU: one graph.  Data parallel (the optimizer carries a gradient all-reduce hook): graph(fwd_bwd) -> eager collective ->
+    graph(fused clip + Adam), because NCCL captured inside a graph stalled an 8-rank run."""
+    import os
+
+    opt.sync_lr_to_device()
+    if opt.pre_step_hook is not None and os.environ.get("CVAD_NCCL_IN_GRAPH", "0") != "1":
+        return GraphedStep(fwd_bwd, example_inputs, mutated, pre_replay=opt.sync_lr_to_device,
+                           between=lambda: opt.pre_step_hook(opt.arena), tail_fn=opt.step_local)
+
+    def step(*inputs):
+        out = fwd_bwd(*inputs)
+        opt.step()
+        return out
+    return GraphedStep(step, example_inputs, mutated, pre_replay=opt.sync_lr_to_device)

@@ -41,6 +41,8 @@ class ResNetBackbone(nn.Module):
         self.layer4 = self._make_layer(128, output_dim, 2, stride=2)
         self.avgpool = nn.AdaptiveAvgPool2d((4, 6))
         self.precision = "fp32"
+        # uint8 input = the loader's raw grayscale frames (cad:89-96); they are normalised on the device as cad:1177-1179 does on the host
+        self.input_mean, self.input_std = 0.5, 0.5
 
     @staticmethod
     def _make_layer(cin, cout, blocks, stride=1):
@@ -56,6 +58,8 @@ class ResNetBackbone(nn.Module):
     def forward(self, x):
         B, T, C, H, W = x.shape
         x = x.reshape(B * T, C, H, W)
+        if x.dtype == torch.uint8 and self.precision != "bf16":
+            x = ops.u8_normalize(x, self.input_mean, self.input_std)
         if self.precision == "bf16":
             from . import tc
             return tc.backbone_forward_bf16(self, x).reshape(B, T, -1)
@@ -348,23 +352,12 @@ class MATrainer:
     def graphed_train_step(self, videos, labels):
         """One CUDA graph for zero_grad + forward + loss + backward (+ all-reduce) + clip/AdamW on this batch shape.
         Returns a callable ``(videos, labels) -> (loss components (5,), anomaly_scores (B,))``."""
-        from .graphs import GraphedStep
+        from .graphs import graphed_optimizer_step
 
-        opt = self.optimizer
-        opt.sync_lr_to_device()
-        if opt.pre_step_hook is not None and os.environ.get("CVAD_NCCL_IN_GRAPH", "0") != "1":
-            # data parallel: graph(zero_grad..backward) -> eager NCCL all-reduce of the gradient arena -> graph(clip+AdamW).
-            # The collective stays outside the captured graphs (NCCL's graph-mode buffer registration stalled an 8-rank run).
-            def fwd_bwd(x, y):
-                comp, out = self.forward_backward(x, y)
-                return comp, out["anomaly_scores"]
-            return GraphedStep(fwd_bwd, (videos, labels), self.mutated_tensors(), pre_replay=opt.sync_lr_to_device,
-                               between=lambda: opt.pre_step_hook(opt.arena), tail_fn=opt.step_local)
-
-        def step(x, y):
-            comp, out = self.train_step(x, y)
+        def fwd_bwd(x, y):
+            comp, out = self.forward_backward(x, y)
             return comp, out["anomaly_scores"]
-        return GraphedStep(step, (videos, labels), self.mutated_tensors(), pre_replay=opt.sync_lr_to_device)
+        return graphed_optimizer_step(self.optimizer, fwd_bwd, (videos, labels), self.mutated_tensors())
 
     @torch.no_grad()
     def eval_step(self, videos, labels):

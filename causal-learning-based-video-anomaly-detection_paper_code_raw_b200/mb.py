@@ -167,6 +167,20 @@ class ImprovedMiniCausalVAD:
         self.optimizer.step()
         return comp
 
+    def graphed_train_step(self, videos, labels):
+        """The same iteration as one CUDA graph (two around the gradient all-reduce under data parallelism): ``(videos, labels) ->
+        ((8,) component tensor,)``.  Pseudo-labels are drawn on the device inside the graph (s2:139-141)."""
+        from .graphs import graphed_optimizer_step
+
+        def fwd_bwd(x, y):
+            self.optimizer.zero_grad()
+            scores, adj, _ = self.model(x)
+            loss, comp = self.loss_on_device(scores, adj, y)
+            loss.backward()
+            return (comp,)
+        a = self.optimizer.arena
+        return graphed_optimizer_step(self.optimizer, fwd_bwd, (videos, labels), [a.p, a.m, a.v, a.state])
+
     def train_epoch_improved(self, dataloader):
         self.model.train()
         acc = torch.zeros(8, device=self.device)

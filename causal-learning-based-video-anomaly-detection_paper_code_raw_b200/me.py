@@ -77,8 +77,19 @@ def score_windows(model, frames, window=8, stride=4, batch=256, device="cuda"):
     if not starts:
         z = torch.zeros(0)
         return np.zeros(0, dtype=np.int64), z.numpy(), np.zeros((0, 16, 16), np.float32), np.zeros((0, model.feature_dim), np.float32)
-    fr = frames.to(dev, non_blocking=True).float()
-    win = fr.unfold(0, window, 1)[::1]                    # (F-window+1, 3, H, W, window) view
+    scores, adjs, feats = score_windows_device(model, frames.to(dev, non_blocking=True), window, stride, batch)
+    return (np.asarray(starts), scores.cpu().numpy(), adjs.cpu().numpy(), feats.cpu().numpy())
+
+
+@torch.no_grad()
+def score_windows_device(model, frames_dev, window=8, stride=4, batch=256):
+    """The device part of ``score_windows``: frames (F,3,H,W) already on the GPU -> (scores (n,), adj (n,16,16), features) device tensors,
+    no host synchronisation."""
+    dev = frames_dev.device
+    F_ = frames_dev.shape[0]
+    starts = list(range(0, F_ - window, stride))
+    fr = frames_dev.float()
+    win = fr.unfold(0, window, 1)                         # (F-window+1, 3, H, W, window) view
     idx = torch.tensor(starts, device=dev)
     scores, adjs, feats = [], [], []
     for i in range(0, len(starts), batch):
@@ -87,7 +98,7 @@ def score_windows(model, frames, window=8, stride=4, batch=256, device="cuda"):
         scores.append(s.reshape(-1))
         adjs.append(a)
         feats.append(f)
-    return (np.asarray(starts), torch.cat(scores).cpu().numpy(), torch.cat(adjs).cpu().numpy(), torch.cat(feats).cpu().numpy())
+    return torch.cat(scores), torch.cat(adjs), torch.cat(feats)
 
 
 def extract_anomalous_windows(model, frames, video_id="video", threshold=0.3, window=8, stride=4, device="cuda"):

@@ -129,6 +129,15 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def u8_normalize(x: torch.Tensor, mean: float, std: float) -> torch.Tensor:
+    """uint8 frames -> fp32 ``(x - mean) / std`` (torchvision Normalize on the reference's FloatTensor frames, cad:1177-1179)."""
+    _cuda(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _call("cvad_u8_normalize_f32", _ptr(x), x.numel(), float(mean), float(std), _ptr(y), _st())
+    return y
+
+
 # ------------------------------------------------------------------------------------------------ convolution
 def _conv_desc(x5, w5, y5, stride, padding) -> ConvDesc:
     d = ConvDesc()

@@ -42,10 +42,22 @@ class DataParallel:
         for w in works:
             w.wait()
 
-    def broadcast_parameters(self, arena, src: int = 0):
+    def broadcast_parameters(self, arena, src: int = 0, model=None):
+        """Make every replica start from rank ``src``'s state: the parameter / Adam-moment arenas, the device-side optimizer state
+        (per-group Adam step counters, skip counter: they matter after a load_state_dict on one rank) and -- when ``model`` is given --
+        every parameter and buffer that does NOT live in the arena (frozen tensors such as M-A's stem, BatchNorm running statistics
+        and num_batches_tracked).  torch's DistributedDataParallel broadcasts buffers the same way."""
         dist.broadcast(arena.p, src=src, group=self.group)
         dist.broadcast(arena.m, src=src, group=self.group)
         dist.broadcast(arena.v, src=src, group=self.group)
+        dist.broadcast(arena.state, src=src, group=self.group)
+        arena._device_lr = None              # the broadcast overwrote lr_device: re-publish on the next sync_lr_to_device()
+        if model is not None:
+            lo, hi = arena.p.data_ptr(), arena.p.data_ptr() + arena.p.numel() * arena.p.element_size()
+            for t in list(model.parameters()) + list(model.buffers()):
+                if lo <= t.data_ptr() < hi:
+                    continue                 # a view into the arena: already sent
+                dist.broadcast(t.data, src=src, group=self.group)
 
     def shard(self, n_items: int):
         """Contiguous shard [lo, hi) of n_items for this rank (inference: disjoint clip shards, no communication)."""

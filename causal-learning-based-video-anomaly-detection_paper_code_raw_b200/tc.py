@@ -73,6 +73,12 @@ class _BackboneBF16(torch.autograd.Function):
             raise RuntimeError("the tensor-core stem implements the reference's 7x7 stride-2 1->32 convolution (cad:115)")
         x = x.contiguous()
         need_bwd = any(ctx.needs_input_grad)
+        if need_bwd and any(p.requires_grad for p in list(conv1.parameters()) + list(bn1.parameters())):
+            # the backward below stops at layer1.0: no gradient is computed for the stem.  That is the reference's training recipe
+            # (apply_memory_efficient_training freezes backbone.conv1 / backbone.bn1, cad:596-598); anything else must not train silently
+            # with all-zero stem gradients
+            raise RuntimeError("cvad_b200 bf16 backbone: backbone.conv1 / backbone.bn1 require grad, but the tensor-core path has no stem "
+                               "backward; freeze them (apply_memory_efficient_training, cad:596-598) or use set_precision('fp32')")
         layers = _layers(bb)
         strides = [conv.stride[0] for conv, _ in layers]
         if strides[0] == 2:
@@ -101,7 +107,10 @@ class _BackboneBF16(torch.autograd.Function):
         if n4 < 0:
             raise RuntimeError(f"frame size {H}x{W} is outside the tensor-core stem's range")
         x4 = torch.empty(n4, device=dev, dtype=torch.float32)       # 2x2 space-to-depth of the batch: 16-byte pixels
-        _call("cvad_stem_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x4), st)
+        if x.dtype == torch.uint8:      # raw frames: Normalize(mean, std) of cad:1177-1179 applied on the fly
+            _call("cvad_stem_space_to_depth_u8", _ptr(x), N, H, W, float(bb.input_mean), float(bb.input_std), _ptr(x4), st)
+        else:
+            _call("cvad_stem_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x4), st)
         x = x4
         if bn1.training:
             _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps),
@@ -153,6 +162,9 @@ class _BackboneBF16(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         bb, saved = ctx.bb, ctx.saved
+        if any(sv is None for sv in saved):
+            raise RuntimeError("cvad_b200 bf16 backbone: backward called a second time; the saved activations are released layer by layer "
+                               "during the first backward (retain_graph is not supported on this path)")
         N, h, w, c = ctx.last
         st = _st()
         dev = dfeat.device
@@ -187,7 +199,8 @@ def backbone_forward_bf16(bb, x):
     """x (B*T, 1, H, W) fp32 -> features (B*T, 6144) fp32."""
     ops._cuda(x)
     params = [p for p in bb.parameters() if p.requires_grad]
-    return _BackboneBF16.apply(x.float().contiguous(), bb, *params)
+    x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
+    return _BackboneBF16.apply(x, bb, *params)
 
 
 # ---- layout helpers (host side; used by the tests and by callers that want NCHW views of the flat buffers)

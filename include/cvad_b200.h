@@ -222,6 +222,12 @@ int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int
  * of a post-ReLU bf16 NHWC tensor into the padded-flat layout. */
 long long cvad_stem_x4_floats(int N, int H, int W);
 int cvad_stem_space_to_depth_f32(const float* x, int N, int H, int W, float* x4, void* stream);
+/* The frame loader's output taken as it is (cad:89-96: cv2.imread grayscale uint8 -> FloatTensor -> Normalize(0.5, 0.5), cad:1177-1179):
+ * x (N,1,H,W) uint8; the space-to-depth applies (float(v) - mean) / std on the fly, bit-identical to normalising on the host, so frames
+ * cross PCIe and HBM at one byte per pixel.  cvad_u8_normalize_f32 is the plain elementwise form (fp32 mode; x and
+ * y 16-byte aligned). */
+int cvad_stem_space_to_depth_u8(const void* x, int N, int H, int W, float mean, float stdv, float* x4, void* stream);
+int cvad_u8_normalize_f32(const void* x, long long n, float mean, float stdv, float* y, void* stream);
 int cvad_stem_tf32_stats(const float* x4, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
                          float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
 int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean, const float* invstd,

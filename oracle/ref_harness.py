@@ -1,9 +1,12 @@
-"""Import harness for the UNMODIFIED reference scripts under /root/reference.
+"""Import harness for the UNMODIFIED reference scripts.
 
-TEST INFRASTRUCTURE ONLY.  Runs in the build container (the reference tree does
-not exist on the GPU box).  It is used by tools/make_golden.py to (a) pin the
-oracle restatement in oracle/ against the real reference code and (b) emit the
-golden fixtures committed under tests/golden/.  Nothing in the product imports it.
+TEST INFRASTRUCTURE ONLY.  Two users:
+  * tools/make_golden.py (build container) imports the scripts from /root/reference to (a) pin the oracle restatement in
+    oracle/ against the real reference code and (b) emit the golden fixtures committed under tests/golden/;
+  * bench.py --impl reference / its cpu_baseline leg import them from ``oracle/_ref`` -- a git-ignored, verbatim copy of the
+    reference's scripts made by ``oracle/build_ref.py`` (run by ``__graft_entry__.build()`` while /root/reference is visible); the
+    copy travels to the GPU box with the snapshot so the timed CPU arm is the reference's own code, Python loops included.
+Nothing in the product imports it.
 
 Shims:
   * stub ``matplotlib`` / ``seaborn`` / ``yolov5`` modules (not installed here);
@@ -23,7 +26,18 @@ import types
 import torch
 import torch.nn as nn
 
+import os
+
 REF_DIR = "/root/reference"
+LOCAL_REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_dir() -> str | None:
+    """Where the unmodified reference scripts can be imported from: /root/reference (build container) or oracle/_ref (GPU box)."""
+    for d in (REF_DIR, LOCAL_REF_DIR):
+        if os.path.exists(os.path.join(d, "causal_anomaly_detection.py")):
+            return d
+    return None
 
 
 class _Anything:
@@ -73,11 +87,12 @@ def install_stubs() -> None:
         sched.ReduceLROnPlateau = ReduceLROnPlateau
 
 
-def import_ref(modname: str):
+def import_ref(modname: str, ref_dir: str | None = None):
     """Import one reference script as a module (its prints are swallowed)."""
     install_stubs()
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    ref_dir = ref_dir or reference_dir() or REF_DIR
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
     with contextlib.redirect_stdout(io.StringIO()):
         mod = importlib.import_module(modname)
     return mod

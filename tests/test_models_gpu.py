@@ -438,6 +438,30 @@ def test_ma_c2_benchmarked_shape_bf16(dev, gold, idx):
             assert rel(sd[k].float(), v.float()) < 5e-3, k
 
 
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_ma_uint8_frames_equal_host_normalised_frames(dev, precision):
+    """raw uint8 grayscale frames (cad:89-96) normalised on the device give bit-identical scores to the reference's
+    host-side Normalize(0.5, 0.5) (cad:1177-1179) -- the input crosses PCIe at 1 byte per pixel instead of 4."""
+    from test_oracle_golden import ma_synth_state
+    from cvad_b200.ma import CausalAnomalyDetector
+    from cvad_b200.noise import FixedNoise
+    B, T, H, W = 3, 4, 120, 180
+    u8 = torch.randint(0, 256, (B, T, 1, H, W), generator=synth.gen(5), dtype=torch.uint8)
+    xf = (u8.float() - 0.5) / 0.5
+    m = CausalAnomalyDetector()
+    m.load_state_dict(ma_synth_state(4, True), strict=True)
+    m = m.to(dev).eval().set_precision(precision)
+    eps = torch.randn(B, 5, 6, generator=synth.gen(6))
+    outs = []
+    for x in (xf, u8):
+        m.noise = FixedNoise({"eps": eps})
+        with torch.no_grad():
+            outs.append(m(x.to(dev)))
+    assert torch.equal(outs[0]["anomaly_scores"], outs[1]["anomaly_scores"])
+    assert torch.equal(outs[0]["dense"]["features"], outs[1]["dense"]["features"])
+
+
 # 3 optimizer steps against the reference's own train_model loop (cad:609-709: AdamW 3e-4 / 1e-5, clip_grad_norm_ 1.0, frozen stem).
 # Distance measure: |ours - ref|_2 / |ref - start|_2 per tensor on a strided sample.  Adam's first steps move every element by ~lr
 # whatever its gradient's size, so elements whose gradient is round-off-sized differ by O(lr) between ANY two summation orders: the

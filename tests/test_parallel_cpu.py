@@ -29,6 +29,7 @@ class _FakeArena:
         self.p = torch.full((n,), float(10 + rank))
         self.m = torch.full((n,), float(20 + rank))
         self.v = torch.full((n,), float(30 + rank))
+        self.state = torch.full((96,), rank + 1, dtype=torch.uint8)      # device-side optimizer state (step counters, skip counter)
 
 
 class _FakeOpt:
@@ -56,8 +57,17 @@ def _worker(rank, world, port, buckets, q):
     opt.pre_step_hook(arena)
     ok = bool((arena.g[16:] == sum(range(1, world + 1))).all())
     ok &= float(arena.g[0]) == 1.0 and float(arena.g[2]) == 1.0 and float(arena.g[1]) == 0.0   # every rank sees the flags
-    dp.broadcast_parameters(arena, src=0)
-    ok &= bool((arena.p == 10).all() and (arena.m == 20).all() and (arena.v == 30).all())
+    # a model with one arena-managed parameter (a view into arena.p), one frozen parameter outside the arena (M-A's stem) and
+    # BatchNorm buffers: after the broadcast the FULL state_dict must agree across ranks (what torch DDP guarantees too)
+    model = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.BatchNorm1d(4))
+    with torch.no_grad():
+        for t in list(model.parameters()) + list(model.buffers()):
+            t.fill_(rank + 1)
+    model[0].weight.data = arena.p[1024:1040].view(4, 4)
+    model[0].bias.requires_grad = False
+    dp.broadcast_parameters(arena, src=0, model=model)
+    ok &= bool((arena.p == 10).all() and (arena.m == 20).all() and (arena.v == 30).all() and (arena.state == 1).all())
+    ok &= all(bool((v == (10 if k == "0.weight" else 1)).all()) for k, v in model.state_dict().items())
     lo, hi = dp.shard(11)
     q.put((rank, ok, lo, hi))
     dist.barrier()

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import synth  # noqa: E402
-from ref_harness import NoiseInjector, import_ref  # noqa: E402
+from oracle.ref_harness import NoiseInjector, import_ref  # noqa: E402
 
 from oracle import ma as o_ma  # noqa: E402
 from oracle import mb as o_mb  # noqa: E402
