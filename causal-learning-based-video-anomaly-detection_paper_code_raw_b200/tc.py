@@ -73,12 +73,6 @@ class _BackboneBF16(torch.autograd.Function):
             raise RuntimeError("the tensor-core stem implements the reference's 7x7 stride-2 1->32 convolution (cad:115)")
         x = x.contiguous()
         need_bwd = any(ctx.needs_input_grad)
-        if need_bwd and any(p.requires_grad for p in list(conv1.parameters()) + list(bn1.parameters())):
-            # the backward below stops at layer1.0: no gradient is computed for the stem.  That is the reference's training recipe
-            # (apply_memory_efficient_training freezes backbone.conv1 / backbone.bn1, cad:596-598); anything else must not train silently
-            # with all-zero stem gradients
-            raise RuntimeError("cvad_b200 bf16 backbone: backbone.conv1 / backbone.bn1 require grad, but the tensor-core path has no stem "
-                               "backward; freeze them (apply_memory_efficient_training, cad:596-598) or use set_precision('fp32')")
         layers = _layers(bb)
         strides = [conv.stride[0] for conv, _ in layers]
         if strides[0] == 2:
@@ -198,6 +192,12 @@ class _BackboneBF16(torch.autograd.Function):
 def backbone_forward_bf16(bb, x):
     """x (B*T, 1, H, W) fp32 -> features (B*T, 6144) fp32."""
     ops._cuda(x)
+    if torch.is_grad_enabled() and any(p.requires_grad for p in list(bb.conv1.parameters()) + list(bb.bn1.parameters())):
+        # the backward stops at layer1.0: no gradient is computed for the stem.  That is the reference's training recipe
+        # (apply_memory_efficient_training freezes backbone.conv1 / backbone.bn1, cad:596-598); anything else must not train silently
+        # with all-zero stem gradients
+        raise RuntimeError("cvad_b200 bf16 backbone: backbone.conv1 / backbone.bn1 require grad, but the tensor-core path has no stem "
+                           "backward; freeze them (apply_memory_efficient_training, cad:596-598) or use set_precision('fp32')")
     params = [p for p in bb.parameters() if p.requires_grad]
     x = x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()
     return _BackboneBF16.apply(x, bb, *params)

@@ -249,6 +249,26 @@ int cvad_memory_score_f32(const float* seq, const float* memory, int B, int n_fi
 int cvad_recon_mse_f32(const float* recon, long long recon_t_stride, const float* frames, int B, int T, long long E, double* ws,
                        float* clip_err, float* loss, float* drecon, float* nonfinite_flag, void* stream);
 
+/* ---- evaluation tail on the device: the numpy / sklearn host code that follows the hot path in the reference.
+ * workspace: cvad_eval_workspace_bytes(n) bytes of device memory (caller-owned, any contents).
+ * cvad_sort_scores_f32        ascending sort (NaNs last, like np.sort) of n float32 scores; sorted (n) and/or order (n, int32) may be NULL.
+ * cvad_percentile_sorted_f32  np.percentile(scores, q) of s1:60 / cad1:609 / cad1:709 (method 'linear', float32 arithmetic exactly as numpy
+ *                             performs it for a float32 array: bit-identical threshold), from the sorted scores.
+ * cvad_threshold_labels_f32   labels = (scores > *threshold) as 0/1 floats (s1:61).
+ * cvad_roc_auc_f32            sklearn.metrics.roc_auc_score of mc3:388 / cad:1233-1248 as the rank statistic with average ranks for ties
+ *                             (fp64); 0.0 when one class is absent.  targets: 0/1 floats.
+ * cvad_mb_eval_metrics_f32    the 8 entries of s2:286-295 from scores (n) and graphs (n,row_len): mean, std, min, max, range of the scores,
+ *                             mean count of entries > edge_threshold, that count / row_len, number of distinct rows (np.unique(axis=0)).
+ * cvad_moving_average_f32     np.convolve(x, ones(w)/w, 'valid') of cad:1085-1087 / vad:833-835 in fp64; out holds n-w+1 doubles. */
+long long cvad_eval_workspace_bytes(long long n);
+int cvad_sort_scores_f32(const float* scores, long long n, void* workspace, float* sorted, int* order, void* stream);
+int cvad_percentile_sorted_f32(const float* sorted, long long n, float q, float* out, void* stream);
+int cvad_threshold_labels_f32(const float* scores, long long n, const float* threshold, float* labels, void* stream);
+int cvad_roc_auc_f32(const float* scores, const float* targets, long long n, void* workspace, double* auc, void* stream);
+int cvad_mb_eval_metrics_f32(const float* scores, const float* graphs, long long n, int row_len, float edge_threshold, void* workspace,
+                             double* out8, void* stream);
+int cvad_moving_average_f32(const float* x, long long n, int w, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
