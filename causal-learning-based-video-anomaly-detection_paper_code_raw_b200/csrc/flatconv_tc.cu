@@ -63,6 +63,12 @@ struct FcParams {
   long long out_row_base;
   int n_units, seg_rows, sub, n_blocks, ld_out, wst, w_resident;
   int big_boxes, tail_rows;      // segment = big_boxes x 256 rows + one exact tail box (0 = none)
+  // "planes": independent sub-problems walked by ONE launch (the four phase planes of a stride-2 data-gradient).  Plane pl uses units
+  // [plane_unit0[pl], + plane_nunits[pl]) and writes its rows at out_row_base + pl * plane_out_stride.  n_planes <= 1: a single plane
+  // made of units [0, n_units).
+  int n_planes;
+  int plane_unit0[4], plane_nunits[4];
+  long long plane_out_stride;
   // fused BatchNorm statistics (forward only, n_blocks == 1): per-channel sum / sum of squares of the bf16-rounded outputs over the
   // interior pixels (1..st_h, 1..st_w of every (st_h+2) x (st_w+2) image), added to st_out[0..N) / st_out[N..2N) (fp64, zeroed by the caller)
   int st_h, st_w;
@@ -129,7 +135,9 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   const int sub = p.sub, n_units = p.n_units, n_blocks = p.n_blocks, wst = p.wst, resident = p.w_resident;
   const int MT = 128 * sub;
   const long long n_tiles = (p.rows + MT - 1) / MT;
-  const long long total = n_tiles * n_blocks;
+  const long long per_plane = n_tiles * n_blocks;
+  const int n_planes = p.n_planes > 1 ? p.n_planes : 1;
+  const long long total = per_plane * n_planes;
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
@@ -150,8 +158,10 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     // ------------------------------------------------------------------ TMA producer: activation segments
     uint32_t src_cnt = 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const long long q0 = (wi / n_blocks) * MT;
-      for (int u = 0; u < n_units; ++u) {
+      const int pl = (int)(wi / per_plane);
+      const long long q0 = ((wi % per_plane) / n_blocks) * MT;
+      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      for (int u = u0; u < u0 + nu; ++u) {
         const int st = src_cnt & 1;
         mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
         if (elect_one()) {
@@ -170,9 +180,11 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     uint32_t w_cnt = 0;
     bool first_item = true;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const int nb = (int)(wi % n_blocks);
+      const int pl = (int)(wi / per_plane);
+      const int nb = (int)((wi % per_plane) % n_blocks);
       if (resident && !first_item) break;
-      for (int u = 0; u < n_units; ++u) {
+      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      for (int u = u0; u < u0 + nu; ++u) {
         const int ntaps = p.units[u].ntaps, col = p.units[u].col;
         const int row0 = p.units[u].w_row0 + nb * 9 * N;
         for (int c = 0; c * TPO < ntaps; ++c) {
@@ -199,7 +211,9 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const long long t_loop_ns = dbg ? (long long)globaltimer_ns() : 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       ++n_items;
-      for (int u = 0; u < n_units; ++u) {
+      const int pl = (int)(wi / per_plane);
+      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      for (int u = u0; u < u0 + nu; ++u) {
         const int ntaps = p.units[u].ntaps;
         const int st = src_cnt & 1;
         long long tq = dbg ? clock64() : 0;
@@ -216,8 +230,8 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           const int tin = ntaps - c * TPO < TPO ? ntaps - c * TPO : TPO;
           for (int j = 0; j < tin; ++j) {
             const int t = c * TPO + j;
-            const bool first = (u == 0 && t == 0);
-            const bool last = (u == n_units - 1 && t == ntaps - 1);
+            const bool first = (u == u0 && t == 0);
+            const bool last = (u == u0 + nu - 1 && t == ntaps - 1);
             // descriptors advance by plain adds: (bytes >> 4) never carries out of the 14-bit address field (smem < 256 KiB)
             const uint64_t db0 = desc_hi | (uint64_t)(((s_w + ws * WBOX_BYTES + j * (N * ROWB)) >> 4) & 0x3FFF);
             const uint64_t da0 = desc_hi | (uint64_t)(((a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB) >> 4) & 0x3FFF);
@@ -279,8 +293,9 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
 #pragma unroll
     for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const long long q0 = (wi / n_blocks) * MT;
-      const int nb = (int)(wi % n_blocks);
+      const int pl = (int)(wi / per_plane);
+      const long long q0 = ((wi % per_plane) / n_blocks) * MT;
+      const int nb = (int)((wi % per_plane) % n_blocks);
       if (nb != cur_nb) {                       // stage this n-block's bias once (epilogue warps only: named barrier 1)
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         tc_fence_after();
         const long long q = q0 + s * 128 + ew * 32 + lane;
         const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
-        __nv_bfloat16* orow = out + (p.out_row_base + q) * (long long)p.ld_out + nb * N;
+        __nv_bfloat16* orow = out + (p.out_row_base + pl * p.plane_out_stride + q) * (long long)p.ld_out + nb * N;
         bool keep = false;                    // interior pixel (the only ones BatchNorm statistics run over)
         if (p.st_out && q < p.rows) {
           const int qi = (int)q;
@@ -358,6 +373,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
 
 // ---------------------------------------------------------------------------------------------- host side
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+bool g_dgrad_one_launch = true;        // cvad_flat_dgrad_mode(0): one launch per phase plane (A/B measurements)
 // Output-channel block = the MMA's N.  One M128 x N x K16 MMA streams 4 KB of A plus N*32 B of B from shared memory at ~80-90 B/cycle
 // (profiles/r01g_flatconv_L0_ncu_full.md), so it is operand-bound below N = 256: take the widest N the layer allows.
 inline int n_block_of(int nout) { return nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32)); }
@@ -378,7 +394,7 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   p.sub = 0;
   for (int sub : cand) {
     if (sub > sub_max) continue;
-    const long long items = ((p.rows + 128LL * sub - 1) / (128LL * sub)) * p.n_blocks;
+    const long long items = ((p.rows + 128LL * sub - 1) / (128LL * sub)) * p.n_blocks * (p.n_planes > 1 ? p.n_planes : 1);
     if (sub > 1 && items < (3LL * cvad_num_sms()) / 2) continue;
     const int seg = round_up(128 * sub + max_delta, 64);
     if (2 * (size_t)seg * ROWB + 1024 + 2 * (size_t)FC_BOX * ROWB > FC_SMEM_BUDGET) continue;
@@ -390,7 +406,7 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   const size_t fixed = 2 * (size_t)p.seg_rows * ROWB + 1024;
   long long wst = (long long)((FC_SMEM_BUDGET - fixed) / ((size_t)FC_BOX * ROWB));
   p.wst = (int)(wst > FC_WST_MAX ? FC_WST_MAX : wst);
-  p.w_resident = (p.n_units == 1 && p.n_blocks == 1 && max_chunks <= p.wst) ? 1 : 0;
+  p.w_resident = (p.n_units == 1 && p.n_blocks == 1 && p.n_planes <= 1 && max_chunks <= p.wst) ? 1 : 0;
   p.big_boxes = p.seg_rows / FC_BOX;
   p.tail_rows = p.seg_rows % FC_BOX;
   const size_t smem = fixed + (size_t)p.wst * FC_BOX * ROWB;
@@ -405,7 +421,7 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   const cudaError_t ce = cvad_ensure_dyn_smem(flatconv_kernel<ROWB, N>, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
   const long long MT = 128LL * p.sub;
-  const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks;
+  const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks * (p.n_planes > 1 ? p.n_planes : 1);
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
   flatconv_kernel<ROWB, N><<<grid, 384, smem, st>>>(ms, mt, mw, p, bias, out);
   CVAD_LAUNCH_CHECK();
@@ -464,6 +480,11 @@ __global__ void pack_w3x3_flat_kernel(const float* __restrict__ w, int Co, int C
 // development hook: device buffer of 8 int64 per CTA (NULL switches the instrumentation off)
 CVAD_API int cvad_flat_debug_buffer(long long* buf) {
   return (int)cudaMemcpyToSymbol(g_fc_debug, &buf, sizeof(buf));
+}
+
+CVAD_API int cvad_flat_dgrad_mode(int one_launch) {
+  g_dgrad_one_launch = one_launch != 0;
+  return 0;
 }
 
 CVAD_API int cvad_flat_pack_w3x3_bf16(const float* w, int Cout, int Cin, int stride, void* w_fwd, void* w_dgrad, void* stream) {
@@ -576,6 +597,34 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
   const long long rows = (long long)N * (Ho + 2) * Wq;
+  if (g_dgrad_one_launch && 4 * nslab <= FC_MAX_UNITS) {
+    // all four phase planes in one launch: plane pl is a set of work items with its own units (its 4 / 2 / 2 / 1 taps) and its own
+    // output offset; one drain and one pass over dy instead of four
+    FcParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows;
+    p.n_planes = 4;
+    p.plane_out_stride = rows;
+    p.n_units = 4 * nslab;
+    for (int pl = 0; pl < 4; ++pl) {
+      int first, count;
+      plane_taps(pl, first, count);
+      p.plane_unit0[pl] = pl * nslab;
+      p.plane_nunits[pl] = nslab;
+      for (int s = 0; s < nslab; ++s) {
+        FcUnit& u = p.units[pl * nslab + s];
+        u.row_off = -(Wq + 1);
+        u.col = s * slab;
+        u.ntaps = count;
+        u.w_row0 = first * nblk;
+        for (int i = 0; i < count; ++i) {
+          const int t = packed_tap(2, first + i), kh = t / 3, kw = t % 3;
+          u.tap_delta[i] = (Wq + 1) - ((kh >> 1) * Wq + (kw >> 1));
+        }
+      }
+    }
+    return run_flat(dy, rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
+  }
   for (int pl = 0; pl < 4; ++pl) {
     FcParams p;
     memset(&p, 0, sizeof(p));

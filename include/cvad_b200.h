@@ -198,6 +198,8 @@ int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N
  * return): coalesced reductions along Cin, then one pass adds the staging buffer into dw (OIHW). */
 int cvad_flat_conv3x3_wgrad_staged_bf16(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin, int Cout,
                                         int stride, void* stream);
+/* development switch: 1 (default) = a stride-2 data-gradient is one launch walking its four phase planes, 0 = four launches */
+int cvad_flat_dgrad_mode(int one_launch);
 /* development switch: 1 (default) = stride-1 32->32 / 64->64 weight gradients stack the three kernel rows in the MMA's N dimension,
  * 0 = one kernel row per MMA */
 int cvad_flat_wgrad_mode(int kh_stack);
