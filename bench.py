@@ -290,14 +290,15 @@ def run_reference(args):
 
 
 # ============================================================================================ M-A train step (headline)
-def profile_calls(tr, x_dev, y_dev, path, reps=5):
-    """Per-ABI-call time inside the replayed step graph (external CUDA events around EVERY call of libcvad_b200.so), written as a
-    markdown table: where the step's milliseconds go, including what is not ours (torch fills / RNG) as the unbracketed rest."""
+def profile_graph(make_graph, path, title, reps=5):
+    """Per-ABI-call time inside a replayed step graph (external CUDA events around EVERY call of libcvad_b200.so), written as a markdown
+    table: where the step's microseconds go, including what is not ours (torch fills / RNG / copies) as the unbracketed rest.
+    ``make_graph()`` captures the step and returns a zero-argument callable that replays it."""
     from cvad_b200 import ops
     ops.TIMED.clear()
     ops.TIMED_NAMES.add("*")
     ops.TIMED_CAPTURE_ONLY[0] = True
-    gp = tr.graphed_train_step(x_dev, y_dev)
+    replay = make_graph()
     ops.TIMED_CAPTURE_ONLY[0] = False
     ops.TIMED_NAMES.clear()
     acc = {k: 0.0 for k in ops.TIMED}
@@ -305,14 +306,14 @@ def profile_calls(tr, x_dev, y_dev, path, reps=5):
     total = 0.0
     for i in range(reps + 1):
         e0.record()
-        gp(x_dev, y_dev)
+        replay()
         e1.record()
         torch.cuda.synchronize()
         if i:
             total += e0.elapsed_time(e1) / reps
             for k, v in ops.TIMED.items():
                 acc[k] += sum(s.elapsed_time(e) for s, e in v) / reps
-    lines = [f"# per-call time inside the replayed M-A train-step graph (batch 32, external CUDA events, mean of {reps} replays)\n",
+    lines = [f"# per-call time inside the replayed {title} (external CUDA events, mean of {reps} replays)\n",
              f"step (instrumented graph) {total * 1e3:.0f} us; sum of bracketed calls {sum(acc.values()) * 1e3:.0f} us "
              "(calls on the side streams overlap the main chain, so the sum may exceed the step)\n",
              "| ABI call | calls | us | share of step |", "|---|---:|---:|---:|"]
@@ -321,7 +322,13 @@ def profile_calls(tr, x_dev, y_dev, path, reps=5):
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     ops.TIMED.clear()
-    del gp
+
+
+def profile_calls(tr, x_dev, y_dev, path, reps=5):
+    def make():
+        gp = tr.graphed_train_step(x_dev, y_dev)
+        return lambda: gp(x_dev, y_dev)
+    profile_graph(make, path, "M-A train-step graph (batch 32)", reps)
 
 
 def ma_self_check(dev, precision, frames):
@@ -575,6 +582,11 @@ def run_small(args, rank, local, world, dev, dp):
             for gph, s in zip(graphs, [gg.static_inputs[0] for gg in graphs]):
                 gph(s)
             return graphs[-1].outputs[0]
+
+        def make_profiled():
+            with torch.no_grad():
+                gps = [GraphedStep(lambda x: (model(x),), (h.to(dev),)) for h in hosts]
+            return lambda: [gp(gp.static_inputs[0]) for gp in gps]
         pins = [h.pin_memory() for h in hosts]
 
         def step_e2e():
@@ -621,6 +633,10 @@ def run_small(args, rank, local, world, dev, dp):
 
         def step_dev():
             return gph(*gph.static_inputs)[0]
+
+        def make_profiled():
+            gp = tr.graphed_train_step(x_host.to(dev), y_host.to(dev))
+            return lambda: gp(*gp.static_inputs)
         xp, yp = x_host.pin_memory(), y_host.pin_memory()
 
         def step_e2e():
@@ -657,6 +673,8 @@ def run_small(args, rank, local, world, dev, dp):
             extra["batch1_loop_clips_per_s_same_gpu"] = n / (time.perf_counter() - t0)
     else:
         raise ValueError(wl)
+    if wl == "me_windows":
+        make_profiled = None
 
     def barrier():
         if world > 1:
@@ -690,6 +708,8 @@ def run_small(args, rank, local, world, dev, dp):
     barrier()
     ms_e2e = t0.elapsed_time(t1)
     sampler.stop_flag = True
+    if args.profile_calls and rank == 0 and make_profiled is not None:
+        profile_graph(make_profiled, args.profile_calls, f"{wl} step graph")
     if world > 1:
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

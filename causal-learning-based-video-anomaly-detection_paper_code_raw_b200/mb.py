@@ -198,7 +198,11 @@ class ImprovedMiniCausalVAD:
         return avg_loss, avg_components
 
     @torch.no_grad()
-    def evaluate_improved(self, dataloader):
+    def evaluate_improved(self, dataloader, return_arrays: bool = True):
+        """s2:265-297.  The eight metrics are computed on the device (evaltail.mb_eval_metrics: one read-back of 8 scalars); the score and
+        graph arrays the reference returns are copied to the host only when ``return_arrays`` (the reference's callers s2:426 keep the
+        predictions; pass False to leave the (N,16,16) graphs on the device and get ``(None, None, metrics)``)."""
+        from . import evaltail
         self.model.eval()
         preds, graphs = [], []
         for videos, _ in dataloader:
@@ -206,17 +210,13 @@ class ImprovedMiniCausalVAD:
             s, a, _f = self.model(videos)
             preds.append(s.reshape(-1))
             graphs.append(a)
-        predictions = torch.cat(preds).cpu().numpy()
-        causal_graphs = torch.cat(graphs).cpu().numpy()
-        e = np.sum(causal_graphs > 0.1, axis=(1, 2))
-        eval_metrics = {
-            "mean_score": float(np.mean(predictions)), "std_score": float(np.std(predictions)),
-            "min_score": float(np.min(predictions)), "max_score": float(np.max(predictions)),
-            "score_range": float(np.max(predictions) - np.min(predictions)),
-            "avg_edges": float(np.mean(e)), "avg_sparsity": float(np.mean(e / 256)),
-            "unique_graphs": len(np.unique(causal_graphs.reshape(len(causal_graphs), -1), axis=0)),
-        }
-        return predictions, causal_graphs, eval_metrics
+        p_dev, g_dev = torch.cat(preds), torch.cat(graphs)
+        vals = evaltail.mb_eval_metrics(p_dev, g_dev, 0.1).tolist()
+        eval_metrics = dict(zip(evaltail.METRIC_KEYS, vals))
+        eval_metrics["unique_graphs"] = int(eval_metrics["unique_graphs"])
+        if not return_arrays:
+            return None, None, eval_metrics
+        return p_dev.cpu().numpy(), g_dev.cpu().numpy(), eval_metrics
 
 
 class MiniCausalVAD(ImprovedMiniCausalVAD):
@@ -250,12 +250,14 @@ def create_unsupervised_labels(test_loader, model, threshold_percentile=95):
     """avenue_training_script1.py:36-67: scores of the whole loader, their percentile threshold and the pseudo-labels above it.
     ``model`` is a MiniCausalVAD-style trainer (``.model`` callable returning a 3-tuple, ``.device``).  Scores stay on the
     device until one concatenated read-back (the reference copies every batch)."""
+    from . import evaltail
     model.model.eval()
     parts = []
     for videos, _ in test_loader:
         s, _, _ = model.model(videos.to(model.device, non_blocking=True))
         parts.append(s.reshape(-1))
-    all_scores = torch.cat(parts).cpu().numpy() if parts else np.zeros(0, dtype=np.float32)
-    threshold = float(np.percentile(all_scores, threshold_percentile)) if all_scores.size else 0.0
-    pseudo_labels = (all_scores > threshold).astype(float)
-    return all_scores, pseudo_labels, threshold
+    if not parts:
+        return np.zeros(0, dtype=np.float32), np.zeros(0), 0.0
+    scores = torch.cat(parts)
+    thr, labels = evaltail.percentile_labels(scores, float(threshold_percentile))      # np.percentile + comparison, on the device
+    return scores.cpu().numpy(), labels.cpu().numpy().astype(float), float(thr)

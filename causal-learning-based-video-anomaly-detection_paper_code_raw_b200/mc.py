@@ -146,14 +146,19 @@ class StableTrainer:
             tgts.append(targets)
         if not outs:
             return float("inf"), 0.0, 0
-        o = torch.cat(outs).cpu().numpy()
-        t = torch.cat(tgts).cpu().numpy()
-        ls = torch.stack(losses).cpu().numpy()
-        good = np.isfinite(o)
-        avg_loss = float(ls[np.isfinite(ls)].sum() / len(self.test_loader))
-        acc = float(((o[good] > 0.5) == (t[good] > 0.5)).mean()) if good.any() else 0
-        auc = roc_auc(t[good], o[good]) if good.any() and len(set(t[good].tolist())) > 1 else 0.0
-        return avg_loss, auc, acc
+        # mc3:372-390 on the device: non-finite outputs are dropped, accuracy at 0.5, rank-based ROC-AUC (evaltail.roc_auc);
+        # one read-back of four scalars instead of every output and target
+        from . import evaltail
+        o, t, ls = torch.cat(outs), torch.cat(tgts), torch.stack(losses)
+        good = torch.isfinite(o)
+        og, tg = o[good], t[good]
+        finite_ls = torch.where(torch.isfinite(ls), ls, torch.zeros_like(ls)).sum().double().reshape(1)
+        correct = ((og > 0.5) == (tg > 0.5)).double().sum().reshape(1)
+        auc = evaltail.roc_auc(og, tg) if og.numel() else torch.zeros(1, device=o.device, dtype=torch.float64)
+        vals = torch.cat([finite_ls, correct, auc, torch.tensor([float(og.numel())], device=o.device, dtype=torch.float64)]).tolist()
+        avg_loss = vals[0] / len(self.test_loader)
+        acc = vals[1] / vals[3] if vals[3] > 0 else 0
+        return avg_loss, (vals[2] if vals[3] > 0 else 0.0), acc
 
     def train_model(self, epochs, save_path="simple_anomaly_model.pth"):
         for epoch in range(epochs):
