@@ -290,7 +290,7 @@ def run_reference(args):
 
 
 # ============================================================================================ M-A train step (headline)
-def profile_graph(make_graph, path, title, reps=5):
+def profile_graph(make_graph, path, title, reps=5, spans=()):
     """Per-ABI-call time inside a replayed step graph (external CUDA events around EVERY call of libcvad_b200.so), written as a markdown
     table: where the step's microseconds go, including what is not ours (torch fills / RNG / copies) as the unbracketed rest.
     ``make_graph()`` captures the step and returns a zero-argument callable that replays it."""
@@ -302,6 +302,7 @@ def profile_graph(make_graph, path, title, reps=5):
     ops.TIMED_CAPTURE_ONLY[0] = False
     ops.TIMED_NAMES.clear()
     acc = {k: 0.0 for k in ops.TIMED}
+    span_acc = [0.0] * len(spans)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     total = 0.0
     for i in range(reps + 1):
@@ -313,12 +314,17 @@ def profile_graph(make_graph, path, title, reps=5):
             total += e0.elapsed_time(e1) / reps
             for k, v in ops.TIMED.items():
                 acc[k] += sum(s.elapsed_time(e) for s, e in v) / reps
+            for j, (a, b, _) in enumerate(spans):       # from the END of the last call named a to the START of the first call named b
+                if a in ops.TIMED and b in ops.TIMED:
+                    span_acc[j] += ops.TIMED[a][-1][1].elapsed_time(ops.TIMED[b][0][0]) / reps
     lines = [f"# per-call time inside the replayed {title} (external CUDA events, mean of {reps} replays)\n",
              f"step (instrumented graph) {total * 1e3:.0f} us; sum of bracketed calls {sum(acc.values()) * 1e3:.0f} us "
              "(calls on the side streams overlap the main chain, so the sum may exceed the step)\n",
              "| ABI call | calls | us | share of step |", "|---|---:|---:|---:|"]
     for k, v in sorted(acc.items(), key=lambda kv: -kv[1]):
         lines.append(f"| `{k}` | {len(ops.TIMED[k])} | {v * 1e3:.1f} | {100 * v / total:.1f}% |")
+    for (a, b, label), v in zip(spans, span_acc):
+        lines.append(f"\n{label}: {v * 1e3:.0f} us (end of `{a}` -> start of `{b}` on the main stream)")
     with open(path, "w") as f:
         f.write("\n".join(lines) + "\n")
     ops.TIMED.clear()
@@ -328,7 +334,10 @@ def profile_calls(tr, x_dev, y_dev, path, reps=5):
     def make():
         gp = tr.graphed_train_step(x_dev, y_dev)
         return lambda: gp(x_dev, y_dev)
-    profile_graph(make, path, "M-A train-step graph (batch 32)", reps)
+    profile_graph(make, path, "M-A train-step graph (batch 32)", reps,
+                  spans=[("cvad_pad_avgpool_bf16_fwd", "cvad_pad_avgpool_bf16_bwd", "dense tail on the critical path (detector ... loss ... classifier backward)"),
+                         ("cvad_stem_space_to_depth_u8", "cvad_pad_maxpool3x3s2_bf16", "stem passes"),
+                         ("cvad_pad_avgpool_bf16_bwd", "cvad_sumsq_f32", "backbone backward")])
 
 
 def ma_self_check(dev, precision, frames):

@@ -31,7 +31,51 @@ struct Geo {
   long long xs[5], ys[5];
   int taps, K;            // taps = kD*kH*kW, K = Cin*taps
   long long Pout, Pin;    // N*Dout*Hout*Wout, N*Din*Hin*Win
+  unsigned m_taps, s_taps, m_khw, s_khw, m_kw, s_kw;      // multiply-shift forms of / taps, / (kH*kW), / kW (the gathers run them per element)
+  unsigned m_wo, s_wo, m_ho, s_ho, m_do, s_do;            // / Wout, / Hout, / Dout (position decode; used when Pout < 2^31)
+  int small;                                               // Pout and Pin below 2^31: 32-bit position arithmetic
 };
+
+// Strided data-gradient, one launch per PARITY CLASS of input positions (blockIdx.z = class).  With stride s an input coordinate i only
+// meets the kernel taps k with (i + p - k) % s == 0, so gathering all taps (the transposed-convolution view) multiplies 1 - 1/s^dims of
+// the operands by structural zeros: 7/8 of the work of a stride-2 3-D convolution.  A class fixes (i % s) per dimension; its rows are the
+// positions of that class, its reduction runs over (co, the taps that do meet them), and everything it touches is dense.
+struct Phase {
+  int pd, ph, pw;         // parity of (id, ih, iw) modulo the stride
+  int Dc, Hc, Wc;         // positions of this class per dimension
+  int kd0, kh0, kw0;      // first matching tap per dimension
+  int nkd, nkh, nkw;      // matching taps per dimension
+  long long rows;         // N*Dc*Hc*Wc
+  unsigned m_pt, s_pt, m_hw, s_hw, m_w, s_w;              // / (nkd*nkh*nkw), / (nkh*nkw), / nkw
+};
+
+__host__ __device__ inline void fdiv_init(unsigned d, unsigned& mul, unsigned& shr) {
+  if (d <= 1) { mul = 0; shr = 0; return; }
+  unsigned lg = 0;
+  while ((1u << lg) < d) ++lg;
+  const unsigned p = 31 + lg;
+  mul = (unsigned)(((1ull << p) + d - 1) / d);
+  shr = p - 32;
+}
+
+__host__ __device__ inline Phase make_phase(const Geo& g, int cls) {
+  Phase f;
+  f.pw = cls % g.sW; cls /= g.sW;
+  f.ph = cls % g.sH; cls /= g.sH;
+  f.pd = cls;
+  f.Dc = f.pd < g.Din ? (g.Din - f.pd + g.sD - 1) / g.sD : 0;
+  f.Hc = f.ph < g.Hin ? (g.Hin - f.ph + g.sH - 1) / g.sH : 0;
+  f.Wc = f.pw < g.Win ? (g.Win - f.pw + g.sW - 1) / g.sW : 0;
+  f.kd0 = (f.pd + g.pD) % g.sD; f.kh0 = (f.ph + g.pH) % g.sH; f.kw0 = (f.pw + g.pW) % g.sW;
+  f.nkd = f.kd0 < g.kD ? (g.kD - f.kd0 + g.sD - 1) / g.sD : 0;
+  f.nkh = f.kh0 < g.kH ? (g.kH - f.kh0 + g.sH - 1) / g.sH : 0;
+  f.nkw = f.kw0 < g.kW ? (g.kW - f.kw0 + g.sW - 1) / g.sW : 0;
+  f.rows = (long long)g.N * f.Dc * f.Hc * f.Wc;
+  fdiv_init((unsigned)(f.nkd * f.nkh * f.nkw), f.m_pt, f.s_pt);
+  fdiv_init((unsigned)(f.nkh * f.nkw), f.m_hw, f.s_hw);
+  fdiv_init((unsigned)f.nkw, f.m_w, f.s_w);
+  return f;
+}
 
 // One decoded position: base element offset and the top-left coordinate of its receptive field.
 struct PosInfo {
@@ -45,64 +89,82 @@ __device__ __forceinline__ PosInfo decode_out_pos(const Geo& g, long long m) {
   PosInfo q;
   q.ok = m < g.Pout;
   long long mm = q.ok ? m : 0;
-  int ow = (int)(mm % g.Wout); mm /= g.Wout;
-  int oh = (int)(mm % g.Hout); mm /= g.Hout;
-  int od = (int)(mm % g.Dout); mm /= g.Dout;
-  int n = (int)mm;
+  int ow, oh, od, n;
+  if (g.small) {
+    int t = (int)mm, u = fast_div(t, g.m_wo, g.s_wo);
+    ow = t - u * g.Wout;
+    t = fast_div(u, g.m_ho, g.s_ho);
+    oh = u - t * g.Hout;
+    n = fast_div(t, g.m_do, g.s_do);
+    od = t - n * g.Dout;
+  } else {
+    ow = (int)(mm % g.Wout); mm /= g.Wout;
+    oh = (int)(mm % g.Hout); mm /= g.Hout;
+    od = (int)(mm % g.Dout); mm /= g.Dout;
+    n = (int)mm;
+  }
   q.d0 = od * g.sD - g.pD; q.h0 = oh * g.sH - g.pH; q.w0 = ow * g.sW - g.pW;
   q.base = n * g.xs[0] + (long long)q.d0 * g.xs[2] + (long long)q.h0 * g.xs[3] + (long long)q.w0 * g.xs[4];
   return q;
 }
 
 __device__ __forceinline__ long long out_offset(const Geo& g, long long m) {
+  if (g.small) {
+    int t = (int)m, u = fast_div(t, g.m_wo, g.s_wo);
+    const int ow = t - u * g.Wout;
+    t = fast_div(u, g.m_ho, g.s_ho);
+    const int oh = u - t * g.Hout;
+    const int n = fast_div(t, g.m_do, g.s_do);
+    return n * g.ys[0] + (t - n * g.Dout) * g.ys[2] + oh * g.ys[3] + ow * g.ys[4];
+  }
   int ow = (int)(m % g.Wout); m /= g.Wout;
   int oh = (int)(m % g.Hout); m /= g.Hout;
   int od = (int)(m % g.Dout); m /= g.Dout;
   return m * g.ys[0] + od * g.ys[2] + oh * g.ys[3] + ow * g.ys[4];
 }
 
-__device__ __forceinline__ PosInfo decode_in_pos(const Geo& g, long long m) {
-  // input position m (DGRAD rows); d0/h0/w0 hold id+pD etc.
+__device__ __forceinline__ PosInfo decode_in_pos(const Geo& g, const Phase& f, long long m) {
+  // row m of parity class f -> input position (DGRAD rows); d0/h0/w0 hold id+pD etc.
   PosInfo q;
-  q.ok = m < g.Pin;
+  q.ok = m < f.rows;
   long long mm = q.ok ? m : 0;
-  int iw = (int)(mm % g.Win); mm /= g.Win;
-  int ih = (int)(mm % g.Hin); mm /= g.Hin;
-  int id = (int)(mm % g.Din); mm /= g.Din;
+  int iw = (int)(mm % f.Wc) * g.sW + f.pw; mm /= f.Wc;
+  int ih = (int)(mm % f.Hc) * g.sH + f.ph; mm /= f.Hc;
+  int id = (int)(mm % f.Dc) * g.sD + f.pd; mm /= f.Dc;
   int n = (int)mm;
   q.d0 = id + g.pD; q.h0 = ih + g.pH; q.w0 = iw + g.pW;
   q.base = n * g.ys[0];
   return q;
 }
 
-__device__ __forceinline__ long long in_offset(const Geo& g, long long m) {
-  int iw = (int)(m % g.Win); m /= g.Win;
-  int ih = (int)(m % g.Hin); m /= g.Hin;
-  int id = (int)(m % g.Din); m /= g.Din;
+__device__ __forceinline__ long long in_offset(const Geo& g, const Phase& f, long long m) {
+  int iw = (int)(m % f.Wc) * g.sW + f.pw; m /= f.Wc;
+  int ih = (int)(m % f.Hc) * g.sH + f.ph; m /= f.Hc;
+  int id = (int)(m % f.Dc) * g.sD + f.pd; m /= f.Dc;
   return m * g.xs[0] + id * g.xs[2] + ih * g.xs[3] + iw * g.xs[4];
 }
 
 // x[pos-window + (ci,kd,kh,kw)] with zero padding
 __device__ __forceinline__ float gather_x(const Geo& g, const float* __restrict__ x, const PosInfo& q, int k) {
   if (!q.ok || k >= g.K) return 0.f;
-  int ci = k / g.taps, tap = k - ci * g.taps;
-  int kd = tap / (g.kH * g.kW); tap -= kd * g.kH * g.kW;
-  int kh = tap / g.kW, kw = tap - kh * g.kW;
+  int ci = fast_div(k, g.m_taps, g.s_taps), tap = k - ci * g.taps;
+  int kd = fast_div(tap, g.m_khw, g.s_khw); tap -= kd * g.kH * g.kW;
+  int kh = fast_div(tap, g.m_kw, g.s_kw), kw = tap - kh * g.kW;
   int id = q.d0 + kd, ih = q.h0 + kh, iw = q.w0 + kw;
   if ((unsigned)id >= (unsigned)g.Din || (unsigned)ih >= (unsigned)g.Hin || (unsigned)iw >= (unsigned)g.Win) return 0.f;
   return __ldg(x + q.base + ci * g.xs[1] + (long long)kd * g.xs[2] + (long long)kh * g.xs[3] + (long long)kw * g.xs[4]);
 }
 
-// dy[(id+p-kd)/s ...][co] for DGRAD, r = (co,kd,kh,kw)
-__device__ __forceinline__ float gather_dy(const Geo& g, const float* __restrict__ dy, const PosInfo& q, int r) {
-  if (!q.ok || r >= g.Cout * g.taps) return 0.f;
-  int co = r / g.taps, tap = r - co * g.taps;
-  int kd = tap / (g.kH * g.kW); tap -= kd * g.kH * g.kW;
-  int kh = tap / g.kW, kw = tap - kh * g.kW;
-  int td = q.d0 - kd, th = q.h0 - kh, tw = q.w0 - kw;
+// dy[(id+p-kd)/s ...][co] for DGRAD; r = (co, kd', kh', kw') over the taps kd = kd0 + kd'*sD ... of the row's parity class, for which the
+// division by the stride is exact by construction
+__device__ __forceinline__ float gather_dy(const Geo& g, const Phase& f, const float* __restrict__ dy, const PosInfo& q, int r, int ptaps) {
+  if (!q.ok || r >= g.Cout * ptaps) return 0.f;
+  int co = fast_div(r, f.m_pt, f.s_pt), tap = r - co * ptaps;
+  int kd = fast_div(tap, f.m_hw, f.s_hw); tap -= kd * f.nkh * f.nkw;
+  int kh = fast_div(tap, f.m_w, f.s_w), kw = tap - kh * f.nkw;
+  int td = q.d0 - (f.kd0 + kd * g.sD), th = q.h0 - (f.kh0 + kh * g.sH), tw = q.w0 - (f.kw0 + kw * g.sW);
   if (td < 0 || th < 0 || tw < 0) return 0.f;
-  int od = td / g.sD, oh = th / g.sH, ow = tw / g.sW;
-  if (od * g.sD != td || oh * g.sH != th || ow * g.sW != tw) return 0.f;
+  int od = g.sD == 2 ? td >> 1 : td / g.sD, oh = g.sH == 2 ? th >> 1 : th / g.sH, ow = g.sW == 2 ? tw >> 1 : tw / g.sW;
   if (od >= g.Dout || oh >= g.Hout || ow >= g.Wout) return 0.f;
   return __ldg(dy + q.base + co * g.ys[1] + (long long)od * g.ys[2] + (long long)oh * g.ys[3] + (long long)ow * g.ys[4]);
 }
@@ -126,19 +188,26 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(Geo g, const float*
 
   long long R, r_begin, r_end;
   int NJ;
+  Phase f = {};
+  int ptaps = 0;
   if (MODE == MODE_FWD) { R = g.K; NJ = g.Cout; }
-  else if (MODE == MODE_DGRAD) { R = (long long)g.Cout * g.taps; NJ = g.Cin; }
-  else { R = g.Pout; NJ = g.Cout; }
-  r_begin = (long long)blockIdx.z * r_per_split;
-  r_end = r_begin + r_per_split < R ? r_begin + r_per_split : R;
-  if (r_begin >= r_end) return;
+  else if (MODE == MODE_DGRAD) {
+    f = make_phase(g, blockIdx.z);                 // blockIdx.z = parity class, never a reduction split
+    ptaps = f.nkd * f.nkh * f.nkw;
+    R = (long long)g.Cout * ptaps;
+    NJ = g.Cin;
+    if (i0 >= f.rows) return;
+  } else { R = g.Pout; NJ = g.Cout; }
+  r_begin = MODE == MODE_DGRAD ? 0 : (long long)blockIdx.z * r_per_split;
+  r_end = MODE == MODE_DGRAD ? R : (r_begin + r_per_split < R ? r_begin + r_per_split : R);
+  if (MODE != MODE_DGRAD && r_begin >= r_end) return;
 
   // ---- operand loaders -------------------------------------------------------------------
   // FWD / DGRAD: A rows are positions; each thread owns one row (tid & 127) and strides over r.
   // WGRAD: A rows are k=(ci,tap); the reduction index r is the position -> lanes run along r.
   PosInfo rowq;
   if (MODE == MODE_FWD) rowq = decode_out_pos(g, i0 + (tid & (BM - 1)));
-  if (MODE == MODE_DGRAD) rowq = decode_in_pos(g, i0 + (tid & (BM - 1)));
+  if (MODE == MODE_DGRAD) rowq = decode_in_pos(g, f, i0 + (tid & (BM - 1)));
 
   float ra[A_PER_THREAD], rb[B_PER_THREAD];
 
@@ -169,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(Geo g, const float*
       for (int e = 0; e < A_PER_THREAD; ++e) {
         int rr = rbase + 2 * e;
         long long r = r0 + rr;
-        ra[e] = (r < r_end) ? (MODE == MODE_FWD ? gather_x(g, src, rowq, (int)r) : gather_dy(g, src, rowq, (int)r)) : 0.f;
+        ra[e] = (r < r_end) ? (MODE == MODE_FWD ? gather_x(g, src, rowq, (int)r) : gather_dy(g, f, src, rowq, (int)r, ptaps)) : 0.f;
       }
       // B(r, j): FWD w[co*K + k];  DGRAD w[(co*Cin + ci)*taps + tap]
       const int rr = tid & (BK - 1);
@@ -182,8 +251,11 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(Geo g, const float*
         if (r < r_end && jj < BN && j < NJ) {
           if (MODE == MODE_FWD) v = __ldg(wgt + (long long)j * g.K + r);
           else {
-            int co = (int)(r / g.taps), tap = (int)(r - (long long)co * g.taps);
-            v = __ldg(wgt + ((long long)co * g.Cin + j) * g.taps + tap);
+            int co = fast_div((int)r, f.m_pt, f.s_pt), tap = (int)r - co * ptaps;
+            int kd = fast_div(tap, f.m_hw, f.s_hw); tap -= kd * f.nkh * f.nkw;
+            int kh = fast_div(tap, f.m_w, f.s_w), kw = tap - kh * f.nkw;
+            const int full = ((f.kd0 + kd * g.sD) * g.kH + (f.kh0 + kh * g.sH)) * g.kW + (f.kw0 + kw * g.sW);
+            v = __ldg(wgt + ((long long)co * g.Cin + j) * g.taps + full);
           }
         }
         rb[e] = v;
@@ -218,8 +290,10 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(Geo g, const float*
 #pragma unroll
     for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
 
-  load_tiles(r_begin);
-  store_tiles();
+  if (r_begin < r_end) {          // (a parity class that no tap reaches still writes its zeros below)
+    load_tiles(r_begin);
+    store_tiles();
+  }
   __syncthreads();
   for (long long r0 = r_begin; r0 < r_end; r0 += BK) {
     const bool more = r0 + BK < r_end;
@@ -259,8 +333,8 @@ __global__ void __launch_bounds__(NTHREADS) conv_gemm_kernel(Geo g, const float*
         }
       }
     } else if (MODE == MODE_DGRAD) {
-      if (i >= g.Pin) continue;
-      long long off = in_offset(g, i);
+      if (i >= f.rows) continue;
+      long long off = in_offset(g, f, i);
 #pragma unroll
       for (int b = 0; b < TN; ++b) {
         int j = j0 + tn * TN + b;
@@ -292,6 +366,13 @@ Geo make_geo(const cvad_conv_desc* d) {
   g.K = g.Cin * g.taps;
   g.Pout = (long long)g.N * g.Dout * g.Hout * g.Wout;
   g.Pin = (long long)g.N * g.Din * g.Hin * g.Win;
+  fdiv_init((unsigned)g.taps, g.m_taps, g.s_taps);
+  fdiv_init((unsigned)(g.kH * g.kW), g.m_khw, g.s_khw);
+  fdiv_init((unsigned)g.kW, g.m_kw, g.s_kw);
+  fdiv_init((unsigned)g.Wout, g.m_wo, g.s_wo);
+  fdiv_init((unsigned)g.Hout, g.m_ho, g.s_ho);
+  fdiv_init((unsigned)g.Dout, g.m_do, g.s_do);
+  g.small = g.Pout < (1LL << 31) - 4096 && g.Pin < (1LL << 31) - 4096;
   return g;
 }
 
@@ -301,6 +382,10 @@ int launch(const Geo& g, const float* src, const float* wgt, const float* aux, f
   int nj = MODE == MODE_DGRAD ? g.Cin : g.Cout;
   long long R = MODE == MODE_FWD ? g.K : (MODE == MODE_DGRAD ? (long long)g.Cout * g.taps : g.Pout);
   int splits = 1;
+  if (MODE == MODE_DGRAD) {       // grid.x covers the largest parity class (class 0), grid.z the sD*sH*sW classes
+    rows = make_phase(g, 0).rows;
+    splits = g.sD * g.sH * g.sW;
+  }
   long long gx = (rows + BM - 1) / BM;
   if (MODE == MODE_WGRAD) {
     // split the (huge) position reduction so that the grid fills the machine ~4x
@@ -311,8 +396,11 @@ int launch(const Geo& g, const float* src, const float* wgt, const float* aux, f
     splits = (int)(want < 1 ? 1 : (want > maxs ? maxs : want));
     if (splits < 1) splits = 1;
   }
-  long long rps = ((R + splits - 1) / splits + BK - 1) / BK * BK;
-  splits = (int)((R + rps - 1) / rps);
+  long long rps = R;
+  if (MODE != MODE_DGRAD) {
+    rps = ((R + splits - 1) / splits + BK - 1) / BK * BK;
+    splits = (int)((R + rps - 1) / rps);
+  }
   if (nj > 32) {
     dim3 grid((unsigned)gx, (nj + 63) / 64, splits);
     conv_gemm_kernel<MODE, 64, 8><<<grid, NTHREADS, 0, st>>>(g, src, wgt, aux, dst, act, rps);

@@ -43,6 +43,7 @@ def _ptr(t):
 TIMED = {}        # bench.py: ABI name -> list of (start_event, end_event); set TIMED_NAMES to enable
 TIMED_NAMES = set()
 TIMED_CAPTURE_ONLY = [False]     # True: bracket the named calls only while a CUDA graph is being captured
+TIMED_SHAPES = [os.environ.get("CVAD_PROFILE_SHAPES", "0") == "1"]
 
 
 def _call(name, *args):
@@ -56,7 +57,10 @@ def _call(name, *args):
         s.record()
         check(getattr(L(), name)(*args), name)
         e.record()
-        TIMED.setdefault(name, []).append((s, e))
+        key = name
+        if TIMED_SHAPES[0] and name == "cvad_sgemm_f32":        # profiling detail: one row per GEMM shape
+            key = f"{name}[M{args[0]} N{args[1]} K{args[2]} splits{args[16]}{' gated' if args[17] else ''}]"
+        TIMED.setdefault(key, []).append((s, e))
         return
     check(getattr(L(), name)(*args), name)
 

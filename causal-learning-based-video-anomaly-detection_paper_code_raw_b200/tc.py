@@ -16,6 +16,7 @@ gradient (the reference only accumulates round-off there); they receive exactly 
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 import torch
@@ -38,6 +39,9 @@ def _wgrad_scratch(device, cin, cout):
 
 
 FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm batch statistics from the convolution epilogue
+# weight-gradient GEMMs on a side stream: wgrad_i needs only draw_i and a_{i-1}, so it can run beside the HBM-bound BatchNorm backward of
+# the next layer down instead of in front of it (a parallel branch of the captured step graph)
+WGRAD_OVERLAP = os.environ.get("CVAD_WGRAD_OVERLAP", "0") == "1"
 
 
 def _layers(bb):
@@ -166,6 +170,9 @@ class _BackboneBF16(torch.autograd.Function):
         dact = torch.empty((N, h + 2, w + 2, c), device=dev, dtype=BF16)
         _call("cvad_pad_avgpool_bf16_bwd", _ptr(dfeat), N, h, w, c, 4, 6, _ptr(dact), st)
         layers = _layers(bb)
+        cur = torch.cuda.current_stream()
+        side = ops.aux_stream(dev, 1) if WGRAD_OVERLAP else None
+        keep = []                     # operands of side-stream launches stay referenced until the join (the allocator tracks one stream)
         for idx in range(len(layers) - 1, -1, -1):
             conv, bn = layers[idx]
             a_in, raw, mean, invstd, wd, (hi, wi, cin, cout, stride, ho, wo), bn_training, phase_out = saved[idx]
@@ -175,17 +182,26 @@ class _BackboneBF16(torch.autograd.Function):
             _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
                   _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
             if _wants_grad(conv.weight):
-                if STAGED_WGRAD:
-                    _call("cvad_flat_conv3x3_wgrad_staged_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)),
-                          _ptr(_wgrad_scratch(dev, cin, cout)), N, hi, wi, cin, cout, stride, st)
-                else:
-                    _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, st)
+                wst = st
+                if side is not None:
+                    side.wait_stream(cur)
+                    keep.append((a_in, draw))
+                    wst = side.cuda_stream
+                with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                    if STAGED_WGRAD:
+                        _call("cvad_flat_conv3x3_wgrad_staged_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)),
+                              _ptr(_wgrad_scratch(dev, cin, cout)), N, hi, wi, cin, cout, stride, wst)
+                    else:
+                        _call("cvad_flat_conv3x3_wgrad_bf16", _ptr(a_in), _ptr(draw), _ptr(grad_buffer(conv.weight)), N, hi, wi, cin, cout, stride, wst)
             if _wants_grad(conv.bias):
                 grad_buffer(conv.bias)          # analytically zero (BatchNorm removes the mean); keep the tensor "with grad"
             if idx > 0:
                 dact = torch.empty(a_in.shape, device=dev, dtype=BF16)
                 _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, st)
             saved[idx] = None
+        if side is not None:
+            cur.wait_stream(side)
+            keep.clear()
         return (None, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
