@@ -76,10 +76,25 @@ class ResNetBackbone(nn.Module):
 
 
 def _mlp(seq, idxs, x, acts, keeps=None, ps=None, gate=None):
-    h = x
-    for i, (li, act) in enumerate(zip(idxs, acts)):
-        keep = keeps[i] if keeps is not None else None
-        h = ops.linear_act(h, seq[li].weight, seq[li].bias, act, keep, ps[i] if keep is not None else 0.0, gate)
+    """The Linear layers ``seq[idxs]`` with activations ``acts`` and dropout keep-masks ``keeps`` (probabilities ``ps``).  Layers wider
+    than the fused-chain limit (the two 6144 -> 512 projections) run as GEMMs; every run of narrower layers behind them is one fused
+    launch forward and one for the data-gradient chain (ops.mlp_chain).  ``gate`` (the detector's "received a gradient" flag) applies
+    to the GEMM layers only: the chain is cheap enough to run on zeros."""
+    layers = [(seq[li].weight, seq[li].bias, act, keeps[i] if keeps is not None else None, ps[i] if keeps is not None and keeps[i] is not None else 0.0)
+              for i, (li, act) in enumerate(zip(idxs, acts))]
+    h, i = x, 0
+    while i < len(layers):
+        din = h.shape[-1]
+        j = i
+        while j < len(layers) and ops.chainable(layers[i:j + 1], din):
+            j += 1
+        if j > i:
+            h = ops.mlp_chain(h, layers[i:j])
+            i = j
+        else:
+            w, b, act, keep, p = layers[i]
+            h = ops.linear_act(h, w, b, act, keep, p, gate)
+            i += 1
     return h
 
 

@@ -305,6 +305,92 @@ def linear_act(x, weight, bias, act=ACT_NONE, mask=None, p_drop=0.0, gate=None):
     return _LinearAct.apply(x, weight, bias, act, mask, scale, gate)
 
 
+
+# ------------------------------------------------------------------------------------------------ fused MLP chains
+CHAIN_MAX_DIM, CHAIN_MAX_LAYERS = 512, 8
+FUSED_CHAINS = os.environ.get("CVAD_FUSED_CHAINS", "1") != "0"
+
+
+def _ptr_array(items):
+    arr = (ctypes.c_void_p * len(items))()
+    for i, t in enumerate(items):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class _MLPChain(torch.autograd.Function):
+    """A stack of nn.Linear layers (width <= 512) with activation / dropout keep-masks as one launch forward and one launch for the
+    data-gradient chain; weight and bias gradients are the usual split-K GEMMs / column sums on the parameter-gradient side stream."""
+
+    @staticmethod
+    def forward(ctx, x, acts, scales, n, *tensors):
+        weights, biases, masks = tensors[:n], tensors[n:2 * n], tensors[2 * n:3 * n]
+        _cuda(x, *weights)
+        shp = x.shape
+        x2 = _f32c(x).reshape(-1, shp[-1])
+        M = x2.shape[0]
+        dims = [x2.shape[1]] + [w.shape[0] for w in weights]
+        masks = [None if m is None else _f32c(m).reshape(M, d) for m, d in zip(masks, dims[1:])]
+        need = torch.is_grad_enabled() or any(ctx.needs_input_grad)
+        saves = [torch.empty((M, d), device=x.device, dtype=torch.float32) if need else None for d in dims[1:]]
+        out = saves[-1] if need else torch.empty((M, dims[-1]), device=x.device, dtype=torch.float32)
+        c_dims, c_acts = (ctypes.c_int * (n + 1))(*dims), (ctypes.c_int * n)(*acts)
+        c_scales = (ctypes.c_float * n)(*scales)
+        # the last layer's stored output IS the result: the kernel writes it through `saves` and `out` (same buffer)
+        _call("cvad_mlp_chain_fwd_f32", _ptr(x2), M, n, c_dims, c_acts, _ptr_array(weights), _ptr_array(biases), _ptr_array(masks), c_scales,
+              _ptr_array(saves), _ptr(out), _st())
+        ctx.meta = (acts, scales, n, shp, dims)
+        ctx.params = (weights, biases)
+        ctx.save_for_backward(x2, *[s for s in saves if s is not None], *[m for m in masks if m is not None])
+        ctx.mask_slots = [m is not None for m in masks]
+        return out.reshape(*shp[:-1], dims[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        acts, scales, n, shp, dims = ctx.meta
+        weights, biases = ctx.params
+        sv = ctx.saved_tensors
+        x2, saves = sv[0], list(sv[1:1 + n])
+        it = iter(sv[1 + n:])
+        masks = [next(it) if has else None for has in ctx.mask_slots]
+        M = x2.shape[0]
+        dy2 = _f32c(dy).reshape(M, dims[-1])
+        dzs = [torch.empty((M, d), device=dy2.device, dtype=torch.float32) for d in dims[1:]]
+        dx = torch.empty((M, dims[0]), device=dy2.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        c_dims, c_acts = (ctypes.c_int * (n + 1))(*dims), (ctypes.c_int * n)(*acts)
+        c_scales = (ctypes.c_float * n)(*scales)
+        _call("cvad_mlp_chain_bwd_f32", _ptr(dy2), M, n, c_dims, c_acts, _ptr_array(weights), _ptr_array(masks), c_scales, _ptr_array(saves),
+              _ptr_array(dzs), _ptr(dx), _st())
+        side = _pg_stream(dy2.device)
+        if side is not None:         # off the critical path: fork here, join when param_grad_overlap() exits
+            side.wait_stream(torch.cuda.current_stream())
+            _ParamGradOverlap.keep.append((dzs, x2, saves))
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            for l in range(n):
+                w, b, dz = weights[l], biases[l], dzs[l]
+                hin = x2 if l == 0 else saves[l - 1]
+                O, K = dims[l + 1], dims[l]
+                if _wants_grad(w):       # dW[o][i] += sum_m dz[m][o] h[m][i]
+                    _sgemm(O, K, M, dz, O, False, hin, K, False, grad_buffer(w), K, accumulate=1, splits=_splits_for(O, K, M))
+                if _wants_grad(b):
+                    _call("cvad_colsum_f32", _ptr(dz), M, O, O, _ptr(grad_buffer(b)), 1, _st())
+        return (None if dx is None else dx.reshape(shp), None, None, None) + (None,) * (3 * n)
+
+
+def mlp_chain(x, layers):
+    """``layers``: sequence of (weight, bias, act, keep_mask or None, p_drop).  Equivalent to chaining ``linear_act`` over them."""
+    n = len(layers)
+    assert 1 <= n <= CHAIN_MAX_LAYERS
+    acts = tuple(int(l[2]) for l in layers)
+    scales = tuple((1.0 / (1.0 - l[4])) if l[3] is not None else 1.0 for l in layers)
+    return _MLPChain.apply(x, acts, scales, n, *[l[0] for l in layers], *[l[1] for l in layers], *[l[3] for l in layers])
+
+
+def chainable(layers, din) -> bool:
+    """Whether a Linear stack fits the fused kernel (every width <= 512)."""
+    return FUSED_CHAINS and 1 <= len(layers) <= CHAIN_MAX_LAYERS and din <= CHAIN_MAX_DIM and all(l[0].shape[0] <= CHAIN_MAX_DIM for l in layers)
+
+
 # ------------------------------------------------------------------------------------------------ batch norm
 class _BatchNormAct(torch.autograd.Function):
     @staticmethod

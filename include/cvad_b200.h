@@ -271,6 +271,21 @@ int cvad_mb_eval_metrics_f32(const float* scores, const float* graphs, long long
                              double* out8, void* stream);
 int cvad_moving_average_f32(const float* x, long long n, int w, double* out, void* stream);
 
+/* ---- fused MLP chains (mlp_chain.cu): n_layers <= 8 nn.Linear layers of width <= 512 with bias, activation and dropout keep-mask in one
+ * launch (forward) / one launch (data-gradient chain).  cad:167-179, 240-246, 318-326, 361-367, 407-413, 435-461, 525-538; s2:43-48, 77-89.
+ * dims[n_layers+1] = {din_0, dout_0 (= din_1), ...}; acts[l] = CvadAct of layer l; weights[l] (dout,din) row-major; biases[l] / masks[l]
+ * (rows,dout) may be NULL (the arrays themselves too); saves[l] (rows,dout) receives layer l's output (post activation, post mask) for
+ * the backward, NULL entries / array = not stored (inference).  The arrays are host arrays, read during the call.
+ * forward:  out (rows, dout_last) = chain(x (rows, din_0)).
+ * backward: dy (rows, dout_last) -> dzs[l] (rows,dout_l) = gradient w.r.t. layer l's pre-activation (what the weight-gradient GEMM
+ *           dW_l += dz_l^T h_{l-1} and the bias column sum consume), and dx (rows, din_0) unless NULL. */
+int cvad_mlp_chain_fwd_f32(const float* x, long long rows, int n_layers, const int* dims, const int* acts, const void* const* weights,
+                           const void* const* biases, const void* const* masks, const float* mask_scales, void* const* saves, float* out,
+                           void* stream);
+int cvad_mlp_chain_bwd_f32(const float* dy, long long rows, int n_layers, const int* dims, const int* acts, const void* const* weights,
+                           const void* const* masks, const float* mask_scales, const void* const* saves, void* const* dzs, float* dx,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

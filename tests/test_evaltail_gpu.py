@@ -117,4 +117,6 @@ def test_evaluate_improved_metrics_on_device_match_host_formulas(dev, gold):
     assert abs(m["avg_edges"] - float(np.mean(e))) < 1e-9 and m["min_score"] == float(np.min(p)) and m["max_score"] == float(np.max(p))
     assert abs(m["mean_score"] - float(np.mean(p))) < 2e-6 and abs(m["std_score"] - float(np.std(p))) < 1e-6
     p2, cg2, m2 = tr.evaluate_improved(loader, return_arrays=False)
-    assert p2 is None and cg2 is None and m2 == m
+    assert p2 is None and cg2 is None and set(m2) == set(m)
+    for k in m:      # two passes over the same clips agree to round-off (split-K atomics order the fp32 sums differently), not bitwise
+        assert abs(m2[k] - m[k]) <= 1e-5 * max(abs(m[k]), 1.0), k

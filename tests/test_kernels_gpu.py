@@ -278,3 +278,52 @@ def test_fused_adam_matches_torch(dev, decoupled, clip_mode):
     for a, b in zip(before, my_p):
         assert torch.equal(a, b.data)
     assert mopt.skipped_steps() == 1
+
+
+# dims, activations, which layers carry a dropout keep-mask -- the M-A stacks (cad:167-179, 240-246, 318-326, 361-367, 407-413, 435-461)
+CHAIN_CASES = [
+    ((512, 256, 128, 64, 20), (1, 1, 1, 0), (0,)),            # detector behind its 6144 -> 512 GEMM (dropout after the first chained layer)
+    ((4, 32, 64, 64), (1, 1, 0), ()),                         # re-id
+    ((68, 192), (0,), ()),                                    # GRU input projection
+    ((64, 32, 1), (1, 3), ()),                                # edge predictor (sigmoid head)
+    ((18, 64, 32, 1), (1, 1, 3), (0,)),                       # causal scorer
+    ((6, 32, 32, 6), (1, 1, 0), ()),                          # dynamics
+    ((512, 256, 128, 64, 2), (1, 1, 1, 0), (0,)),             # direct classifier behind its first GEMM
+    ((100, 70, 33, 130, 5, 77, 9, 3, 40), (1, 4, 3, 0, 1, 2, 1, 0), (1, 4)),      # eight ragged layers, every activation
+]
+
+
+@pytest.mark.parametrize("dims,acts,masked", CHAIN_CASES)
+@pytest.mark.parametrize("rows", [1, 7, 8, 33, 160, 2560])
+def test_mlp_chain_fwd_bwd(dev, dims, acts, masked, rows):
+    """ops.mlp_chain (one launch forward, one for the data-gradient chain) against the same stack in plain PyTorch fp32: output,
+    input gradient and every weight / bias gradient."""
+    from cvad_b200 import ops
+    actf = {0: lambda t: t, 1: F.relu, 2: lambda t: F.leaky_relu(t, 0.1), 3: torch.sigmoid, 4: torch.tanh}
+    n = len(dims) - 1
+    x = torch.randn(rows, dims[0], generator=_g(1)).to(dev).requires_grad_(True)
+    Ws = [(torch.randn(dims[l + 1], dims[l], generator=_g(10 + l)) / dims[l] ** 0.5).to(dev).requires_grad_(True) for l in range(n)]
+    bs = [torch.randn(dims[l + 1], generator=_g(30 + l)).mul(0.1).to(dev).requires_grad_(True) for l in range(n)]
+    keeps = [(torch.rand(rows, dims[l + 1], generator=_g(50 + l)) >= 0.3).float().to(dev) if l in masked else None for l in range(n)]
+    h = x
+    for l in range(n):
+        h = actf[acts[l]](F.linear(h, Ws[l], bs[l]))
+        if keeps[l] is not None:
+            h = h * keeps[l] / 0.7
+    dy = torch.randn(rows, dims[-1], generator=_g(3)).to(dev)
+    ref = torch.autograd.grad(h, [x] + Ws + bs, dy)
+    x2 = x.detach().clone().requires_grad_(True)
+    W2 = [w.detach().clone().requires_grad_(True) for w in Ws]
+    b2 = [b.detach().clone().requires_grad_(True) for b in bs]
+    y = ops.mlp_chain(x2, [(W2[l], b2[l], acts[l], keeps[l], 0.3 if keeps[l] is not None else 0.0) for l in range(n)])
+    assert rel(y, h) < 2e-5
+    with ops.param_grad_overlap():
+        y.backward(dy)
+    torch.cuda.synchronize()
+    got = [x2.grad] + [w.grad for w in W2] + [b.grad for b in b2]
+    for i, (a, r) in enumerate(zip(got, ref)):
+        assert rel(a, r) < 5e-5, (i, rel(a, r))
+    # inference: nothing is stored, same numbers
+    with torch.no_grad():
+        y2 = ops.mlp_chain(x.detach(), [(w.detach(), b.detach(), acts[l], keeps[l], 0.3 if keeps[l] is not None else 0.0) for l, (w, b) in enumerate(zip(Ws, bs))])
+    assert torch.equal(y2, y.detach())

@@ -2,6 +2,7 @@
 import copy
 import os
 
+import numpy as np
 import pytest
 import torch
 
