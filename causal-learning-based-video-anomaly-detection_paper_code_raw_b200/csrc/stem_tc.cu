@@ -73,21 +73,41 @@ __global__ void stem_s2d_kernel(const float* __restrict__ x, StemGeo g, float4* 
 // fly, x = (float(v) - mean) / std -- exactly torchvision's sub_().div_() on the FloatTensor, so the result is bit-identical to the fp32
 // path while the frames cross PCIe and are read from HBM at 1 byte per pixel.  Conv padding stays 0 (it pads the NORMALISED tensor).
 __global__ void stem_s2d_u8_kernel(const uint8_t* __restrict__ x, StemGeo g, float mean, float stdv, float4* __restrict__ x4) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.np4; t += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(t % g.Wq);
-    const long long r = t / g.Wq;
+  // one thread = four horizontally adjacent X4 pixels = 8 source bytes from each of two frame rows (two aligned 4-byte loads per row when
+  // the frame width is a multiple of 4) -> 64 contiguous output bytes
+  const int wq4 = (g.Wq + 3) >> 2;
+  const long long items = (long long)g.N * g.Hq * wq4;
+  const bool aligned = (g.W & 3) == 0;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < items; t += (long long)gridDim.x * blockDim.x) {
+    const int jq = (int)(t % wq4);
+    const long long r = t / wq4;
     const int i = (int)(r % g.Hq), n = (int)(r / g.Hq);
-    const int h0 = 2 * (i - 2), w0 = 2 * (j - 2);
+    const int j0 = jq * 4;
+    const int h0 = 2 * (i - 2), w0 = 2 * (j0 - 2);          // w0 = 4 (mod 8)
     const uint8_t* xn = x + (long long)n * g.H * g.W;
-    float v[4];
+    float v[2][8];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a) {
+      const int h = h0 + a;
+      const bool hok = (unsigned)h < (unsigned)g.H;
+      const uint8_t* row = xn + (long long)h * g.W;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int h = h0 + a, w = w0 + b;
-        v[a * 2 + b] = ((unsigned)h < (unsigned)g.H && (unsigned)w < (unsigned)g.W) ? ((float)__ldg(xn + (long long)h * g.W + w) - mean) / stdv : 0.f;
+      for (int half = 0; half < 2; ++half) {
+        const int w = w0 + 4 * half;
+        if (hok && aligned && w >= 0 && w + 3 < g.W) {
+          const unsigned q = __ldg(reinterpret_cast<const unsigned*>(row + w));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[a][4 * half + e] = ((float)((q >> (8 * e)) & 255u) - mean) / stdv;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[a][4 * half + e] = (hok && (unsigned)(w + e) < (unsigned)g.W) ? ((float)__ldg(row + w + e) - mean) / stdv : 0.f;
+        }
       }
-    x4[t] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    const long long o = (r * g.Wq) + j0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      if (j0 + p < g.Wq) x4[o + p] = make_float4(v[0][2 * p], v[0][2 * p + 1], v[1][2 * p], v[1][2 * p + 1]);
   }
 }
 
@@ -409,7 +429,7 @@ CVAD_API int cvad_stem_space_to_depth_f32(const float* x, int N, int H, int W, f
 CVAD_API int cvad_stem_space_to_depth_u8(const void* x, int N, int H, int W, float mean, float stdv, float* x4, void* stream) {
   StemGeo g;
   if (stem_geo(g, N, H, W) || stdv == 0.f) return (int)cudaErrorInvalidValue;
-  long long blocks = (g.np4 + 255) / 256;
+  long long blocks = ((long long)g.N * g.Hq * ((g.Wq + 3) / 4) + 255) / 256;
   if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
   stem_s2d_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint8_t*)x, g, mean, stdv, reinterpret_cast<float4*>(x4));
   CVAD_LAUNCH_CHECK();

@@ -144,10 +144,12 @@ def resume_from(model, path):
 
 
 def train_improved_minicausal_vad(dataset_path, num_epochs: int = 100, batch_size: int = 4, save_interval: int = 20,
-                                  output_dir="improved_avenue_results", resume=None, device="cuda", loaders=None, dp=None, verbose=True):
+                                  output_dir="improved_avenue_results", resume=None, device="cuda", loaders=None, dp=None, verbose=True,
+                                  on_epoch_end=None):
     """s2:339-468.  Returns (model, training_history).  ``resume``: a ``checkpoint_epoch_<e>.pth`` written by this function (or by the
     reference: then only model / optimizer / scheduler / history are restored).  ``loaders``: (train_loader, test_loader) to use instead of
-    ``create_avenue_dataloaders(dataset_path, ...)``."""
+    ``create_avenue_dataloaders(dataset_path, ...)``.  ``on_epoch_end(epoch, training_history)`` is called after an epoch's files are
+    queued (raise from it to stop a run: queued checkpoints are still flushed)."""
     from .mb import ImprovedMiniCausalVAD
 
     def say(*a):
@@ -190,6 +192,8 @@ def train_improved_minicausal_vad(dataset_path, num_epochs: int = 100, batch_siz
             if epoch % save_interval == 0:
                 writer.save(checkpoint_state(model, epoch, training_history, best_score_range), output_dir / f"checkpoint_epoch_{epoch}.pth")
             safe_json_save(training_history, output_dir / "improved_training_history.json")
+            if on_epoch_end is not None:
+                on_epoch_end(epoch, training_history)
     finally:
         writer.wait()
         writer.close()

@@ -271,7 +271,8 @@ int cvad_mb_eval_metrics_f32(const float* scores, const float* graphs, long long
                              double* out8, void* stream);
 int cvad_moving_average_f32(const float* x, long long n, int w, double* out, void* stream);
 
-/* ---- fused MLP chains (mlp_chain.cu): n_layers <= 8 nn.Linear layers of width <= 512 with bias, activation and dropout keep-mask in one
+/* ---- fused MLP chains (mlp_chain.cu): n_layers <= 8 nn.Linear layers (widths <= 256, (din|1)*dout <= 33024 per layer: the weight matrix of a
+ * layer is staged in shared memory) with bias, activation and dropout keep-mask in one
  * launch (forward) / one launch (data-gradient chain).  cad:167-179, 240-246, 318-326, 361-367, 407-413, 435-461, 525-538; s2:43-48, 77-89.
  * dims[n_layers+1] = {din_0, dout_0 (= din_1), ...}; acts[l] = CvadAct of layer l; weights[l] (dout,din) row-major; biases[l] / masks[l]
  * (rows,dout) may be NULL (the arrays themselves too); saves[l] (rows,dout) receives layer l's output (post activation, post mask) for

@@ -282,13 +282,13 @@ def test_fused_adam_matches_torch(dev, decoupled, clip_mode):
 
 # dims, activations, which layers carry a dropout keep-mask -- the M-A stacks (cad:167-179, 240-246, 318-326, 361-367, 407-413, 435-461)
 CHAIN_CASES = [
-    ((512, 256, 128, 64, 20), (1, 1, 1, 0), (0,)),            # detector behind its 6144 -> 512 GEMM (dropout after the first chained layer)
+    ((256, 128, 64, 20), (1, 1, 0), (0,)),                    # detector behind its 6144 -> 512 -> 256 GEMMs (dropout mask on a chained layer)
     ((4, 32, 64, 64), (1, 1, 0), ()),                         # re-id
     ((68, 192), (0,), ()),                                    # GRU input projection
     ((64, 32, 1), (1, 3), ()),                                # edge predictor (sigmoid head)
     ((18, 64, 32, 1), (1, 1, 3), (0,)),                       # causal scorer
     ((6, 32, 32, 6), (1, 1, 0), ()),                          # dynamics
-    ((512, 256, 128, 64, 2), (1, 1, 1, 0), (0,)),             # direct classifier behind its first GEMM
+    ((256, 128, 64, 2), (1, 1, 0), (0,)),                     # direct classifier behind its first two GEMMs
     ((100, 70, 33, 130, 5, 77, 9, 3, 40), (1, 4, 3, 0, 1, 2, 1, 0), (1, 4)),      # eight ragged layers, every activation
 ]
 

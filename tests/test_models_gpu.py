@@ -804,19 +804,27 @@ def test_train_driver_resume_matches_uninterrupted_run(dev, tmp_path):
     def loaders():
         return a.create_avenue_dataloaders("synthetic:16", batch_size=4, clip_length=8, frame_size=(64, 64))
 
-    def run(out, epochs, resume=None):
+    class Killed(Exception):
+        pass
+
+    def kill_after_epoch_1(epoch, _hist):
+        if epoch == 1:
+            raise Killed()
+
+    def run(out, resume=None, hook=None):
         torch.manual_seed(77)
         torch.cuda.manual_seed(77)
-        return drv.train_improved_minicausal_vad("synthetic:16", num_epochs=epochs, batch_size=4, save_interval=1, output_dir=out, resume=resume,
-                                                 device=dev, loaders=loaders(), verbose=False)
+        return drv.train_improved_minicausal_vad("synthetic:16", num_epochs=4, batch_size=4, save_interval=1, output_dir=out, resume=resume,
+                                                 device=dev, loaders=loaders(), verbose=False, on_epoch_end=hook)
 
-    full, hist_full = run(tmp_path / "full", 4)
-    run(tmp_path / "part", 2)
+    full, hist_full = run(tmp_path / "full")
+    with pytest.raises(Killed):
+        run(tmp_path / "part", hook=kill_after_epoch_1)           # the same 4-epoch job, killed after its second epoch
     ck = torch.load(tmp_path / "part" / "checkpoint_epoch_1.pth", map_location="cpu", weights_only=False)
     assert {"model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "epoch", "training_history"} <= set(ck) and ck["epoch"] == 1
     best = torch.load(tmp_path / "part" / "best_improved_model.pth", map_location="cpu", weights_only=False)
     assert set(best) == {"model_state_dict", "optimizer_state_dict", "epoch", "eval_metrics"}
-    resumed, hist_res = run(tmp_path / "part", 4, resume=tmp_path / "part" / "checkpoint_epoch_1.pth")
+    resumed, hist_res = run(tmp_path / "part", resume=tmp_path / "part" / "checkpoint_epoch_1.pth")
     assert hist_res["epochs"] == [1, 2, 3, 4] == hist_full["epochs"] and len(hist_res["train_losses"]) == 4
     for k in ("train_losses", "learning_rates"):
         assert np.allclose(hist_res[k], hist_full[k], rtol=1e-4, atol=1e-7), (k, hist_res[k], hist_full[k])
