@@ -74,6 +74,14 @@ struct FcParams {
   int st_h, st_w;
   unsigned st_mul_img, st_shr_img, st_mul_row, st_shr_row;
   double* st_out;
+  // fused BatchNorm-BACKWARD reductions (data-gradient only, n_blocks == 1): the rows this launch writes are the gradient dact w.r.t. the
+  // output of relu(bn(raw)) of the layer below; with g = dact * (raw*ga + gb > 0) (ga = gamma*invstd, gb = beta - mean*ga) the epilogue adds
+  // sum g and sum g*xhat over the interior pixels to st_out[0..N) / st_out[N..2N) -- the two per-channel sums of the BatchNorm backward,
+  // which otherwise cost a full read pass over raw and dact.  bw_planes: the rows are the four phase planes of a stride-2 input
+  // (geometry (st_h+2) x (st_w+2) per plane) and map to pixel (2(i-1)+a, 2(j-1)+b) of the bw_H x bw_W interior of raw.
+  const __nv_bfloat16* bw_raw;
+  const float *bw_gamma, *bw_beta, *bw_mean, *bw_invstd;
+  int bw_H, bw_W, bw_planes;
   FcUnit units[FC_MAX_UNITS];
 };
 
@@ -105,6 +113,31 @@ __device__ __forceinline__ void warp_colsum16_sq(const float (&x)[16], int lane,
   sumsq = vv + __shfl_xor_sync(0xffffffffu, vv, 1);
 }
 
+// the same butterfly for two independent 32 x 16 tiles (column sums of a and of b)
+__device__ __forceinline__ void warp_colsum16_pair(const float (&a)[16], const float (&b)[16], int lane, float& sum_a, float& sum_b) {
+  float y[8], z[4], w[2], yy[8], zz[4], ww[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    y[i] = (b4 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, b4 ? a[i] : a[i + 8], 16);
+    yy[i] = (b4 ? b[i + 8] : b[i]) + __shfl_xor_sync(0xffffffffu, b4 ? b[i] : b[i + 8], 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    z[i] = (b3 ? y[i + 4] : y[i]) + __shfl_xor_sync(0xffffffffu, b3 ? y[i] : y[i + 4], 8);
+    zz[i] = (b3 ? yy[i + 4] : yy[i]) + __shfl_xor_sync(0xffffffffu, b3 ? yy[i] : yy[i + 4], 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    w[i] = (b2 ? z[i + 2] : z[i]) + __shfl_xor_sync(0xffffffffu, b2 ? z[i] : z[i + 2], 4);
+    ww[i] = (b2 ? zz[i + 2] : zz[i]) + __shfl_xor_sync(0xffffffffu, b2 ? zz[i] : zz[i + 2], 4);
+  }
+  const float v = (b1 ? w[1] : w[0]) + __shfl_xor_sync(0xffffffffu, b1 ? w[0] : w[1], 2);
+  const float vv = (b1 ? ww[1] : ww[0]) + __shfl_xor_sync(0xffffffffu, b1 ? ww[0] : ww[1], 2);
+  sum_a = v + __shfl_xor_sync(0xffffffffu, v, 1);
+  sum_b = vv + __shfl_xor_sync(0xffffffffu, vv, 1);
+}
+
 template <int ROWB, int N>
 __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
                                                           const __grid_constant__ CUtensorMap map_w, const FcParams p,
@@ -123,7 +156,14 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   __shared__ uint32_t tmem_base_sh;
   __shared__ float s_bias[N];
   __shared__ float s_stat[2 * N];          // fused BatchNorm statistics of this CTA's rows (fp32 partial sums, flushed once at the end)
+  __shared__ float s_ga[N], s_gb[N];       // fused BatchNorm-backward reductions: the forward's per-channel scale / shift
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stat[i] = 0.f;
+  if (p.bw_raw)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      const float ga = p.bw_gamma[i] * p.bw_invstd[i];
+      s_ga[i] = ga;
+      s_gb[i] = p.bw_beta[i] - p.bw_mean[i] * ga;
+    }
   const long long t_entry = g_fc_debug ? (long long)globaltimer_ns() : 0;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -311,11 +351,21 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
         __nv_bfloat16* orow = out + (p.out_row_base + pl * p.plane_out_stride + q) * (long long)p.ld_out + nb * N;
         bool keep = false;                    // interior pixel (the only ones BatchNorm statistics run over)
+        const bool bw = p.bw_raw != nullptr;
+        const __nv_bfloat16* rrow = nullptr;  // bw: this row's pixel in raw
         if (p.st_out && q < p.rows) {
           const int qi = (int)q;
-          const int r = qi - fast_div(qi, p.st_mul_img, p.st_shr_img) * ((p.st_h + 2) * (p.st_w + 2));
+          const int n = fast_div(qi, p.st_mul_img, p.st_shr_img);
+          const int r = qi - n * ((p.st_h + 2) * (p.st_w + 2));
           const int i = fast_div(r, p.st_mul_row, p.st_shr_row), j = r - i * (p.st_w + 2);
-          keep = i >= 1 && i <= p.st_h && j >= 1 && j <= p.st_w;
+          if (!p.bw_planes) {
+            keep = i >= 1 && i <= p.st_h && j >= 1 && j <= p.st_w;
+            if (bw) rrow = p.bw_raw + q * (long long)N;
+          } else {
+            const int hp = 2 * (i - 1) + (pl >> 1), wp = 2 * (j - 1) + (pl & 1);
+            keep = hp >= 1 && hp <= p.bw_H && wp >= 1 && wp <= p.bw_W;
+            rrow = p.bw_raw + (((long long)n * (p.bw_H + 2) + hp) * (p.bw_W + 2) + wp) * (long long)N;
+          }
         }
 #pragma unroll
         for (int c0 = 0; c0 < N; c0 += 16) {
@@ -333,7 +383,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
             *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          if (p.st_out) {                     // warp-uniform: statistics of exactly the values the BatchNorm kernels will read back
+          if (p.st_out && !bw) {              // warp-uniform: statistics of exactly the values the BatchNorm kernels will read back
             float x[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -342,6 +392,29 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
             }
             float cs, cq;
             warp_colsum16_sq(x, lane, cs, cq);
+            st_s[c0 / 16] += cs;
+            st_q[c0 / 16] += cq;
+          } else if (p.st_out) {              // BatchNorm-backward sums over g = dact * relu'(bn(raw)) and g * raw, from the bf16 values just stored
+            uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (keep) {
+              rv[0] = __ldg(reinterpret_cast<const uint4*>(rrow + c0));
+              rv[1] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8));
+            }
+            const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+            float ga[16], gx[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float x0 = __uint_as_float(rw[i] << 16), x1 = __uint_as_float(rw[i] & 0xffff0000u);
+              const float d0 = __uint_as_float(pk[i] << 16), d1 = __uint_as_float(pk[i] & 0xffff0000u);
+              const float g0 = (keep && fmaf(x0, s_ga[c0 + 2 * i], s_gb[c0 + 2 * i]) > 0.f) ? d0 : 0.f;
+              const float g1 = (keep && fmaf(x1, s_ga[c0 + 2 * i + 1], s_gb[c0 + 2 * i + 1]) > 0.f) ? d1 : 0.f;
+              ga[2 * i] = g0;
+              ga[2 * i + 1] = g1;
+              gx[2 * i] = g0 * x0;
+              gx[2 * i + 1] = g1 * x1;
+            }
+            float cs, cq;
+            warp_colsum16_pair(ga, gx, lane, cs, cq);
             st_s[c0 / 16] += cs;
             st_q[c0 / 16] += cq;
           }
@@ -363,8 +436,14 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
-  if (p.st_out)
+  if (p.st_out && !p.bw_raw)
     for (int i = tid; i < 2 * N; i += blockDim.x) atomicAdd(p.st_out + i, (double)s_stat[i]);
+  if (p.st_out && p.bw_raw)               // sum g*xhat = invstd * (sum g*x - mean * sum g), combined in fp64 (as pad_reduce_kernel does)
+    for (int i = tid; i < N; i += blockDim.x) {
+      const double a0 = (double)s_stat[i], a1 = (double)s_stat[N + i];
+      atomicAdd(p.st_out + i, a0);
+      atomicAdd(p.st_out + N + i, (a1 - (double)p.bw_mean[i] * a0) * (double)p.bw_invstd[i]);
+    }
   if (g_fc_debug && tid == 0) {      // grid-wide first entry / last exit (ns) behind the per-CTA records
     atomicMin((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8, (unsigned long long)t_entry);
     atomicMax((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8 + 1, globaltimer_ns());
@@ -569,8 +648,28 @@ int flat_fwd(const void* x, const void* w_fwd, const float* bias, void* y, int N
 }
 }  // namespace
 
-CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
-                                          void* stream) {
+namespace {
+struct BwStats {           // BatchNorm-backward reductions fused into the data-gradient epilogue (see FcParams::bw_raw)
+  const void* raw;
+  const float *gamma, *beta, *mean, *invstd;
+  double* ws;
+};
+
+void set_bw(FcParams& p, const BwStats* bw, int H, int W, int planes) {
+  if (!bw) return;
+  p.bw_raw = (const __nv_bfloat16*)bw->raw;
+  p.bw_gamma = bw->gamma; p.bw_beta = bw->beta; p.bw_mean = bw->mean; p.bw_invstd = bw->invstd;
+  p.st_out = bw->ws;
+  p.bw_H = H; p.bw_W = W; p.bw_planes = planes;
+  // the rows of this launch live in the geometry (st_h+2) x (st_w+2): the padded input itself (stride 1) or one phase plane (stride 2)
+  p.st_h = planes ? (H - 1) / 2 + 1 : H;
+  p.st_w = planes ? (W - 1) / 2 + 1 : W;
+  fast_div_init((unsigned)((p.st_h + 2) * (p.st_w + 2)), p.st_mul_img, p.st_shr_img);
+  fast_div_init((unsigned)(p.st_w + 2), p.st_mul_row, p.st_shr_row);
+}
+
+int flat_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride, const BwStats* bw,
+               void* stream) {
   // (N,H,W,Cin) is the convolution INPUT geometry.  stride 1: dy, dx padded-flat (N,H+2,W+2,.).  stride 2: dy padded-flat
   // (N,Ho+2,Wo+2,Cout), dx = four phase planes in that same geometry.
   if (stride != 1 && stride != 2) return (int)cudaErrorInvalidValue;
@@ -593,6 +692,8 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
       u.w_row0 = 0;
       for (int t = 0; t < 9; ++t) u.tap_delta[t] = (2 - t / 3) * Wp + (2 - t % 3);
     }
+    if (bw && p.rows > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    set_bw(p, bw, H, W, 0);
     return run_flat(dy, p.rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
@@ -623,8 +724,11 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
         }
       }
     }
+    if (bw && rows > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    set_bw(p, bw, H, W, 1);
     return run_flat(dy, rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
   }
+  if (bw) return (int)cudaErrorNotSupported;      // the fused reductions need the one-launch form (plane index per work item)
   for (int pl = 0; pl < 4; ++pl) {
     FcParams p;
     memset(&p, 0, sizeof(p));
@@ -648,6 +752,20 @@ CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, v
     if (e) return e;
   }
   return 0;
+}
+}  // namespace
+
+CVAD_API int cvad_flat_conv3x3_dgrad_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                                          void* stream) {
+  return flat_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, stride, nullptr, stream);
+}
+
+CVAD_API int cvad_flat_conv3x3_dgrad_bnstats_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout,
+                                                  int stride, const void* raw_in, const float* gamma, const float* beta, const float* mean,
+                                                  const float* invstd, double* ws, void* stream) {
+  if (!raw_in || !ws || Cin != n_block_of(Cin)) return (int)cudaErrorInvalidValue;
+  BwStats bw = {raw_in, gamma, beta, mean, invstd, ws};
+  return flat_dgrad(dy, w_dgrad, dx, N, H, W, Cin, Cout, stride, &bw, stream);
 }
 
 // ================================================================================================ weight gradient

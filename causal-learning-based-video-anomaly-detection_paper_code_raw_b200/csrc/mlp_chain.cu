@@ -8,24 +8,27 @@
 // in shared memory.  The weight / bias gradients stay what they were
 // (split-K GEMMs and column sums on the side stream, off the critical path): the backward kernel leaves every layer's dz in HBM for them.
 //
-// Per layer a CTA first stages the whole weight matrix in shared memory (cooperative, coalesced, every thread with several loads in
-// flight -- a first version that read weights from L2 inside the dot-product loops was latency-bound at 80 us per chain), then every thread
-// computes (row, column) dot products from shared memory: forward h'[r][j] = sum_k h[r][k] W[j][k] (weight rows padded to an odd pitch:
-// conflict-free across j), backward dh[r][k] = sum_j dz[r][j] W[j][k] (consecutive k: conflict-free).  A layer must fit: (din | 1) * dout <= 33024
-// and widths <= 256 -- the 6144 -> 512 -> 256 layers of the detector / classifier stay split-K GEMMs, which spread their weights over many SMs
-// instead of streaming 0.5 MB through each of 4..64 CTAs.
+// A CTA first stages the weight matrices of ALL layers of the chain in shared memory -- one cooperative, coalesced pass with every
+// thread keeping several 16-byte loads in flight, issued BEFORE the programmatic-dependent-launch wait: parameters do not depend on the
+// stream predecessor, so the staging overlaps the tail of the previous kernel (two earlier versions, weights read from L2 inside the
+// dot-product loops / staged layer by layer, were latency-bound at 80 / 20 us per chain).  Then the layers run back to back out of shared
+// memory, separated only by __syncthreads: a thread owns one output column (forward) or one input column (backward) for four of the
+// CTA's eight rows -- weights are read once per four rows, activations as 16-byte broadcasts.  Forward h'[r][j] = sum_k h[r][k] W[j][k]
+// (weight rows padded to an odd pitch: conflict-free across j); backward dh[r][k] = sum_j dz[r][j] W[j][k] (consecutive k: conflict-free).
+// A chain must fit: widths <= 256 and all its (padded) weight matrices together <= 50 000 floats (the 6144 -> 512 -> 256 layers of the
+// detector / classifier stay split-K GEMMs, which spread their weights over many SMs instead of streaming 0.5 MB through each of 4..64 CTAs).
 #include "common.cuh"
 #include "cvad_b200.h"
 
 namespace {
 
 constexpr int MC_MAX_LAYERS = 8;
-constexpr int MC_ROWS = 8;
+constexpr int MC_ROWS = 8;                             // rows per CTA
+constexpr int MC_RB = 4;                               // rows per thread
 constexpr int MC_THREADS = 256;
 constexpr int MC_MAXDIM = 256;
-constexpr int MC_MAXW = 33024;                         // (din | 1) * dout of one layer: up to 256 -> 128 (129 KB of shared memory)
-constexpr int MC_HPITCH = MC_MAXDIM + 4;
-constexpr size_t MC_SMEM = (size_t)(2 * MC_ROWS * MC_HPITCH + MC_MAXW + MC_MAXDIM) * sizeof(float);      // activations x2 + weights (padded pitch)
+constexpr int MC_MAXW = 50000;                         // floats of all staged weight matrices of a chain (200 KB)
+constexpr int MC_HPITCH = MC_MAXDIM + 4;               // multiple of 4: rows are read as float4
 
 struct McLayer {
   const float* W;         // (dout, din) row-major, nn.Linear layout
@@ -35,6 +38,7 @@ struct McLayer {
   float* dz;              // backward: (rows, dout) gradient w.r.t. the pre-activation, written for the weight-gradient GEMMs
   float mask_scale;
   int din, dout, act;
+  int woff;               // offset (floats) of this layer's staged weights in shared memory
 };
 
 struct McChain {
@@ -43,7 +47,7 @@ struct McChain {
   McLayer L[MC_MAX_LAYERS];
 };
 
-// stage W (dout, din) row-major into shared memory with row pitch wp (odd when din is even: rows land in different banks)
+// stage W (dout, din) row-major into shared memory with row pitch wp
 __device__ __forceinline__ void stage_weights(const float* __restrict__ W, int din, int dout, int wp, float* __restrict__ ws) {
   const int n = din * dout;
   if ((din & 3) == 0 && ((uintptr_t)W & 15) == 0) {
@@ -63,66 +67,93 @@ __device__ __forceinline__ void stage_weights(const float* __restrict__ W, int d
 }
 
 __global__ void __launch_bounds__(MC_THREADS) mlp_chain_fwd_kernel(const McChain ch, const float* __restrict__ x, float* __restrict__ out) {
-  cvad_pdl_enter();
-  extern __shared__ float mc_smem[];
+  extern __shared__ __align__(16) float mc_smem[];
   float* hb[2] = {mc_smem, mc_smem + MC_ROWS * MC_HPITCH};
-  float* ws = mc_smem + 2 * MC_ROWS * MC_HPITCH;
+  float* wsm = mc_smem + 2 * MC_ROWS * MC_HPITCH;
   const int tid = threadIdx.x;
+  // parameters first: they do not depend on the kernel in front of this one
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int l = 0; l < ch.n; ++l) stage_weights(ch.L[l].W, ch.L[l].din, ch.L[l].dout, ch.L[l].din | 1, wsm + ch.L[l].woff);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long r0 = (long long)blockIdx.x * MC_ROWS;
   const int nr = (int)(ch.rows - r0 < MC_ROWS ? ch.rows - r0 : MC_ROWS);
   const int d0 = ch.L[0].din;
-  for (int i = tid; i < MC_ROWS * d0; i += MC_THREADS) {
-    const int r = i / d0, k = i - r * d0;
-    hb[0][r * MC_HPITCH + k] = r < nr ? __ldg(x + (r0 + r) * d0 + k) : 0.f;
+  for (int i = tid; i < MC_ROWS * MC_HPITCH; i += MC_THREADS) {
+    const int r = i / MC_HPITCH, k = i - r * MC_HPITCH;
+    hb[0][i] = (r < nr && k < d0) ? __ldg(x + (r0 + r) * d0 + k) : 0.f;       // zero fill: the float4 reads below run to a multiple of 4
+    hb[1][i] = 0.f;
   }
+  __syncthreads();
   int cur = 0;
   for (int l = 0; l < ch.n; ++l) {
     const McLayer L = ch.L[l];
-    const int din = L.din, dout = L.dout;
-    const int wp = din | 1;
+    const int din = L.din, dout = L.dout, wp = din | 1;
     const float* h = hb[cur];
     float* hn = hb[cur ^ 1];
+    const float* ws = wsm + L.woff;
     const bool last = l == ch.n - 1;
-    stage_weights(L.W, din, dout, wp, ws);
-    __syncthreads();
-    // (row, column) items, column fastest: a warp reads 32 weight rows at an odd pitch (conflict-free) and one activation row (broadcast)
-    for (int i = tid; i < MC_ROWS * dout; i += MC_THREADS) {
-      const int r = i / dout, j = i - r * dout;
+    const int din4 = (din + 3) & ~3;
+    // item = (row block of MC_RB rows, column j), column fastest
+    for (int i = tid; i < (MC_ROWS / MC_RB) * dout; i += MC_THREADS) {
+      const int rb = i / dout, j = i - rb * dout;
       const float* w = ws + j * wp;
-      const float* hr = h + r * MC_HPITCH;
-      float a0 = 0.f, a1 = 0.f;
-      int k = 0;
-      for (; k + 1 < din; k += 2) {
-        a0 = fmaf(hr[k], w[k], a0);
-        a1 = fmaf(hr[k + 1], w[k + 1], a1);
+      float acc[MC_RB];
+#pragma unroll
+      for (int r = 0; r < MC_RB; ++r) acc[r] = 0.f;
+      for (int k = 0; k < din4; k += 4) {
+        float wv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wv[e] = k + e < din ? w[k + e] : 0.f;
+#pragma unroll
+        for (int r = 0; r < MC_RB; ++r) {
+          const float4 hv = *reinterpret_cast<const float4*>(h + (rb * MC_RB + r) * MC_HPITCH + k);
+          acc[r] = fmaf(hv.x, wv[0], acc[r]);
+          acc[r] = fmaf(hv.y, wv[1], acc[r]);
+          acc[r] = fmaf(hv.z, wv[2], acc[r]);
+          acc[r] = fmaf(hv.w, wv[3], acc[r]);
+        }
       }
-      if (k < din) a0 = fmaf(hr[k], w[k], a0);
-      float v = a0 + a1 + (L.b ? __ldg(L.b + j) : 0.f);
-      v = cvad_act(v, L.act);
-      if (r < nr) {
-        if (L.mask) v *= __ldg(L.mask + (r0 + r) * dout + j) * L.mask_scale;
-        if (L.save) L.save[(r0 + r) * dout + j] = v;
-        if (last) out[(r0 + r) * dout + j] = v;
+      const float bj = L.b ? __ldg(L.b + j) : 0.f;
+#pragma unroll
+      for (int r = 0; r < MC_RB; ++r) {
+        const int row = rb * MC_RB + r;
+        float v = cvad_act(acc[r] + bj, L.act);
+        if (row < nr) {
+          if (L.mask) v *= __ldg(L.mask + (r0 + row) * dout + j) * L.mask_scale;
+          if (L.save) L.save[(r0 + row) * dout + j] = v;
+          if (last) out[(r0 + row) * dout + j] = v;
+        } else {
+          v = 0.f;
+        }
+        hn[row * MC_HPITCH + j] = v;
       }
-      hn[r * MC_HPITCH + j] = v;
     }
     __syncthreads();
+    // columns dout .. dout4 of the new activations must read as zero for the next layer's float4 loop
+    if (!last) {
+      const int dn4 = (dout + 3) & ~3;
+      for (int i = tid; i < MC_ROWS * (dn4 - dout); i += MC_THREADS) hn[(i / (dn4 - dout)) * MC_HPITCH + dout + i % (dn4 - dout)] = 0.f;
+      if (dn4 != dout) __syncthreads();
+    }
     cur ^= 1;
   }
 }
 
 __global__ void __launch_bounds__(MC_THREADS) mlp_chain_bwd_kernel(const McChain ch, const float* __restrict__ dy, float* __restrict__ dx) {
-  cvad_pdl_enter();
-  extern __shared__ float mc_smem[];
+  extern __shared__ __align__(16) float mc_smem[];
   float* gb[2] = {mc_smem, mc_smem + MC_ROWS * MC_HPITCH};
-  float* ws = mc_smem + 2 * MC_ROWS * MC_HPITCH;
+  float* wsm = mc_smem + 2 * MC_ROWS * MC_HPITCH;
   const int tid = threadIdx.x;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int l = ch.n - 1; l >= (dx ? 0 : 1); --l) stage_weights(ch.L[l].W, ch.L[l].din, ch.L[l].dout, ch.L[l].din, wsm + ch.L[l].woff);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long r0 = (long long)blockIdx.x * MC_ROWS;
   const int nr = (int)(ch.rows - r0 < MC_ROWS ? ch.rows - r0 : MC_ROWS);
   const int dl = ch.L[ch.n - 1].dout;
-  for (int i = tid; i < MC_ROWS * dl; i += MC_THREADS) {
-    const int r = i / dl, j = i - r * dl;
-    gb[0][r * MC_HPITCH + j] = r < nr ? __ldg(dy + (r0 + r) * dl + j) : 0.f;
+  for (int i = tid; i < MC_ROWS * MC_HPITCH; i += MC_THREADS) {
+    const int r = i / MC_HPITCH, j = i - r * MC_HPITCH;
+    gb[0][i] = (r < nr && j < dl) ? __ldg(dy + (r0 + r) * dl + j) : 0.f;
+    gb[1][i] = 0.f;
   }
   __syncthreads();
   int cur = 0;
@@ -131,8 +162,7 @@ __global__ void __launch_bounds__(MC_THREADS) mlp_chain_bwd_kernel(const McChain
     const int din = L.din, dout = L.dout;
     float* g = gb[cur];
     float* gp = gb[cur ^ 1];
-    const bool need_prev = l > 0 || dx != nullptr;
-    if (need_prev) stage_weights(L.W, din, dout, din, ws);            // natural pitch: the reads below run along k
+    const float* ws = wsm + L.woff;
     // dz = g * mask*scale * act'(y); y is the stored post-mask output (sigmoid / tanh: the pre-mask value is recovered, as cvad_act_mask_bwd_f32 does)
     for (int i = tid; i < MC_ROWS * dout; i += MC_THREADS) {
       const int r = i / dout, j = i - r * dout;
@@ -151,20 +181,33 @@ __global__ void __launch_bounds__(MC_THREADS) mlp_chain_bwd_kernel(const McChain
       g[r * MC_HPITCH + j] = v;
     }
     __syncthreads();
-    if (!need_prev) break;
-    // gp[r][k] = sum_j dz[r][j] W[j][k]   ((row, k) items, k fastest)
-    for (int i = tid; i < MC_ROWS * din; i += MC_THREADS) {
-      const int r = i / din, k = i - r * din;
-      const float* gr = g + r * MC_HPITCH;
-      float a0 = 0.f, a1 = 0.f;
-      int j = 0;
-      for (; j + 1 < dout; j += 2) {
-        a0 = fmaf(gr[j], ws[j * din + k], a0);
-        a1 = fmaf(gr[j + 1], ws[(j + 1) * din + k], a1);
+    if (l == 0 && dx == nullptr) break;
+    // gp[r][k] = sum_j dz[r][j] W[j][k]: item = (row block, column k), k fastest; columns >= dout of g are zero (fill above / below)
+    const int dout4 = (dout + 3) & ~3;
+    for (int i = tid; i < (MC_ROWS / MC_RB) * din; i += MC_THREADS) {
+      const int rb = i / din, k = i - rb * din;
+      float acc[MC_RB];
+#pragma unroll
+      for (int r = 0; r < MC_RB; ++r) acc[r] = 0.f;
+      for (int j = 0; j < dout4; j += 4) {
+        float wv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) wv[e] = j + e < dout ? ws[(j + e) * din + k] : 0.f;
+#pragma unroll
+        for (int r = 0; r < MC_RB; ++r) {
+          const float4 gv = *reinterpret_cast<const float4*>(g + (rb * MC_RB + r) * MC_HPITCH + j);
+          acc[r] = fmaf(gv.x, wv[0], acc[r]);
+          acc[r] = fmaf(gv.y, wv[1], acc[r]);
+          acc[r] = fmaf(gv.z, wv[2], acc[r]);
+          acc[r] = fmaf(gv.w, wv[3], acc[r]);
+        }
       }
-      if (j < dout) a0 = fmaf(gr[j], ws[j * din + k], a0);
-      gp[r * MC_HPITCH + k] = a0 + a1;
+#pragma unroll
+      for (int r = 0; r < MC_RB; ++r) gp[(rb * MC_RB + r) * MC_HPITCH + k] = acc[r];
     }
+    // the next layer reads gp as its g with width din: keep the columns up to the next multiple of 4 zero
+    const int din4 = (din + 3) & ~3;
+    for (int i = tid; i < MC_ROWS * (din4 - din); i += MC_THREADS) gp[(i / (din4 - din)) * MC_HPITCH + din + i % (din4 - din)] = 0.f;
     __syncthreads();
     cur ^= 1;
   }
@@ -177,14 +220,15 @@ __global__ void __launch_bounds__(MC_THREADS) mlp_chain_bwd_kernel(const McChain
   }
 }
 
-int fill_chain(McChain& ch, long long rows, int n_layers, const int* dims, const int* acts, const void* const* weights,
+// returns 0 and the dynamic shared-memory size, or an error; `fwd` selects the padded (odd) weight pitch of the forward kernel
+int fill_chain(McChain& ch, size_t& smem, bool fwd, long long rows, int n_layers, const int* dims, const int* acts, const void* const* weights,
                const void* const* biases, const void* const* masks, const float* mask_scales, void* const* saves, void* const* dzs) {
   if (n_layers < 1 || n_layers > MC_MAX_LAYERS || rows < 0) return (int)cudaErrorInvalidValue;
   ch.n = n_layers;
   ch.rows = rows;
+  long long off = 0;
   for (int l = 0; l < n_layers; ++l) {
     if (dims[l] < 1 || dims[l] > MC_MAXDIM || dims[l + 1] < 1 || dims[l + 1] > MC_MAXDIM) return (int)cudaErrorInvalidValue;
-    if ((long long)(dims[l] | 1) * dims[l + 1] > MC_MAXW) return (int)cudaErrorInvalidValue;
     McLayer& L = ch.L[l];
     L.W = (const float*)weights[l];
     L.b = biases ? (const float*)biases[l] : nullptr;
@@ -195,7 +239,11 @@ int fill_chain(McChain& ch, long long rows, int n_layers, const int* dims, const
     L.din = dims[l];
     L.dout = dims[l + 1];
     L.act = acts[l];
+    L.woff = (int)off;
+    off += (long long)((fwd ? (dims[l] | 1) : dims[l]) * dims[l + 1] + 3) & ~3LL;
   }
+  if (off > MC_MAXW) return (int)cudaErrorInvalidValue;
+  smem = (size_t)(2 * MC_ROWS * MC_HPITCH + off) * sizeof(float);
   return 0;
 }
 
@@ -206,13 +254,14 @@ CVAD_API int cvad_mlp_chain_fwd_f32(const float* x, long long rows, int n_layers
                                     void* stream) {
   if (rows == 0) return 0;
   McChain ch;
-  int e = fill_chain(ch, rows, n_layers, dims, acts, weights, biases, masks, mask_scales, saves, nullptr);
+  size_t smem = 0;
+  int e = fill_chain(ch, smem, true, rows, n_layers, dims, acts, weights, biases, masks, mask_scales, saves, nullptr);
   if (e) return e;
   const unsigned grid = (unsigned)((rows + MC_ROWS - 1) / MC_ROWS);
   static size_t configured[CVAD_MAX_DEVICES] = {};
-  cudaError_t ce = cvad_ensure_dyn_smem(mlp_chain_fwd_kernel, MC_SMEM, configured);
+  cudaError_t ce = cvad_ensure_dyn_smem(mlp_chain_fwd_kernel, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
-  ce = cvad_launch_pdl(mlp_chain_fwd_kernel, dim3(grid), dim3(MC_THREADS), MC_SMEM, (cudaStream_t)stream, ch, x, out);
+  ce = cvad_launch_pdl(mlp_chain_fwd_kernel, dim3(grid), dim3(MC_THREADS), smem, (cudaStream_t)stream, ch, x, out);
   return (int)ce;
 }
 
@@ -221,14 +270,15 @@ CVAD_API int cvad_mlp_chain_bwd_f32(const float* dy, long long rows, int n_layer
                                     void* stream) {
   if (rows == 0) return 0;
   McChain ch;
-  int e = fill_chain(ch, rows, n_layers, dims, acts, weights, nullptr, masks, mask_scales, (void* const*)saves, dzs);
+  size_t smem = 0;
+  int e = fill_chain(ch, smem, false, rows, n_layers, dims, acts, weights, nullptr, masks, mask_scales, (void* const*)saves, dzs);
   if (e) return e;
   for (int l = 0; l < n_layers; ++l)
     if (!ch.L[l].dz || (ch.L[l].act != ACT_NONE && !ch.L[l].save)) return (int)cudaErrorInvalidValue;
   const unsigned grid = (unsigned)((rows + MC_ROWS - 1) / MC_ROWS);
   static size_t configured[CVAD_MAX_DEVICES] = {};
-  cudaError_t ce = cvad_ensure_dyn_smem(mlp_chain_bwd_kernel, MC_SMEM, configured);
+  cudaError_t ce = cvad_ensure_dyn_smem(mlp_chain_bwd_kernel, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
-  ce = cvad_launch_pdl(mlp_chain_bwd_kernel, dim3(grid), dim3(MC_THREADS), MC_SMEM, (cudaStream_t)stream, ch, dy, dx);
+  ce = cvad_launch_pdl(mlp_chain_bwd_kernel, dim3(grid), dim3(MC_THREADS), smem, (cudaStream_t)stream, ch, dy, dx);
   return (int)ce;
 }

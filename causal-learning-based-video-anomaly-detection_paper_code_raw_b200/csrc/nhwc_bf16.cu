@@ -516,6 +516,27 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   return 0;
 }
 
+// The same with the two per-channel sums already in ws (taken by the data-gradient epilogue of the layer above,
+// cvad_flat_conv3x3_dgrad_bnstats_bf16): only the apply pass and the dgamma / dbeta update run -- one pass over raw and dact instead of two.
+CVAD_API int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in,
+                                             const float* mean, const float* invstd, const float* gamma, const float* beta, int training,
+                                             double* ws, float* dgamma, float* dbeta, void* stream) {
+  PadGeo g;
+  if (make_geo(g, N, H, W, C, phase_in) || !draw) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
+  const int rows = N * (H + 2);
+  const int ab = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
+  if (phase_in)
+    pad_bn_relu_bwd_apply_kernel<1><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W, training);
+  else
+    pad_bn_relu_bwd_apply_kernel<0><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W, training);
+  CVAD_LAUNCH_CHECK();
+  bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
 CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream) {
   long long total = (long long)N * OH * OW * (C / 8);
   if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;

@@ -307,7 +307,7 @@ def linear_act(x, weight, bias, act=ACT_NONE, mask=None, p_drop=0.0, gate=None):
 
 
 # ------------------------------------------------------------------------------------------------ fused MLP chains
-CHAIN_MAX_DIM, CHAIN_MAX_LAYERS, CHAIN_MAX_W = 256, 8, 33024
+CHAIN_MAX_DIM, CHAIN_MAX_LAYERS, CHAIN_MAX_W = 256, 8, 50000
 FUSED_CHAINS = os.environ.get("CVAD_FUSED_CHAINS", "1") != "0"
 
 
@@ -387,10 +387,12 @@ def mlp_chain(x, layers):
 
 
 def chainable(layers, din) -> bool:
-    """Whether a Linear stack fits the fused kernel: widths <= 256 and every weight matrix small enough to be staged in shared memory."""
+    """Whether a Linear stack fits the fused kernel: widths <= 256 and all weight matrices together small enough for shared memory."""
     if not FUSED_CHAINS or not 1 <= len(layers) <= CHAIN_MAX_LAYERS or din > CHAIN_MAX_DIM:
         return False
-    return all(l[0].shape[0] <= CHAIN_MAX_DIM and (l[0].shape[1] | 1) * l[0].shape[0] <= CHAIN_MAX_W for l in layers)
+    if any(l[0].shape[0] > CHAIN_MAX_DIM for l in layers):
+        return False
+    return sum(((l[0].shape[1] | 1) * l[0].shape[0] + 3) // 4 * 4 for l in layers) <= CHAIN_MAX_W
 
 
 # ------------------------------------------------------------------------------------------------ batch norm

@@ -42,6 +42,8 @@ FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm 
 # weight-gradient GEMMs on a side stream: wgrad_i needs only draw_i and a_{i-1}, so it can run beside the HBM-bound BatchNorm backward of
 # the next layer down instead of in front of it (a parallel branch of the captured step graph)
 WGRAD_OVERLAP = os.environ.get("CVAD_WGRAD_OVERLAP", "0") == "1"
+# BatchNorm-backward reductions of layer i-1 taken in the data-gradient epilogue of layer i (one pass over raw / dact instead of two)
+FUSED_BN_BWD = os.environ.get("CVAD_FUSED_BN_BWD", "1") != "0"
 
 
 def _layers(bb):
@@ -173,14 +175,20 @@ class _BackboneBF16(torch.autograd.Function):
         cur = torch.cuda.current_stream()
         side = ops.aux_stream(dev, 1) if WGRAD_OVERLAP else None
         keep = []                     # operands of side-stream launches stay referenced until the join (the allocator tracks one stream)
+        sums_ready = False            # the BatchNorm-backward sums of layer idx were taken by the data-gradient of layer idx + 1
         for idx in range(len(layers) - 1, -1, -1):
             conv, bn = layers[idx]
             a_in, raw, mean, invstd, wd, (hi, wi, cin, cout, stride, ho, wo), bn_training, phase_out = saved[idx]
             draw = torch.empty_like(raw)
             dg = grad_buffer(bn.weight) if _wants_grad(bn.weight) else None
             db = grad_buffer(bn.bias) if _wants_grad(bn.bias) else None
-            _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
-                  _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
+            if sums_ready:      # the two per-channel sums are already in the workspace (taken by the data-gradient above)
+                _call("cvad_pad_bn_relu_bwd_apply_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
+                      _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
+            else:
+                _call("cvad_pad_bn_relu_bwd_bf16", _ptr(raw), _ptr(dact), _ptr(draw), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
+                      _ptr(bn.weight), _ptr(bn.bias), int(bn_training), _ptr(ops.bn_workspace(dev, cout)), _ptr(dg), _ptr(db), st)
+            sums_ready = False
             if _wants_grad(conv.weight):
                 wst = st
                 if side is not None:
@@ -197,7 +205,15 @@ class _BackboneBF16(torch.autograd.Function):
                 grad_buffer(conv.bias)          # analytically zero (BatchNorm removes the mean); keep the tensor "with grad"
             if idx > 0:
                 dact = torch.empty(a_in.shape, device=dev, dtype=BF16)
-                _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, st)
+                _, raw_lo, mean_lo, invstd_lo, _, _, lo_training, _ = saved[idx - 1]
+                bn_lo = layers[idx - 1][1]
+                if FUSED_BN_BWD and lo_training and cin in (32, 64, 128, 256):
+                    # dact is the gradient w.r.t. relu(bn(raw_lo)): its epilogue also takes sum g / sum g*xhat for that BatchNorm's backward
+                    _call("cvad_flat_conv3x3_dgrad_bnstats_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, _ptr(raw_lo),
+                          _ptr(bn_lo.weight), _ptr(bn_lo.bias), _ptr(mean_lo), _ptr(invstd_lo), _ptr(ops.bn_workspace(dev, cin)), st)
+                    sums_ready = True
+                else:
+                    _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(draw), _ptr(wd), _ptr(dact), N, hi, wi, cin, cout, stride, st)
             saved[idx] = None
         if side is not None:
             cur.wait_stream(side)

@@ -198,6 +198,16 @@ int cvad_flat_conv3x3_wgrad_bf16(const void* x, const void* dy, float* dw, int N
  * return): coalesced reductions along Cin, then one pass adds the staging buffer into dw (OIHW). */
 int cvad_flat_conv3x3_wgrad_staged_bf16(const void* x, const void* dy, float* dw, float* scratch, int N, int H, int W, int Cin, int Cout,
                                         int stride, void* stream);
+/* Data-gradient with the BatchNorm-BACKWARD reductions of the layer below fused into its epilogue (cad:131-136 backward): the rows it writes
+ * are dact = dL/d relu(bn(raw_in)); with g = dact * (bn(raw_in) > 0) it adds sum g and sum g*xhat over the interior pixels of raw_in
+ * (N,H+2,W+2,Cin padded-flat) to ws[0..Cin) / ws[Cin..2Cin) (fp64, zero on entry) -- what the reduce pass of cvad_pad_bn_relu_bwd_bf16
+ * computes by re-reading raw and dact.  cvad_pad_bn_relu_bwd_apply_bf16 then finishes the BatchNorm backward from those sums. */
+int cvad_flat_conv3x3_dgrad_bnstats_bf16(const void* dy, const void* w_dgrad, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                                         const void* raw_in, const float* gamma, const float* beta, const float* mean, const float* invstd,
+                                         double* ws, void* stream);
+int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in, const float* mean,
+                                    const float* invstd, const float* gamma, const float* beta, int training, double* ws, float* dgamma,
+                                    float* dbeta, void* stream);
 /* development switch: 1 (default) = a stride-2 data-gradient is one launch walking its four phase planes, 0 = four launches */
 int cvad_flat_dgrad_mode(int one_launch);
 /* development switch: 1 (default) = stride-1 32->32 / 64->64 weight gradients stack the three kernel rows in the MMA's N dimension,
@@ -271,8 +281,8 @@ int cvad_mb_eval_metrics_f32(const float* scores, const float* graphs, long long
                              double* out8, void* stream);
 int cvad_moving_average_f32(const float* x, long long n, int w, double* out, void* stream);
 
-/* ---- fused MLP chains (mlp_chain.cu): n_layers <= 8 nn.Linear layers (widths <= 256, (din|1)*dout <= 33024 per layer: the weight matrix of a
- * layer is staged in shared memory) with bias, activation and dropout keep-mask in one
+/* ---- fused MLP chains (mlp_chain.cu): n_layers <= 8 nn.Linear layers (widths <= 256, sum over layers of (din|1)*dout <= 50000: all weight
+ * matrices of the chain are staged in shared memory) with bias, activation and dropout keep-mask in one
  * launch (forward) / one launch (data-gradient chain).  cad:167-179, 240-246, 318-326, 361-367, 407-413, 435-461, 525-538; s2:43-48, 77-89.
  * dims[n_layers+1] = {din_0, dout_0 (= din_1), ...}; acts[l] = CvadAct of layer l; weights[l] (dout,din) row-major; biases[l] / masks[l]
  * (rows,dout) may be NULL (the arrays themselves too); saves[l] (rows,dout) receives layer l's output (post activation, post mask) for

@@ -118,6 +118,51 @@ def test_flat_conv3x3_fwd_dgrad_wgrad(dev, case):
     assert e_f < 1e-2 and e_d < 1e-2 and e_w < 2e-3 and e_w2 < 2e-3
 
 
+@pytest.mark.parametrize("case", FLAT_CASES)
+def test_flat_dgrad_fused_bn_backward_reductions(dev, case):
+    """cvad_flat_conv3x3_dgrad_bnstats_bf16: the same dx as the plain data-gradient, and its epilogue's per-channel sums
+    sum g / sum g*xhat (g = dx * [bn(raw) > 0] over the interior pixels, from the bf16 dx it stored) equal what the BatchNorm
+    backward's own reduce pass computes from raw and dx -- for padded-flat (stride 1) and phase-plane (stride 2) outputs."""
+    from cvad_b200 import tc
+    from cvad_b200.ops import _call, _ptr, _st
+    N, H, W, Ci, Co, s = case
+    x, w, b, ref, dy, gx, gw = _inputs(dev, *case)
+    wd = torch.empty(9 * Ci, Co, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_pack_w3x3_bf16", _ptr(w), Co, Ci, s, None, _ptr(wd), _st())
+    dyp = tc.to_padded(dy)
+    shape = (N, H + 2, W + 2, Ci) if s == 1 else tuple(tc.act_shape(N, H, W, Ci, True))
+    dx0 = torch.full(shape, 7.0, device=dev, dtype=torch.bfloat16)
+    dx1 = torch.full(shape, 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_flat_conv3x3_dgrad_bf16", _ptr(dyp), _ptr(wd), _ptr(dx0), N, H, W, Ci, Co, s, _st())
+    # the layer below: raw (junk border), BatchNorm scale / shift chosen so that roughly half of the ReLUs are open
+    rawf = (torch.randn(N, Ci, H, W, generator=_g(21)) * 1.5 + 0.3).to(dev).to(torch.bfloat16).float()
+    raw = tc.to_padded(rawf)
+    raw[:, 0] = 9.0
+    raw[:, :, -1] = -5.0
+    gam = (torch.rand(Ci, generator=_g(22)) + 0.5).to(dev)
+    gam[::5] *= -1.0
+    bet = (torch.randn(Ci, generator=_g(23)) * 0.3).to(dev)
+    mean = (torch.randn(Ci, generator=_g(24)) * 0.2 + 0.3).to(dev)
+    invstd = (torch.rand(Ci, generator=_g(25)) * 0.5 + 0.4).to(dev)
+    ws = torch.zeros(2 * Ci, device=dev, dtype=torch.float64)
+    _call("cvad_flat_conv3x3_dgrad_bnstats_bf16", _ptr(dyp), _ptr(wd), _ptr(dx1), N, H, W, Ci, Co, s, _ptr(raw), _ptr(gam), _ptr(bet), _ptr(mean),
+          _ptr(invstd), _ptr(ws), _st())
+    torch.cuda.synchronize()
+    d0 = tc.from_padded(dx0, H, W) if s == 1 else tc.from_phase(dx0, H, W)
+    d1 = tc.from_padded(dx1, H, W) if s == 1 else tc.from_phase(dx1, H, W)
+    assert torch.equal(d0, d1)
+    sh = (1, -1, 1, 1)
+    ga = (gam * invstd).view(sh)
+    gate = (rawf * ga + (bet.view(sh) - mean.view(sh) * ga)) > 0
+    g = (d1 * gate).double()
+    xhat = ((rawf - mean.view(sh)) * invstd.view(sh)).double()
+    s0, s1 = g.sum(dim=(0, 2, 3)), (g * xhat).sum(dim=(0, 2, 3))
+    scale = float(g.abs().sum(dim=(0, 2, 3)).max())
+    e0, e1 = float((ws[:Ci] - s0).abs().max()) / scale, float((ws[Ci:] - s1).abs().max()) / scale
+    print(f"[flat] {case}: fused BN-backward sums, error relative to sum|g|: {e0:.2e} / {e1:.2e}")
+    assert e0 < 2e-5 and e1 < 5e-5
+
+
 def test_layout_helpers_roundtrip(dev):
     from cvad_b200 import tc
     x = torch.randn(2, 8, 15, 23, generator=_g(1)).to(dev).to(torch.bfloat16).float()
