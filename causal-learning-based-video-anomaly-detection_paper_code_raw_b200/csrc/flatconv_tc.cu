@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
       for (int s = eg; s < sub; s += 2) {
         const uint32_t use = acc_cnt + s;
         const int slot = use % NSLOT;
-        mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
-        tc_fence_after();
+        // row bookkeeping first: none of it depends on the accumulator, and the raw loads of the fused BatchNorm-backward reductions
+        // are issued BEFORE the wait so that their latency hides behind the MMAs still running for this slot
         const long long q = q0 + s * 128 + ew * 32 + lane;
         const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
         __nv_bfloat16* orow = out + (p.out_row_base + pl * p.plane_out_stride + q) * (long long)p.ld_out + nb * N;
@@ -367,6 +367,21 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
             rrow = p.bw_raw + (((long long)n * (p.bw_H + 2) + hp) * (p.bw_W + 2) + wp) * (long long)N;
           }
         }
+        constexpr int NCH = N / 16;
+        constexpr int PF = NCH < 4 ? NCH : 4;             // 16-column chunks of raw in flight per thread (a ring of 2*PF 16-byte registers)
+        uint4 rq[PF][2];
+        const bool bwk = bw && keep;
+#pragma unroll
+        for (int c = 0; c < PF; ++c) {
+          rq[c][0] = make_uint4(0, 0, 0, 0);
+          rq[c][1] = make_uint4(0, 0, 0, 0);
+          if (bwk) {
+            rq[c][0] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16));
+            rq[c][1] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16 + 8));
+          }
+        }
+        mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t v[16];
@@ -395,10 +410,14 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
             st_s[c0 / 16] += cs;
             st_q[c0 / 16] += cq;
           } else if (p.st_out) {              // BatchNorm-backward sums over g = dact * relu'(bn(raw)) and g * raw, from the bf16 values just stored
-            uint4 rv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (keep) {
-              rv[0] = __ldg(reinterpret_cast<const uint4*>(rrow + c0));
-              rv[1] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 8));
+            uint4 rv[2] = {rq[(c0 / 16) % PF][0], rq[(c0 / 16) % PF][1]};
+            if (c0 / 16 + PF < NCH) {         // refill the ring slot just consumed
+              rq[(c0 / 16) % PF][0] = make_uint4(0, 0, 0, 0);
+              rq[(c0 / 16) % PF][1] = make_uint4(0, 0, 0, 0);
+              if (bwk) {
+                rq[(c0 / 16) % PF][0] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + PF * 16));
+                rq[(c0 / 16) % PF][1] = __ldg(reinterpret_cast<const uint4*>(rrow + c0 + PF * 16 + 8));
+              }
             }
             const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
             float ga[16], gx[16];

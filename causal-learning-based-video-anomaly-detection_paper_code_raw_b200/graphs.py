@@ -23,12 +23,18 @@ class GraphedStep:
     ``__call__(*inputs)`` copies the inputs into the static buffers (an H2D copy when they live in pinned host memory),
     replays the graph and returns the static output tensors (valid until the next replay)."""
 
-    def __init__(self, step_fn, example_inputs, mutated=(), warmup: int = 3, pre_replay=None, between=None, tail_fn=None):
+    def __init__(self, step_fn, example_inputs, mutated=(), warmup: int = 3, pre_replay=None, between=None, tail_fn=None, stages=None):
         """``between`` / ``tail_fn`` split the step in two graphs around an eagerly issued call: graph(step_fn) ->
         between() -> graph(tail_fn).  The data-parallel trainer uses it to keep the NCCL gradient all-reduce OUT of the
-        captured graphs (``between``) while forward/backward and the fused optimizer are each one graph launch."""
+        captured graphs (``between``) while forward/backward and the fused optimizer are each one graph launch.
+
+        ``stages``: the general form, a list ``[(eager_fn or None, graph_fn), ...]`` run after ``step_fn``'s graph: for every entry
+        the eager callable is issued on the current stream (e.g. an asynchronous collective), then the graph of ``graph_fn()`` is
+        replayed.  All graphs share one memory pool, so later stages may use tensors that earlier stages produced."""
         self.pre_replay = pre_replay
-        self.between, self.tail_graph = between, None
+        if stages is None:
+            stages = [(between, tail_fn)] if (between is not None or tail_fn is not None) else []
+        self.stages = [(e, f, None) for e, f in stages]
         self.static_inputs = [torch.empty_like(t, device=t.device if t.is_cuda else torch.cuda.current_device()) for t in example_inputs]
         for s, t in zip(self.static_inputs, example_inputs):
             s.copy_(t)
@@ -39,10 +45,11 @@ class GraphedStep:
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 step_fn(*self.static_inputs)
-                if between is not None:
-                    between()
-                if tail_fn is not None:
-                    tail_fn()
+                for eager, fn, _g in self.stages:
+                    if eager is not None:
+                        eager()
+                    if fn is not None:
+                        fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         with torch.no_grad():
@@ -53,10 +60,16 @@ class GraphedStep:
         n0 = ops.LAUNCHES[0]
         with torch.cuda.graph(self.graph):
             out = step_fn(*self.static_inputs)
-        if tail_fn is not None:
-            self.tail_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.tail_graph):
-                tail_fn()
+        pool = self.graph.pool()
+        captured = []
+        for eager, fn, _g in self.stages:
+            g = None
+            if fn is not None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    fn()
+            captured.append((eager, fn, g))
+        self.stages = captured
         self.launches = ops.LAUNCHES[0] - n0          # cvad ABI calls inside one replay
         self.outputs = out if isinstance(out, tuple) else (out,)
 
@@ -64,10 +77,11 @@ class GraphedStep:
         if self.pre_replay is not None:
             self.pre_replay()
         self.graph.replay()
-        if self.between is not None:
-            self.between()
-        if self.tail_graph is not None:
-            self.tail_graph.replay()
+        for eager, _fn, g in self.stages:
+            if eager is not None:
+                eager()
+            if g is not None:
+                g.replay()
         ops.LAUNCHES[0] += self.launches
 
     # ---- input prefetch: the H2D copy of batch i+1 runs on a copy stream while the graph of batch i executes
@@ -105,20 +119,39 @@ class GraphedStep:
         return self.outputs
 
 
-def graphed_optimizer_step(opt, fwd_bwd, example_inputs, mutated):
+def graphed_optimizer_step(opt, fwd_bwd, example_inputs, mutated, late_backward=None):
     """Capture ``fwd_bwd(*inputs) -> tuple`` (zero_grad + forward + loss + backward) followed by ``opt``'s fused step.
 
-    Single GPU: one graph.  Data parallel (the optimizer carries a gradient all-reduce hook): graph(fwd_bwd) -> eager collective ->
-    graph(fused clip + Adam), because NCCL captured inside a graph stalled an 8-rank run."""
+    Single GPU: one graph.  Data parallel (the optimizer carries a gradient all-reduce hook): the collective stays between graphs,
+    because NCCL captured inside a graph stalled an 8-rank run:
+        graph(fwd_bwd) -> eager all-reduce -> graph(fused clip + Adam).
+    ``late_backward``: an optional second part of the backward (M-A: the backbone's) whose gradients live in the arena range the hook
+    calls "late".  Then the gradients ``fwd_bwd`` produced are reduced asynchronously WHILE the late backward runs:
+        graph(fwd_bwd) -> start all-reduce(early range) -> graph(late_backward) -> all-reduce(late range), wait -> graph(clip + Adam)."""
     import os
 
     opt.sync_lr_to_device()
-    if opt.pre_step_hook is not None and os.environ.get("CVAD_NCCL_IN_GRAPH", "0") != "1":
+    hook = opt.pre_step_hook
+    if hook is not None and os.environ.get("CVAD_NCCL_IN_GRAPH", "0") != "1":
+        overlap = getattr(hook, "__self__", None)
+        if late_backward is not None and overlap is not None and hasattr(overlap, "start_early") and os.environ.get("CVAD_ALLREDUCE_OVERLAP", "1") != "0":
+            return GraphedStep(fwd_bwd, example_inputs, mutated, pre_replay=opt.sync_lr_to_device,
+                               stages=[(lambda: overlap.start_early(opt.arena), late_backward),
+                                       (lambda: overlap.finish_late(opt.arena), opt.step_local)])
+        if late_backward is not None:
+            def both(*inputs):
+                out = fwd_bwd(*inputs)
+                late_backward()
+                return out
+            return GraphedStep(both, example_inputs, mutated, pre_replay=opt.sync_lr_to_device,
+                               between=lambda: hook(opt.arena), tail_fn=opt.step_local)
         return GraphedStep(fwd_bwd, example_inputs, mutated, pre_replay=opt.sync_lr_to_device,
-                           between=lambda: opt.pre_step_hook(opt.arena), tail_fn=opt.step_local)
+                           between=lambda: hook(opt.arena), tail_fn=opt.step_local)
 
     def step(*inputs):
         out = fwd_bwd(*inputs)
+        if late_backward is not None:
+            late_backward()
         opt.step()
         return out
     return GraphedStep(step, example_inputs, mutated, pre_replay=opt.sync_lr_to_device)

@@ -27,7 +27,33 @@ class DataParallel:
     def attach(self, optimizer):
         optimizer.pre_step_hook = self.all_reduce_grads
         optimizer.grad_scale = 1.0 / self.world
+        self._early_work = None
         return optimizer
+
+    # -- overlapped exchange (graphs.graphed_optimizer_step): the gradient arena is [header | late range | early range]; "early" = the
+    # tensors whose gradients are complete first (M-A: everything behind the backbone -- detector, tail, direct classifier: 26 of the
+    # 31 MB), "late" = the rest plus the header flags.  The early bucket is reduced on NCCL's stream while the late backward still runs.
+    def set_split(self, early_offset: int):
+        """Arena element offset where the early range starts (a multiple of the arena block)."""
+        self.early_offset = int(early_offset)
+
+    def start_early(self, arena):
+        if self.world == 1:
+            return
+        off = getattr(self, "early_offset", 0)
+        if 0 < off < arena.g.numel():
+            self._early_work = dist.all_reduce(arena.g[off:], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish_late(self, arena):
+        if self.world == 1:
+            return
+        off = getattr(self, "early_offset", 0)
+        if self._early_work is None:          # no split configured: one collective over everything
+            dist.all_reduce(arena.g, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        dist.all_reduce(arena.g[:off], op=dist.ReduceOp.SUM, group=self.group)
+        self._early_work.wait()
+        self._early_work = None
 
     def all_reduce_grads(self, arena):
         if self.world == 1:

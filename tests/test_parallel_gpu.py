@@ -1,0 +1,114 @@
+"""Data-parallel M-A training on two GPUs (NCCL): the overlapped, two-bucket gradient exchange (tail gradients reduced while the backbone's
+backward runs, graphs.graphed_optimizer_step) against (a) the sum of the ranks' locally computed gradients and (b) the single-collective
+exchange between two graphs.  Skipped on a single-GPU box; run with ``gpurun --gpus 2``."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    try:
+        for p in (ROOT, os.path.join(ROOT, "tests")):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        import torch.distributed as dist
+        import synth
+        from test_oracle_golden import ma_synth_state
+        from cvad_b200.ma import CausalAnomalyDetector, MATrainer
+        from cvad_b200.noise import FixedNoise
+        from cvad_b200.parallel import DataParallel, init_from_env
+        init_from_env()
+        dev = torch.device(f"cuda:{rank}")
+        torch.cuda.set_device(dev)
+        B, T, H, W = 2, 3, 64, 96
+        x = synth.ma_clips(B, T, H, W, 900 + rank, wide=False).to(dev)
+        y = torch.tensor([rank, 1 - rank], device=dev)
+
+        def noise():
+            k = {"det0": synth.keep_mask((B, T, 512), 0.3, 11 + rank), "det1": synth.keep_mask((B, T, 256), 0.2, 12 + rank),
+                 "scorer0": synth.keep_mask((B, 64), 0.2, 13 + rank), "cls0": synth.keep_mask((B, 512), 0.3, 14 + rank),
+                 "cls1": synth.keep_mask((B, 256), 0.2, 15 + rank)}
+            return FixedNoise({"eps": torch.randn(B, 5, 6, generator=synth.gen(16 + rank)), **k})
+
+        def trainer(dp):
+            m = CausalAnomalyDetector()
+            m.load_state_dict(ma_synth_state(4, True), strict=True)
+            tr = MATrainer(m, dev, precision="bf16", dp=dp)
+            tr.model.train()
+            tr.model.noise = noise()
+            return tr
+
+        # (a) local gradients, summed by hand
+        t0 = trainer(None)
+        t0.forward_backward(x, y)
+        gsum = t0.optimizer.arena.g.clone()
+        dist.all_reduce(gsum)
+        ok, msg = True, []
+        results = {}
+        for mode in ("1", "0"):
+            os.environ["CVAD_ALLREDUCE_OVERLAP"] = mode
+            dp = DataParallel()
+            tr = trainer(dp)
+            dp.broadcast_parameters(tr.optimizer.arena, model=tr.model)
+            gs = tr.graphed_train_step(x, y)
+            assert len(gs.stages) == (2 if mode == "1" else 1), len(gs.stages)
+            comp = gs(x, y)[0]
+            torch.cuda.synchronize()
+            g = tr.optimizer.arena.g
+            err = float((g - gsum).abs().max() / gsum.abs().max())
+            if err > 1e-4:          # bf16 backbone + atomics: the two passes agree to round-off, not bitwise
+                ok = False
+                msg.append(f"mode {mode}: reduced gradient differs from the sum of local gradients by {err:.2e}")
+            for _ in range(2):
+                gs(x, y)
+            torch.cuda.synchronize()
+            p = tr.optimizer.arena.p.clone()
+            ref = p.clone()
+            dist.broadcast(ref, src=0)
+            if not torch.equal(p, ref):
+                ok = False
+                msg.append(f"mode {mode}: parameters differ across ranks after 3 steps")
+            results[mode] = (p, float(comp[0]))
+            del gs
+        d = float((results["1"][0] - results["0"][0]).abs().max())
+        if d > 1e-4:
+            ok = False
+            msg.append(f"overlapped vs single-collective exchange: parameters differ by {d:.2e} after 3 steps")
+        q.put((rank, ok, "; ".join(msg)))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+        raise e
+
+
+def test_overlapped_two_bucket_allreduce_on_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+    assert all(r[1] for r in res), res
