@@ -43,7 +43,8 @@ def _worker(rank, world, port, q):
             k = {"det0": synth.keep_mask((B, T, 512), 0.3, 11 + rank), "det1": synth.keep_mask((B, T, 256), 0.2, 12 + rank),
                  "scorer0": synth.keep_mask((B, 64), 0.2, 13 + rank), "cls0": synth.keep_mask((B, 512), 0.3, 14 + rank),
                  "cls1": synth.keep_mask((B, 256), 0.2, 15 + rank)}
-            return FixedNoise({"eps": torch.randn(B, 5, 6, generator=synth.gen(16 + rank)), **k})
+            vals = {"eps": torch.randn(B, 5, 6, generator=synth.gen(16 + rank)), **k}
+            return FixedNoise({name: t.to(dev) for name, t in vals.items()})      # on the device: the step is captured into CUDA graphs
 
         def trainer(dp):
             m = CausalAnomalyDetector()
