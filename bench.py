@@ -758,6 +758,11 @@ def run_ours(args):
     from cvad_b200.parallel import DataParallel, init_from_env
 
     trace("imports done")
+    # NCCL writes its version banner to the process's stdout when the first communicator is created (the image sets NCCL_DEBUG=VERSION for
+    # child processes): stdout must carry exactly one JSON line, so file descriptor 1 points at stderr until that line is printed
+    saved_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
     rank, local, world = init_from_env()
     trace(f"process group up (world {world})")
     dev = torch.device(f"cuda:{local}")
@@ -769,6 +774,8 @@ def run_ours(args):
             steps, warm = (2, 1) if args.workload == "ma_train" else (10, 2)
             rate, dt, cores, kind, sample = cpu_reference(args.workload, args.batch, steps, warm)
             line["cpu_baseline"] = {"value": rate, "unit": line["unit"], "cores": cores, "kind": kind, "sample": sample}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         # orderly teardown (the captured graphs are gone by now): every rank drains its GPU, meets at a barrier, then drops the group

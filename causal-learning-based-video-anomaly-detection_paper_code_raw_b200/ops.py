@@ -230,6 +230,9 @@ def _sgemm(M, N, K, A, lda, a_k, B, ldb, b_k, C, ldc, bias=None, act=ACT_NONE, m
           float(mask_scale), int(accumulate), int(splits), _ptr(gate), _st())
 
 
+TF32X3 = os.environ.get("CVAD_TF32X3", "1") != "0"      # tensor-core (3xTF32) forward of the wide projections
+
+
 def _splits_for(M, N, K):
     """Split the reduction over gridDim.z whenever the 64x64 output tiles alone cannot fill the 148 SMs."""
     tiles = ((M + 63) // 64) * ((N + 63) // 64)
@@ -252,7 +255,13 @@ class _LinearAct(torch.autograd.Function):
         splits = _splits_for(M, O, K)
         if mask is not None:
             mask = _f32c(mask).reshape(M, O)
-        if splits > 1:
+        if TF32X3 and K >= 2048 and K % 32 == 0 and O >= 128 and x2.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0:
+            # the two 6144 -> 512 projections: tcgen05 kind::tf32 with the 3xTF32 split (fp32-level accuracy), split-K + atomic reduction
+            y = torch.zeros((M, O), device=x.device, dtype=torch.float32)
+            _call("cvad_linear_fwd_tf32x3", _ptr(x2), _ptr(weight), _ptr(y), M, O, K, _st())
+            if bias is not None or act != ACT_NONE or mask is not None:
+                _call("cvad_bias_act_mask_f32", _ptr(y), M, O, _ptr(bias), act, _ptr(mask), float(mask_scale), _st())
+        elif splits > 1:
             y = torch.zeros((M, O), device=x.device, dtype=torch.float32)
             _sgemm(M, O, K, x2, K, True, weight, K, True, y, O, splits=splits)
             if bias is not None or act != ACT_NONE or mask is not None:

@@ -297,6 +297,12 @@ int cvad_mlp_chain_bwd_f32(const float* dy, long long rows, int n_layers, const 
                            const void* const* masks, const float* mask_scales, const void* const* saves, void* const* dzs, float* dx,
                            void* stream);
 
+/* ---- 6144 -> 512 projections on the tensor cores (gemm_tf32x3_tc.cu): y (M,N) += x (M,K) @ w (N,K)^T with TMA-fed tcgen05 kind::tf32 MMAs and
+ * the 3xTF32 operand split (hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator): fp32-level accuracy (~1e-6) on the tensor pipe.  Replaces
+ * cvad_sgemm_f32 for the forward of cad:167 (detector, M = B*T) and cad:526 (direct classifier, M = B).  y must be zero on entry (split-K
+ * partial sums are reduced atomically); K % 32 == 0; x, w 16-byte aligned; rows beyond M / N are handled by TMA zero fill. */
+int cvad_linear_fwd_tf32x3(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,3 +327,20 @@ def test_mlp_chain_fwd_bwd(dev, dims, acts, masked, rows):
     with torch.no_grad():
         y2 = ops.mlp_chain(x.detach(), [(w.detach(), b.detach(), acts[l], keeps[l], 0.3 if keeps[l] is not None else 0.0) for l, (w, b) in enumerate(zip(Ws, bs))])
     assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 512, 6144), (32, 512, 6144), (130, 200, 2048), (1, 128, 4096), (300, 512, 96)])
+def test_linear_fwd_tf32x3_matches_fp32(dev, M, N, K):
+    """tcgen05 kind::tf32 GEMM with the 3xTF32 operand split: fp32-level accuracy (a plain tf32 product would be ~1e-3 off), ragged M / N
+    through TMA zero fill, split-K reduction.  Reference: fp64 matmul of the same fp32 operands."""
+    from cvad_b200.ops import _call, _ptr, _st
+    x = torch.randn(M, K, generator=_g(1)).to(dev)
+    w = (torch.randn(N, K, generator=_g(2)) / K ** 0.5).to(dev)
+    y = torch.zeros(M, N, device=dev)
+    _call("cvad_linear_fwd_tf32x3", _ptr(x), _ptr(w), _ptr(y), M, N, K, _st())
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t()
+    e = rel(y, ref)
+    e32 = rel(x @ w.t(), ref)
+    print(f"[tf32x3] M{M} N{N} K{K}: rel err {e:.2e} (torch fp32 matmul: {e32:.2e})")
+    assert e < 5e-6

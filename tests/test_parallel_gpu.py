@@ -86,8 +86,14 @@ def _worker(rank, world, port, q):
                 msg.append(f"mode {mode}: parameters differ across ranks after 3 steps")
             results[mode] = (p, float(comp[0]))
             del gs
+        # the two exchanges see the same gradients (checked above against the hand-made sum), so they start the same trajectory: equal
+        # first-step loss; after three Adam steps the parameters agree to within what atomics-order round-off in a near-zero gradient
+        # element can do through Adam's normalisation (a few lr), not bitwise
+        if abs(results["1"][1] - results["0"][1]) > 1e-5 * abs(results["0"][1]):
+            ok = False
+            msg.append(f"first-step loss differs between the exchanges: {results['1'][1]} vs {results['0'][1]}")
         d = float((results["1"][0] - results["0"][0]).abs().max())
-        if d > 1e-4:
+        if d > 3 * 2 * 3e-4:
             ok = False
             msg.append(f"overlapped vs single-collective exchange: parameters differ by {d:.2e} after 3 steps")
         q.put((rank, ok, "; ".join(msg)))
