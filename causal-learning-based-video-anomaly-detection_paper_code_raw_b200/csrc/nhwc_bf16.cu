@@ -91,7 +91,7 @@ __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, i
 // Block = 256 threads, two 16-byte vectors per thread and pass (v = tid, tid + 256): every padded row of the backbone
 // (368..448 vectors) is one pass with all loads issued before the first use.  PHASE=1 handles the two column-phase planes
 // (a,0) and (a,1) of one plane row in the same block, so the raw row both of them sample is fetched from HBM once.
-template <int PHASE>
+template <int PHASE, int R>
 __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ act, PadGeo g,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                 const float* __restrict__ gamma, const float* __restrict__ beta) {
@@ -108,52 +108,62 @@ __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloa
   const int items = PHASE ? 2 * g.N * g.Hq : g.N * Hp;          // PHASE: (a, n, i) with both b planes per item
   const int rowlen = (PHASE ? g.Wq : Wp) << g.lg;
   const int span = PHASE ? 2 * rowlen : rowlen;
-  for (int r = blockIdx.x; r < items; r += gridDim.x) {
-    int n, hp, a = 0;
-    long long row0, row1 = 0;                                      // first vector of the output row(s)
-    if (PHASE) {
-      const int i = r % g.Hq;
-      const int t = r / g.Hq;
-      n = t % g.N;
-      a = t / g.N;
-      hp = 2 * (i - 1) + a;
-      row0 = ((((long long)(2 * a) * g.N + n) * g.Hq) + i) * rowlen;
-      row1 = ((((long long)(2 * a + 1) * g.N + n) * g.Hq) + i) * rowlen;
-    } else {
-      hp = r % Hp;
-      n = r / Hp;
-      row0 = (long long)r * rowlen;
-    }
-    const bool row_ok = hp >= 1 && hp <= g.H;
+  // R items (rows) per iteration: all their loads (2 per thread and row) are issued before the first is consumed, which keeps
+  // 2R x 16 bytes per thread in flight -- with one row per iteration the kernel ran at 0.6 of the copy bandwidth, latency-bound
+  for (int r0 = blockIdx.x * R; r0 < items; r0 += gridDim.x * R) {
     for (int v0 = threadIdx.x; v0 < span; v0 += 512) {
-      uint4 x[2];
-      bool in[2], ok[2];
-      long long dst[2];
+      uint4 x[R][2];
+      bool in[R][2], ok[R][2];
+      long long dst[R][2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int v = v0 + u * 256;
-        in[u] = v < span;
-        const int b = PHASE && v >= rowlen ? 1 : 0;
-        const int vv = v - b * rowlen;
-        const int j = vv >> g.lg;
-        const int wp = PHASE ? 2 * (j - 1) + b : j;
-        ok[u] = in[u] && row_ok && wp >= 1 && wp <= g.W;
-        dst[u] = (b ? row1 : row0) + vv;
-        if (ok[u]) x[u] = __ldg(reinterpret_cast<const uint4*>(raw) + ((plain_row(g, n, hp, wp) << g.lg) + cg));
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (!in[u]) continue;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (ok[u]) {
-          float f[8];
-          unpack8(x[u], f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
-          o = pack8(f);
+      for (int rr = 0; rr < R; ++rr) {
+        const int r = r0 + rr;
+        int n = 0, hp = -1, a = 0;
+        long long row0 = 0, row1 = 0;                              // first vector of the output row(s)
+        if (r < items) {
+          if (PHASE) {
+            const int i = r % g.Hq;
+            const int t = r / g.Hq;
+            n = t % g.N;
+            a = t / g.N;
+            hp = 2 * (i - 1) + a;
+            row0 = ((((long long)(2 * a) * g.N + n) * g.Hq) + i) * rowlen;
+            row1 = ((((long long)(2 * a + 1) * g.N + n) * g.Hq) + i) * rowlen;
+          } else {
+            hp = r % Hp;
+            n = r / Hp;
+            row0 = (long long)r * rowlen;
+          }
         }
-        reinterpret_cast<uint4*>(act)[dst[u]] = o;
+        const bool row_ok = hp >= 1 && hp <= g.H;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int v = v0 + u * 256;
+          in[rr][u] = v < span && r < items;
+          const int b = PHASE && v >= rowlen ? 1 : 0;
+          const int vv = v - b * rowlen;
+          const int j = vv >> g.lg;
+          const int wp = PHASE ? 2 * (j - 1) + b : j;
+          ok[rr][u] = in[rr][u] && row_ok && wp >= 1 && wp <= g.W;
+          dst[rr][u] = (b ? row1 : row0) + vv;
+          if (ok[rr][u]) x[rr][u] = __ldg(reinterpret_cast<const uint4*>(raw) + ((plain_row(g, n, hp, wp) << g.lg) + cg));
+        }
       }
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!in[rr][u]) continue;
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (ok[rr][u]) {
+            float f[8];
+            unpack8(x[rr][u], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaxf(fmaf(f[i], sc[i], sh[i]), 0.f);
+            o = pack8(f);
+          }
+          reinterpret_cast<uint4*>(act)[dst[rr][u]] = o;
+        }
     }
   }
 }
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(256, 4) pad_reduce_kernel(const __nv_bfloat16*
 }
 
 // ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)
-template <int PHASE>
+template <int PHASE, int R>
 __global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
                                                                     __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -295,42 +305,49 @@ __global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_b
   }
   const int Hp = g.H + 2, Wp = g.W + 2;
   const int rows = g.N * Hp, rowlen = Wp << g.lg;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int hp = r % Hp, n = r / Hp;
-    const bool row_ok = hp >= 1 && hp <= g.H;
-    const long long vbase = (long long)r * rowlen;
+  // R rows per iteration, every load (2 tensors x 2 vectors x R rows per thread) issued before the first use
+  for (int r0 = blockIdx.x * R; r0 < rows; r0 += gridDim.x * R) {
     for (int v0 = threadIdx.x; v0 < rowlen; v0 += 512) {
-      uint4 x[2], dd[2];
-      bool in[2], ok[2];
+      uint4 x[R][2], dd[R][2];
+      bool in[R][2], ok[R][2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int v = v0 + u * 256;
-        const int wp = v >> g.lg;
-        in[u] = v < rowlen;
-        ok[u] = in[u] && row_ok && wp >= 1 && wp <= g.W;
-        if (ok[u]) {
-          x[u] = __ldg(reinterpret_cast<const uint4*>(raw) + vbase + v);
-          const long long dv = PHASE ? ((phase_row(g, n, hp, wp) << g.lg) + cg) : vbase + v;
-          dd[u] = __ldg(reinterpret_cast<const uint4*>(dact) + dv);
-        }
-      }
+      for (int rr = 0; rr < R; ++rr) {
+        const int r = r0 + rr;
+        const int hp = r % Hp, n = r / Hp;
+        const bool row_ok = r < rows && hp >= 1 && hp <= g.H;
+        const long long vbase = (long long)r * rowlen;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (!in[u]) continue;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (ok[u]) {
-          float f[8], d[8];
-          unpack8(x[u], f);
-          unpack8(dd[u], d);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float gg = fmaf(f[i], ca[i], cb[i]) > 0.f ? d[i] : 0.f;
-            f[i] = fmaf(-k1[i], f[i], fmaf(ca[i], gg, -k0[i]));
+        for (int u = 0; u < 2; ++u) {
+          const int v = v0 + u * 256;
+          const int wp = v >> g.lg;
+          in[rr][u] = v < rowlen && r < rows;
+          ok[rr][u] = in[rr][u] && row_ok && wp >= 1 && wp <= g.W;
+          if (ok[rr][u]) {
+            x[rr][u] = __ldg(reinterpret_cast<const uint4*>(raw) + vbase + v);
+            const long long dv = PHASE ? ((phase_row(g, n, hp, wp) << g.lg) + cg) : vbase + v;
+            dd[rr][u] = __ldg(reinterpret_cast<const uint4*>(dact) + dv);
           }
-          o = pack8(f);
         }
-        reinterpret_cast<uint4*>(draw)[vbase + v0 + u * 256] = o;
       }
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!in[rr][u]) continue;
+          uint4 o = make_uint4(0, 0, 0, 0);
+          if (ok[rr][u]) {
+            float f[8], d[8];
+            unpack8(x[rr][u], f);
+            unpack8(dd[rr][u], d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float gg = fmaf(f[i], ca[i], cb[i]) > 0.f ? d[i] : 0.f;
+              f[i] = fmaf(-k1[i], f[i], fmaf(ca[i], gg, -k0[i]));
+            }
+            o = pack8(f);
+          }
+          reinterpret_cast<uint4*>(draw)[(long long)(r0 + rr) * rowlen + v0 + u * 256] = o;
+        }
     }
   }
 }
@@ -433,6 +450,26 @@ __global__ void avgpool_pad_bwd_frame_kernel(const float* __restrict__ dout, int
   }
 }
 
+// development knobs for the apply kernels: rows per CTA iteration (1, 2 or 4) and CTAs per SM
+inline int bn_rows_per_iter() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVAD_BN_ROWS");
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2 && v != 4) v = 2;
+  }
+  return v;
+}
+inline int bn_ctas_per_sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVAD_BN_CTAS");
+    v = e ? atoi(e) : 8;
+    if (v < 1 || v > 32) v = 8;
+  }
+  return v;
+}
+
 inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   if (C % 8 || C > 256 || (C / 8) & (C / 8 - 1) || (long long)N * (H + 2) * (W + 2) * 4 > 0x7fffffffLL) return 1;
   g.N = N; g.H = H; g.W = W; g.C = C;
@@ -442,6 +479,22 @@ inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   while ((8 << g.lg) < C) ++g.lg;
   fast_div_init((unsigned)W, g.mulW, g.shrW);
   fast_div_init((unsigned)H, g.mulH, g.shrH);
+  return 0;
+}
+
+int launch_bwd_apply(const __nv_bfloat16* r, const __nv_bfloat16* d, __nv_bfloat16* draw, const PadGeo& g, int N, int H, int W, int phase_in,
+                     const float* mean, const float* invstd, const float* gamma, const float* beta, const double* ws, int training,
+                     cudaStream_t st) {
+  const int rows = N * (H + 2);
+  const int R = bn_rows_per_iter();
+  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
+  const int ab = want < cap ? want : cap;
+  const double count = (double)N * H * W;
+#define CVAD_BAPPLY(PH, RR) pad_bn_relu_bwd_apply_kernel<PH, RR><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training)
+  if (phase_in) { if (R == 1) CVAD_BAPPLY(1, 1); else if (R == 2) CVAD_BAPPLY(1, 2); else CVAD_BAPPLY(1, 4); }
+  else { if (R == 1) CVAD_BAPPLY(0, 1); else if (R == 2) CVAD_BAPPLY(0, 2); else CVAD_BAPPLY(0, 4); }
+#undef CVAD_BAPPLY
+  CVAD_LAUNCH_CHECK();
   return 0;
 }
 
@@ -478,11 +531,15 @@ CVAD_API int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int 
   if (make_geo(g, N, H, W, C, phase_out)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
-  const int blocks = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
-  if (phase_out)
-    pad_bn_apply_relu_kernel<1><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
-  else
-    pad_bn_apply_relu_kernel<0><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, mean, invstd, gamma, beta);
+  const int R = bn_rows_per_iter();
+  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
+  const int blocks = want < cap ? want : cap;
+  const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
+  __nv_bfloat16* a = (__nv_bfloat16*)act;
+#define CVAD_APPLY(PH, RR) pad_bn_apply_relu_kernel<PH, RR><<<blocks, 256, 0, st>>>(r, a, g, mean, invstd, gamma, beta)
+  if (phase_out) { if (R == 1) CVAD_APPLY(1, 1); else if (R == 2) CVAD_APPLY(1, 2); else CVAD_APPLY(1, 4); }
+  else { if (R == 1) CVAD_APPLY(0, 1); else if (R == 2) CVAD_APPLY(0, 2); else CVAD_APPLY(0, 4); }
+#undef CVAD_APPLY
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -501,15 +558,8 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
     pad_reduce_kernel<true, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
   CVAD_LAUNCH_CHECK();
   if (draw) {
-    const int rows = N * (H + 2);
-    const int ab = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
-    if (phase_in)
-      pad_bn_relu_bwd_apply_kernel<1><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
-                                                          training);
-    else
-      pad_bn_relu_bwd_apply_kernel<0><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W,
-                                                          training);
-    CVAD_LAUNCH_CHECK();
+    int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, st);
+    if (e) return e;
   }
   bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
   CVAD_LAUNCH_CHECK();
@@ -525,13 +575,8 @@ CVAD_API int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, 
   if (make_geo(g, N, H, W, C, phase_in) || !draw) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  const int rows = N * (H + 2);
-  const int ab = rows < 8 * cvad_num_sms() ? rows : 8 * cvad_num_sms();
-  if (phase_in)
-    pad_bn_relu_bwd_apply_kernel<1><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W, training);
-  else
-    pad_bn_relu_bwd_apply_kernel<0><<<ab, 256, 0, st>>>(r, d, (__nv_bfloat16*)draw, g, mean, invstd, gamma, beta, ws, (double)N * H * W, training);
-  CVAD_LAUNCH_CHECK();
+  int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, st);
+  if (e) return e;
   bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
   CVAD_LAUNCH_CHECK();
   return 0;
