@@ -65,17 +65,29 @@ __global__ void bn_eval_prepare_kernel(int C, float eps, const float* __restrict
   }
 }
 
-// y = act((x - mean) * invstd * gamma + beta); grid.x strides over N*C planes
+// y = act((x - mean) * invstd * gamma + beta).  grid.x strides over the N*C planes, grid.y splits a plane into chunks (a few long planes --
+// M-C at T = 256 has 32 planes of 4 MB -- must still fill the machine); 16-byte accesses when the plane size and pointers allow.
 __global__ void bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int C, long long S,
                                 const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, int act) {
+                                const float* __restrict__ beta, int act, int vec4) {
   for (long long p = blockIdx.x; p < planes; p += gridDim.x) {
     int c = (int)(p % C);
     float sc = invstd[c] * gamma[c];
     float sh = beta[c] - mean[c] * sc;
     const float* xp = x + p * S;
     float* yp = y + p * S;
-    for (long long i = threadIdx.x; i < S; i += blockDim.x) yp[i] = cvad_act(fmaf(xp[i], sc, sh), act);
+    if (vec4) {
+      const long long S4 = S >> 2;
+      for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < S4; i += (long long)gridDim.y * blockDim.x) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(xp) + i);
+        v.x = cvad_act(fmaf(v.x, sc, sh), act); v.y = cvad_act(fmaf(v.y, sc, sh), act);
+        v.z = cvad_act(fmaf(v.z, sc, sh), act); v.w = cvad_act(fmaf(v.w, sc, sh), act);
+        reinterpret_cast<float4*>(yp)[i] = v;
+      }
+    } else {
+      for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.y * blockDim.x)
+        yp[i] = cvad_act(fmaf(xp[i], sc, sh), act);
+    }
   }
 }
 
@@ -135,7 +147,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
     const float* xp = x + p * S;
     const float* gp = dy + p * S;
     float* dp = dx + p * S;
-    for (long long i = threadIdx.x; i < S; i += blockDim.x) {
+    for (long long i = blockIdx.y * (long long)blockDim.x + threadIdx.x; i < S; i += (long long)gridDim.y * blockDim.x) {
       float xh = (xp[i] - mu) * is;
       float pre = fmaf(xh, ga, be);
       const float g = gp[i] * act_grad_from_pre(pre, act);
@@ -231,6 +243,34 @@ __global__ void adaptive_avgpool_fwd_kernel(const float* __restrict__ x, float* 
   }
 }
 
+// the same with one CTA per output bin: large bins (M-C's global pooling over T/4 x 8 x 8 = up to 4096 elements, mc3:56) as a block reduction
+__global__ void __launch_bounds__(256) adaptive_avgpool_fwd_bin_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int D,
+                                                                       int H, int W, int OD, int OH, int OW) {
+  __shared__ float sh[32];
+  const long long osz = (long long)OD * OH * OW;
+  const long long total = planes * osz;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    long long p = t / osz;
+    int r = (int)(t - p * osz);
+    int ow = r % OW; r /= OW;
+    int oh = r % OH;
+    int od = r / OH;
+    const int d0 = bin_start(od, D, OD), d1 = bin_end(od, D, OD);
+    const int h0 = bin_start(oh, H, OH), h1 = bin_end(oh, H, OH);
+    const int w0 = bin_start(ow, W, OW), w1 = bin_end(ow, W, OW);
+    const int bw = w1 - w0, bh = h1 - h0, n = (d1 - d0) * bh * bw;
+    const float* xp = x + p * (long long)D * H * W;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = i % bw, q = i / bw, b = q % bh, a = q / bh;
+      s += __ldg(xp + ((long long)(d0 + a) * H + (h0 + b)) * W + (w0 + c));
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) y[t] = s / (float)n;
+    __syncthreads();
+  }
+}
+
 // gather form: each input element sums the (possibly overlapping) bins that contain it
 __global__ void adaptive_avgpool_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long planes, int D, int H, int W,
                                             int OD, int OH, int OW) {
@@ -298,6 +338,14 @@ __global__ void channel_sum_add_kernel(const float* __restrict__ x, int N, int C
   if (threadIdx.x == 0 && beg < end) atomicAdd(out + c, s);
 }
 
+// chunks per plane (grid.y) so that planes x chunks CTAs cover the machine ~8 times, each chunk at least `min_elems` elements
+inline int plane_chunks(int plane_blocks, long long S, int min_elems) {
+  long long want = (8LL * cvad_num_sms() + plane_blocks - 1) / plane_blocks;
+  long long most = (S + min_elems - 1) / min_elems;
+  long long c = want < most ? want : most;
+  return (int)(c < 1 ? 1 : (c > 65535 ? 65535 : c));
+}
+
 inline int ew_blocks(long long n) {
   long long b = (n + 255) / 256;
   long long cap = 16LL * cvad_num_sms();
@@ -335,7 +383,9 @@ CVAD_API int cvad_bn_apply_f32(const float* x, float* y, int N, int C, long long
   long long planes = (long long)N * C;
   int blocks = (int)(planes < 8LL * cvad_num_sms() ? planes : 8LL * cvad_num_sms());
   int threads = S >= 1024 ? 256 : (S >= 128 ? 128 : 32);
-  bn_apply_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(x, y, planes, C, S, mean, invstd, gamma, beta, act);
+  const int vec4 = (S % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+  bn_apply_kernel<<<dim3(blocks, plane_chunks(blocks, S, threads * (vec4 ? 16 : 4))), threads, 0, (cudaStream_t)stream>>>(
+      x, y, planes, C, S, mean, invstd, gamma, beta, act, vec4);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -355,10 +405,36 @@ CVAD_API int cvad_bn_bwd_f32(const float* dy, const float* x, float* dx, int N, 
     long long planes = (long long)N * C;
     int blocks = (int)(planes < 8LL * cvad_num_sms() ? planes : 8LL * cvad_num_sms());
     int threads = S >= 1024 ? 256 : (S >= 128 ? 128 : 32);
-    bn_bwd_apply_kernel<<<blocks, threads, 0, st>>>(dy, x, dx, planes, C, S, mean, invstd, gamma, beta, act, ws, (double)total, training);
+    bn_bwd_apply_kernel<<<dim3(blocks, plane_chunks(blocks, S, threads * 4)), threads, 0, st>>>(dy, x, dx, planes, C, S, mean, invstd, gamma, beta,
+                                                                                               act, ws, (double)total, training);
     CVAD_LAUNCH_CHECK();
   }
   bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+// Eval-mode BatchNorm folded into the convolution in front of it: w'[co][...] = w[co][...] * s, b' = (b - running_mean) * s + beta
+// with s = gamma / sqrt(running_var + eps), so that conv + BN (+ ReLU in the convolution's epilogue) is ONE launch at inference.
+__global__ void bn_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ rm, const float* __restrict__ rv, float eps, int Cout,
+                                    int per_out, float* __restrict__ w_out, float* __restrict__ b_out) {
+  const int total = Cout * per_out;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i / per_out;
+    const float sc = gamma[co] * (1.f / sqrtf(rv[co] + eps));
+    w_out[i] = w[i] * sc;
+    if (i == co * per_out) b_out[co] = ((b ? b[co] : 0.f) - rm[co]) * sc + beta[co];
+  }
+}
+
+CVAD_API int cvad_bn_fold_conv_f32(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
+                                   const float* running_var, float eps, int Cout, int per_out, float* w_out, float* b_out, void* stream) {
+  if (Cout <= 0 || per_out <= 0) return (int)cudaErrorInvalidValue;
+  const int total = Cout * per_out;
+  bn_fold_conv_kernel<<<(total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024, 256, 0, (cudaStream_t)stream>>>(w, b, gamma, beta, running_mean,
+                                                                                                              running_var, eps, Cout, per_out,
+                                                                                                              w_out, b_out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -399,7 +475,12 @@ CVAD_API int cvad_adaptive_avgpool_fwd_f32(const float* x, float* y, long long p
                                            void* stream) {
   long long total = planes * OD * OH * OW;
   if (total <= 0) return 0;
-  adaptive_avgpool_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, y, planes, D, H, W, OD, OH, OW);
+  const long long bin = ((long long)(D + OD - 1) / OD) * ((H + OH - 1) / OH) * ((W + OW - 1) / OW);
+  if (bin >= 256 && total <= 16LL * cvad_num_sms() * 8)      // few, large bins: one CTA per bin
+    adaptive_avgpool_fwd_bin_kernel<<<(unsigned)(total < 16LL * cvad_num_sms() ? total : 16LL * cvad_num_sms()), 256, 0, (cudaStream_t)stream>>>(
+        x, y, planes, D, H, W, OD, OH, OW);
+  else
+    adaptive_avgpool_fwd_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, y, planes, D, H, W, OD, OH, OW);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

@@ -56,6 +56,11 @@ class SimpleVideoAnomalyDetector(nn.Module):
         h = x
         for blk, pool in enumerate(_POOLS):
             conv, bn = self.features[4 * blk], self.features[4 * blk + 1]
+            if not (self.training and bn.training) and not torch.is_grad_enabled():
+                # inference: the BatchNorm's running statistics fold into the convolution (one launch for conv + BN + ReLU)
+                wf, bf = ops.bn_fold_conv(conv.weight, conv.bias, bn)
+                h = ops.maxpool(ops.conv_act(h, wf, bf, 1, 1, ACT_RELU), pool, pool, 0)
+                continue
             h = ops.conv_act(h, conv.weight, conv.bias, 1, 1, ACT_NONE)
             h = ops.batchnorm_act(h, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                                   ops.bn_workspace(h.device, bn.num_features), self.training and bn.training, ACT_RELU, bn.eps,

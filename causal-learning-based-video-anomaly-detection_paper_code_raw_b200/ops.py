@@ -224,6 +224,17 @@ def conv_act(x, weight, bias, stride=1, padding=0, act=ACT_NONE):
     return _ConvAct.apply(x, weight, bias, stride, padding, act)
 
 
+def bn_fold_conv(weight, bias, bn):
+    """(w', b') of the convolution that equals conv followed by ``bn`` in eval mode (running statistics)."""
+    _cuda(weight)
+    w = _f32c(weight.detach())
+    wf = torch.empty_like(w)
+    bf = torch.empty(w.shape[0], device=w.device, dtype=torch.float32)
+    _call("cvad_bn_fold_conv_f32", _ptr(w), _ptr(bias), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var), float(bn.eps),
+          w.shape[0], w[0].numel(), _ptr(wf), _ptr(bf), _st())
+    return wf, bf
+
+
 # ------------------------------------------------------------------------------------------------ linear
 def _sgemm(M, N, K, A, lda, a_k, B, ldb, b_k, C, ldc, bias=None, act=ACT_NONE, mask=None, mask_scale=1.0, accumulate=0, splits=1, gate=None):
     _call("cvad_sgemm_f32", M, N, K, _ptr(A), lda, int(a_k), _ptr(B), ldb, int(b_k), _ptr(C), ldc, _ptr(bias), act, _ptr(mask),

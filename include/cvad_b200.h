@@ -303,6 +303,11 @@ int cvad_mlp_chain_bwd_f32(const float* dy, long long rows, int n_layers, const 
  * partial sums are reduced atomically); K % 32 == 0; x, w 16-byte aligned; rows beyond M / N are handled by TMA zero fill. */
 int cvad_linear_fwd_tf32x3(const float* x, const float* w, float* y, int M, int N, int K, void* stream);
 
+/* Eval-mode BatchNorm folded into the preceding convolution (mc3:38-53 at inference): w_out = w * s per output channel,
+ * b_out = (b - running_mean) * s + beta, s = gamma / sqrt(running_var + eps); w (Cout, per_out) contiguous, b may be NULL. */
+int cvad_bn_fold_conv_f32(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
+                          const float* running_var, float eps, int Cout, int per_out, float* w_out, float* b_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
