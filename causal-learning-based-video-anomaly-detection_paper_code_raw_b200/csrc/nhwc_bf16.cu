@@ -58,8 +58,10 @@ __global__ void bn_bwd_params_nhwc_kernel(double* __restrict__ ws, int C, float*
 }
 
 // ------------------------------------------------------------------------------------------------ adaptive average pool
-__device__ __forceinline__ int bstart(int o, int in, int out) { return (int)(((long long)o * in) / out); }
-__device__ __forceinline__ int bend(int o, int in, int out) { return (int)((((long long)(o + 1)) * in + out - 1) / out); }
+// adaptive-pool bin bounds; 32-bit arithmetic (frame dimensions are far below 2^15: the 64-bit divisions these used to be cost the
+// per-frame backward kernel more than its memory traffic)
+__device__ __forceinline__ int bstart(int o, int in, int out) { return (int)(((unsigned)o * (unsigned)in) / (unsigned)out); }
+__device__ __forceinline__ int bend(int o, int in, int out) { return (int)((((unsigned)(o + 1)) * (unsigned)in + (unsigned)out - 1u) / (unsigned)out); }
 
 inline int blocks_for(long long n, int per = 256) {
   long long b = (n + per - 1) / per;
@@ -175,7 +177,7 @@ __device__ unsigned int g_pad_ticket = 0u;
 // per-channel reductions over the INTERIOR of raw.  !BWD: sum x, sum x^2.  BWD: g = dact*(pre>0): sum g, sum g*xhat.
 // dact is plain (PHASE=0) or phase planes (PHASE=1).
 template <bool BWD, int PHASE>
-__global__ void __launch_bounds__(256, 4) pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact, PadGeo g,
+__global__ void __launch_bounds__(256, 3) pad_reduce_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact, PadGeo g,
                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             double* __restrict__ ws) {
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256, 4) pad_reduce_kernel(const __nv_bfloat16*
   const int P = g.N * g.H * g.W;               // < 2^31 (checked by the launcher)
   const int chunk = (P + gridDim.x - 1) / gridDim.x;
   const int p_end = min(P, (int)(blockIdx.x + 1) * chunk);
-  constexpr int U = BWD ? 2 : 4;     // 16-byte loads in flight per thread and tensor (the backward reads two tensors)
+  constexpr int U = 4;               // 16-byte loads in flight per thread and tensor (the backward reads two tensors: 8 loads)
   for (int p0 = blockIdx.x * chunk + slot; p0 < p_end; p0 += U * slots) {
     uint4 xv[U], dv[U];
     bool ok[U];
@@ -551,7 +553,7 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   if (make_geo(g, N, H, W, C, phase_in)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();
+  int blocks = N * H < 3 * cvad_num_sms() ? N * H : 3 * cvad_num_sms();      // one wave (launch bounds: 3 CTAs per SM)
   if (phase_in)
     pad_reduce_kernel<true, 1><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
   else
