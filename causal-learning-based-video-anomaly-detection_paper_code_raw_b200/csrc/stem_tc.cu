@@ -299,6 +299,225 @@ __global__ void __launch_bounds__(384, 1) stem_tf32_kernel(const __grid_constant
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// Pass 2 fused with MaxPool2d(3,2,1) (cad:118,148): the 708 MB bf16 NHWC tensor between the stem and the pool is never written.
+//
+// A work item is a BAND of one frame: SP_P pooled rows = the 2*SP_P + 1 convolution rows 2*SP_P*b - 1 .. 2*SP_P*b + 2*SP_P - 1 (one row
+// of overlap with the next band: 17 % more MMAs than pass 2 alone).  The band's positions are contiguous in the flat X4 index, so the
+// stream machinery is unchanged -- one TMA box per band (it starts at the enclosing 128-byte row; the pixel remainder goes into the
+// MMA descriptors' start address), SP_SUB sub-tiles of 128 positions, the same 8 MMAs each.  The epilogue applies BN + ReLU and parks
+// the band as bf16 [row][column][32] in shared memory instead of HBM; when the band is complete, the eight epilogue warps pool it
+// (values are post-ReLU, so an absent neighbour is a 0) and write the padded-flat rows of the next layer's input, borders included.
+constexpr int SP_P = 3;                       // pooled rows per band
+constexpr int SP_ROWS = 2 * SP_P + 1;         // convolution rows per band
+
+struct PoolGeo {
+  int PH, PW;                 // pooled frame
+  int bands_per_frame;
+  long long n_items;          // N * bands_per_frame
+  int sub;                    // 128-position sub-tiles per band
+  int seg_rows;               // 128-byte rows per stream segment
+  int tile_pitch;             // bf16 elements per parked row (Wo * 32)
+};
+
+__global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant__ CUtensorMap map_x4, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, StemGeo g, PoolGeo pg, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_seg_full[2], bar_seg_empty[2], bar_acc_full[ST_SLOTS], bar_acc_empty[ST_SLOTS];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float s_sc[ST_C], s_sh[ST_C];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t seg_bytes = (uint32_t)pg.seg_rows * 128;
+  const uint32_t s_w = smem_base;                           // 8 KiB of packed weights
+  const uint32_t s_seg = smem_base + ST_W_BYTES;            // 2 stream segments
+  __nv_bfloat16* band = reinterpret_cast<__nv_bfloat16*>(smem_gen + ST_W_BYTES + 2 * seg_bytes);       // [SP_ROWS][Wo][32]
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int sub = pg.sub;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_seg_full[i], 1); mbar_init(&bar_seg_empty[i], 1); }
+    for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+    fence_barrier_init();
+    prefetch_tmap(&map_x4);
+  }
+  if (tid < ST_C) {
+    const float sc = invstd[tid] * gamma[tid];
+    s_sc[tid] = sc;
+    s_sh[tid] = (bias[tid] - mean[tid]) * sc + beta[tid];
+  }
+  for (int i = tid; i < 8 * 2 * ST_C * 4; i += blockDim.x) {       // weights, as in stem_tf32_kernel
+    const int e = i & 3, n = (i >> 2) & 31, c = (i >> 7) & 1, m = i >> 8;
+    const int u = m >> 1, v = 2 * (m & 1) + c, a = e >> 1, b = e & 1;
+    const int kh = 2 * u + a - 1, kw = 2 * v + b - 1;
+    const float val = ((unsigned)kh < (unsigned)ST_K && (unsigned)kw < (unsigned)ST_K) ? w[n * ST_K * ST_K + kh * ST_K + kw] : 0.f;
+    reinterpret_cast<float*>(smem_gen)[i] = val;
+  }
+  if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  // first flat X4 pixel of work item t (may be negative for the first band of the first frame: TMA zero-fills)
+  auto item_start = [&](long long t) -> long long {
+    const long long n = t / pg.bands_per_frame;
+    const int b = (int)(t - n * pg.bands_per_frame);
+    return (n * g.Hq + (2 * SP_P * b - 1)) * (long long)g.Wq;
+  };
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: one box per band
+    uint32_t cnt = 0;
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_empty[st], ((cnt >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        const long long p0 = item_start(t);
+        const long long row = p0 >= 0 ? p0 / 8 : -((-p0 + 7) / 8);          // floor(p0 / 8)
+        mbar_expect_tx(&bar_seg_full[st], seg_bytes);
+        tma_load_2d(s_seg + st * seg_bytes, &map_x4, 0, (int)row, &bar_seg_full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    uint32_t idesc = 0;
+    idesc |= 1u << 4;                 // D = f32
+    idesc |= 2u << 7;                 // A = tf32
+    idesc |= 2u << 10;                // B = tf32
+    idesc |= (uint32_t)(ST_C >> 3) << 17;
+    idesc |= (uint32_t)(128 >> 4) << 24;
+    const uint64_t da_hi = make_smem_desc(0, 16, 128, UMMA_NOSW);
+    const uint64_t db_hi = make_smem_desc(0, 512, 128, UMMA_NOSW);
+    uint32_t cnt = 0, acc_cnt = 0;
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      const long long p0 = item_start(t);
+      const long long row = p0 >= 0 ? p0 / 8 : -((-p0 + 7) / 8);
+      const int off = (int)(p0 - row * 8);                          // 0..7 pixels into the box
+      mbar_wait(&bar_seg_full[st], (cnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t seg = s_seg + st * seg_bytes;
+      for (int s = 0; s < sub; ++s) {
+        const uint32_t use = acc_cnt + s;
+        const int slot = use % ST_SLOTS;
+        mbar_wait(&bar_acc_empty[slot], ((use / ST_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            const uint32_t a_addr = seg + (uint32_t)(off + s * 128 + (m >> 1) * g.Wq + 2 * (m & 1)) * 16;
+            const uint64_t da = da_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+            const uint64_t db = db_hi | (uint64_t)(((s_w + m * 1024) >> 4) & 0x3FFF);
+            tc_mma_tf32(tmem_base + slot * ST_C, da, db, idesc, m != 0);
+          }
+          tc_commit(&bar_acc_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&bar_seg_empty[st]);
+      __syncwarp();
+      acc_cnt += sub;
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue: park the band (BN + ReLU, bf16) in shared memory, then pool it
+    const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
+    const int et = tid - 128;                                       // 0..255 among the epilogue threads
+    uint32_t acc_cnt = 0;
+    const int groups = ST_C / 8;                                    // 16-byte vectors per pixel
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x) {
+      const long long n = t / pg.bands_per_frame;
+      const int b = (int)(t - n * pg.bands_per_frame);
+      const int i0 = 2 * SP_P * b - 1;                              // first convolution row of the band
+      for (int sb = eg; sb < sub; sb += 2) {
+        const uint32_t use = acc_cnt + sb;
+        const int slot = use % ST_SLOTS;
+        mbar_wait(&bar_acc_full[slot], (use / ST_SLOTS) & 1);
+        tc_fence_after();
+        uint32_t a0[16], a1[16];
+        const uint32_t taddr = tmem_base + slot * ST_C + ((uint32_t)(ew * 32) << 16);
+        tmem_ld16(taddr, a0);
+        tmem_ld16(taddr + 16, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_acc_empty[slot]);
+        const int ql = sb * 128 + ew * 32 + lane;                   // position inside the band
+        const int r = ql / g.Wq, j = ql - r * g.Wq;
+        if (r < SP_ROWS && j < g.Wo) {
+          const int i = i0 + r;
+          uint32_t pk[16];
+          if (i >= 0 && i < g.Ho) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), s_sc[2 * c], s_sh[2 * c]), 0.f);
+              const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), s_sc[2 * c + 1], s_sh[2 * c + 1]), 0.f);
+              const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), s_sc[16 + 2 * c], s_sh[16 + 2 * c]), 0.f);
+              const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), s_sc[16 + 2 * c + 1], s_sh[16 + 2 * c + 1]), 0.f);
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
+              pk[c] = *reinterpret_cast<uint32_t*>(&h0);
+              pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) pk[c] = 0u;               // rows outside the frame: post-ReLU zeros never win a max
+          }
+          uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)j * ST_C);
+          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+          o[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+        }
+      }
+      acc_cnt += sub;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band is complete
+      // ---- pool: pooled rows SP_P*b .. SP_P*b + SP_P - 1 (band rows 2k, 2k+1, 2k+2 for the k-th of them), padded-flat output
+      const int rowlen = (pg.PW + 2) * groups;                       // vectors per padded output row
+      for (int v = et; v < SP_P * rowlen; v += 256) {
+        const int k = v / rowlen, vv = v - k * rowlen;
+        const int ph = SP_P * b + k;
+        if (ph >= pg.PH) continue;
+        const int pwp = vv / groups, cg = vv - pwp * groups;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (pwp >= 1 && pwp <= pg.PW) {
+          const int pw = pwp - 1;
+          __nv_bfloat162 best[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) best[i] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const __nv_bfloat16* rowp = band + (size_t)(2 * k + a) * pg.tile_pitch;
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb) {
+              const int ww = 2 * pw - 1 + bb;
+              if ((unsigned)ww >= (unsigned)g.Wo) continue;
+              const uint4 tv = *reinterpret_cast<const uint4*>(rowp + (size_t)ww * ST_C + cg * 8);
+              const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&tv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], tp[i]);
+            }
+          }
+          o = *reinterpret_cast<uint4*>(best);
+        }
+        reinterpret_cast<uint4*>(out)[((n * (pg.PH + 2) + ph + 1) * (long long)rowlen) + vv] = o;
+      }
+      // the frame's top / bottom border rows belong to its first / last band
+      if (b == 0)
+        for (int v = et; v < rowlen; v += 256) reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2)) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
+      if (b == pg.bands_per_frame - 1)
+        for (int v = et; v < rowlen; v += 256)
+          reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2) + pg.PH + 1) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band buffer may be overwritten
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
 // ws holds sum / sum of squares of the RAW accumulator; y = acc + bias: mean_y = mean_acc + b, var_y = var_acc
 __global__ void stem_finalize_kernel(double* __restrict__ ws, const float* __restrict__ bias, double count, float eps, float momentum,
                                      float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
@@ -408,6 +627,44 @@ int stem_launch(int mode, const float* x4, const float* w, const float* bias, co
   return 0;
 }
 
+// pass 2 + max-pool in one kernel; returns cudaErrorNotSupported when a band does not fit (very wide frames): callers fall back
+int stem_pool_launch(const float* x4, const float* w, const float* bias, const StemGeo& g, const float* mean, const float* invstd,
+                     const float* gamma, const float* beta, void* out, cudaStream_t st) {
+  PoolGeo pg;
+  pg.PH = (g.Ho - 1) / 2 + 1;
+  pg.PW = (g.Wo - 1) / 2 + 1;
+  pg.bands_per_frame = (pg.PH + SP_P - 1) / SP_P;
+  pg.n_items = (long long)g.N * pg.bands_per_frame;
+  pg.sub = (SP_ROWS * g.Wq + 127) / 128;
+  const int seg_px = 128 * pg.sub + 3 * g.Wq + 3 + 8;              // + the pixel remainder of the box's 128-byte alignment
+  pg.seg_rows = (seg_px + 7) / 8;
+  pg.tile_pitch = g.Wo * ST_C;
+  const size_t band_bytes = (size_t)SP_ROWS * pg.tile_pitch * sizeof(__nv_bfloat16);
+  const size_t smem = ST_W_BYTES + 2 * (size_t)pg.seg_rows * 128 + band_bytes + 1024;
+  if (pg.seg_rows > 256 || pg.sub > ST_SLOTS || smem > 220 * 1024) return (int)cudaErrorNotSupported;
+  CUtensorMap mx;
+  {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    memset(&mx, 0, sizeof(mx));
+    cuuint64_t dims[2] = {32, (cuuint64_t)((g.np4 + 7) / 8)};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {32, (cuuint32_t)pg.seg_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x4), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  }
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(stem_pool_kernel, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
+  long long grid = cvad_num_sms();
+  if (grid > pg.n_items) grid = pg.n_items;
+  stem_pool_kernel<<<(unsigned)grid, 384, smem, st>>>(mx, w, bias, g, pg, mean, invstd, gamma, beta, (__nv_bfloat16*)out);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace
 
 CVAD_API long long cvad_stem_x4_floats(int N, int H, int W) {
@@ -465,6 +722,13 @@ CVAD_API int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float
   StemGeo g;
   if (stem_geo(g, N, H, W)) return (int)cudaErrorInvalidValue;
   return stem_launch(1, x4, w, bias, g, mean, invstd, gamma, beta, nullptr, y, (cudaStream_t)stream);
+}
+
+CVAD_API int cvad_stem_tf32_bn_relu_maxpool(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean,
+                                            const float* invstd, const float* gamma, const float* beta, void* out, void* stream) {
+  StemGeo g;
+  if (stem_geo(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  return stem_pool_launch(x4, w, bias, g, mean, invstd, gamma, beta, out, (cudaStream_t)stream);
 }
 
 CVAD_API int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream) {

@@ -46,23 +46,30 @@ TIMED_CAPTURE_ONLY = [False]     # True: bracket the named calls only while a CU
 TIMED_SHAPES = [os.environ.get("CVAD_PROFILE_SHAPES", "0") == "1"]
 
 
-def _call(name, *args):
+def _call(name, *args, accept=()):
+    """Invoke one C-ABI entry point; raises on a non-zero status unless it is listed in ``accept`` (then it is returned: e.g. 801 =
+    "this fused variant does not fit, use the unfused calls")."""
     LAUNCHES[0] += 1
-    if (name in TIMED_NAMES or "*" in TIMED_NAMES) and (not TIMED_CAPTURE_ONLY[0] or torch.cuda.is_current_stream_capturing()):
+    timed = (name in TIMED_NAMES or "*" in TIMED_NAMES) and (not TIMED_CAPTURE_ONLY[0] or torch.cuda.is_current_stream_capturing())
+    if timed:
         # inside a capture the events become event-record nodes of the graph ("external" events): every replay re-records
         # them, so elapsed_time() measures the call as it runs inside the replayed step
         ext = torch.cuda.is_current_stream_capturing()
         s = torch.cuda.Event(enable_timing=True, external=ext)
         e = torch.cuda.Event(enable_timing=True, external=ext)
         s.record()
-        check(getattr(L(), name)(*args), name)
+    status = getattr(L(), name)(*args)
+    if status in accept and status != 0:
+        LAUNCHES[0] -= 1
+        return status
+    check(status, name)
+    if timed:
         e.record()
         key = name
         if TIMED_SHAPES[0] and name == "cvad_sgemm_f32":        # profiling detail: one row per GEMM shape
             key = f"{name}[M{args[0]} N{args[1]} K{args[2]} splits{args[16]}{' gated' if args[17] else ''}]"
         TIMED.setdefault(key, []).append((s, e))
-        return
-    check(getattr(L(), name)(*args), name)
+    return 0
 
 
 class _ParamGradOverlap:

@@ -38,6 +38,7 @@ def _wgrad_scratch(device, cin, cout):
     return buf
 
 
+STEM_FUSED_POOL = os.environ.get("CVAD_STEM_FUSED_POOL", "1") != "0"   # stem pass 2 + max-pool as one kernel
 FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm batch statistics from the convolution epilogue
 # weight-gradient GEMMs on a side stream: wgrad_i needs only draw_i and a_{i-1}, so it can run beside the HBM-bound BatchNorm backward of
 # the next layer down instead of in front of it (a parallel branch of the captured step graph)
@@ -119,12 +120,19 @@ class _BackboneBF16(torch.autograd.Function):
                   float(bn1.momentum), _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
         else:
             _call("cvad_bn_eval_prepare_f32", C1, float(bn1.eps), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(mean), _ptr(invstd), st)
-        y1 = torch.empty((N, H1, W1, C1), device=dev, dtype=BF16)
-        _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
-              _ptr(y1), st)
         h, w = out_hw(H1, W1, 2)
         a = torch.empty(act_shape(N, h, w, C1, False), device=dev, dtype=BF16)
-        _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
+        fused = 801
+        if STEM_FUSED_POOL:
+            # pass 2 and MaxPool(3,2,1) in one kernel: the 708 MB tensor between them stays in shared memory (801 = a band does not fit)
+            fused = _call("cvad_stem_tf32_bn_relu_maxpool", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight),
+                          _ptr(bn1.bias), _ptr(a), st, accept=(801,))
+        y1 = None
+        if fused == 801:
+            y1 = torch.empty((N, H1, W1, C1), device=dev, dtype=BF16)
+            _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
+                  _ptr(y1), st)
+            _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
         del y1, x4, x
         cur.wait_stream(side)
         saved = []

@@ -244,6 +244,11 @@ int cvad_stem_tf32_stats(const float* x4, const float* w, const float* bias, int
                          float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
 int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean, const float* invstd,
                            const float* gamma, const float* beta, void* y, void* stream);
+/* Pass 2 and the max-pool as ONE kernel: relu(bn1(conv)) is pooled out of shared memory, the (N,Ho,Wo,32) tensor between them is never
+ * written; out = padded-flat (N,PH+2,PW+2,32) bf16 with its zero border.  Returns cudaErrorNotSupported (801) when a band of a very wide
+ * frame does not fit in shared memory: use the two calls above / below instead. */
+int cvad_stem_tf32_bn_relu_maxpool(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, void* out, void* stream);
 int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream);
 
 /* ---- M-D: conv autoencoder + LSTM + memory bank (md_kernels.cu), causal_anomaly_detection1.py --------------------------------

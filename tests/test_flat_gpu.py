@@ -245,7 +245,7 @@ def test_pad_avgpool(dev):
     assert rel(tc.from_padded(dxp, H, W), gxr) < 1e-2
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 37, 53), (3, 240, 360), (1, 16, 20), (5, 64, 64)])
+@pytest.mark.parametrize("N,H,W", [(2, 37, 53), (3, 240, 360), (1, 16, 20), (5, 64, 64), (40, 240, 360), (2, 50, 36)])
 @pytest.mark.parametrize("training", [True, False])
 def test_stem_tf32(dev, N, H, W, training):
     """conv 7x7 s2 p3 1->32 + bn1 (+ running statistics) + relu + maxpool(3,2,1), tf32 tensor-core passes vs fp32 torch."""
@@ -282,3 +282,10 @@ def test_stem_tf32(dev, N, H, W, training):
     e = rel(a0.float(), tc.to_padded(ref).float())
     print(f"[stem] N={N} {H}x{W} training={training}: rel err {e:.2e}")
     assert e < 1e-2
+    # pass 2 + max-pool as ONE kernel (bands pooled out of shared memory): bit-identical to the two kernels, zero border included
+    a1 = torch.full((N, PH + 2, PW + 2, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    status = _call("cvad_stem_tf32_bn_relu_maxpool", _ptr(x), _ptr(w), _ptr(b), N, H, W, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), _ptr(a1), _st(),
+                   accept=(801,))
+    torch.cuda.synchronize()
+    assert status == 0
+    assert torch.equal(a0, a1)
