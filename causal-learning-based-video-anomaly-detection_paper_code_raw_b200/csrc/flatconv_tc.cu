@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
     uint32_t acc_cnt = 0;
     int cur_nb = -1;
+    float rbias[N <= 64 ? N : 1];
     float st_s[N / 16], st_q[N / 16];          // fused statistics: this lane's column of every 16-column chunk, over all its tiles
 #pragma unroll
     for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
@@ -341,6 +342,10 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         cur_nb = nb;
+        if (N <= 64) {                          // narrow layers: the bias lives in registers (the MMAs of these layers are bound by the
+#pragma unroll                                  // shared-memory operand stream; N broadcast loads per thread and sub-tile compete with it)
+          for (int i = 0; i < (N <= 64 ? N : 1); ++i) rbias[i] = s_bias[i];
+        }
       }
       for (int s = eg; s < sub; s += 2) {
         const uint32_t use = acc_cnt + s;
@@ -388,11 +393,21 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
           uint32_t pk[8];
+          if (bias) {                         // (uniform) the data-gradient has none: no shared-memory reads beside the MMAs' operand stream
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            for (int i = 0; i < 8; ++i) {
+              const float b0 = N <= 64 ? rbias[(c0 + 2 * i) % (N <= 64 ? N : 1)] : s_bias[c0 + 2 * i];
+              const float b1 = N <= 64 ? rbias[(c0 + 2 * i + 1) % (N <= 64 ? N : 1)] : s_bias[c0 + 2 * i + 1];
+              const float a = __uint_as_float(v[2 * i]) + b0, b = __uint_as_float(v[2 * i + 1]) + b1;
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
           }
           if (q < p.rows) {
             *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

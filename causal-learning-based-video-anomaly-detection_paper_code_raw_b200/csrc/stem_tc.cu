@@ -225,11 +225,11 @@ __global__ void __launch_bounds__(384, 1) stem_tf32_kernel(const __grid_constant
     // ---------------------------------------------------------------- epilogue: thread <-> TMEM lane (row) 32*(warp-4)+lane
     // two groups of four warps (warps 4-7 and 8-11) take alternate sub-tiles; warp w reads TMEM lanes 32*(w%4)..
     const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
+    // MODE 0: s / q are the per-channel sums.  MODE 1: s / q hold the BatchNorm scale / shift -- in REGISTERS: the MMAs stream their
+    // operands from shared memory at the pipe's limit, and 64 broadcast loads per thread and sub-tile took a third of it away
     float s[ST_C], q[ST_C];
-    if (MODE == 0) {
 #pragma unroll
-      for (int c = 0; c < ST_C; ++c) { s[c] = 0.f; q[c] = 0.f; }
-    }
+    for (int c = 0; c < ST_C; ++c) { s[c] = MODE == 0 ? 0.f : s_sc[c]; q[c] = MODE == 0 ? 0.f : s_sh[c]; }
     const int frame = g.Hq * g.Wq;
     uint32_t acc_cnt = 0;
     for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
@@ -261,10 +261,10 @@ __global__ void __launch_bounds__(384, 1) stem_tf32_kernel(const __grid_constant
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), s_sc[2 * c], s_sh[2 * c]), 0.f);
-              const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), s_sc[2 * c + 1], s_sh[2 * c + 1]), 0.f);
-              const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), s_sc[16 + 2 * c], s_sh[16 + 2 * c]), 0.f);
-              const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), s_sc[16 + 2 * c + 1], s_sh[16 + 2 * c + 1]), 0.f);
+              const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), s[2 * c], q[2 * c]), 0.f);
+              const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), s[2 * c + 1], q[2 * c + 1]), 0.f);
+              const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), s[16 + 2 * c], q[16 + 2 * c]), 0.f);
+              const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), s[16 + 2 * c + 1], q[16 + 2 * c + 1]), 0.f);
               __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
               pk[c] = *reinterpret_cast<uint32_t*>(&h0);
               pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
@@ -429,6 +429,12 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
     const int et = tid - 128;                                       // 0..255 among the epilogue threads
     uint32_t acc_cnt = 0;
     const int groups = ST_C / 8;                                    // 16-byte vectors per pixel
+    // BatchNorm scale / shift in registers (see stem_tf32_kernel): the epilogue's shared-memory traffic competes with the MMAs' operand
+    // stream, so it is kept to the parked band itself -- stored with the pixel's four 16-byte vectors XOR-swizzled by (column >> 1) & 3,
+    // which makes both the parking stores (lane = column, 64-byte pitch) and the pooling reads bank-conflict free
+    float rs[ST_C], rq[ST_C];
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) { rs[c] = s_sc[c]; rq[c] = s_sh[c]; }
     for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x) {
       const long long n = t / pg.bands_per_frame;
       const int b = (int)(t - n * pg.bands_per_frame);
@@ -453,10 +459,10 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
           if (i >= 0 && i < g.Ho) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
-              const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), s_sc[2 * c], s_sh[2 * c]), 0.f);
-              const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), s_sc[2 * c + 1], s_sh[2 * c + 1]), 0.f);
-              const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), s_sc[16 + 2 * c], s_sh[16 + 2 * c]), 0.f);
-              const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), s_sc[16 + 2 * c + 1], s_sh[16 + 2 * c + 1]), 0.f);
+              const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), rs[2 * c], rq[2 * c]), 0.f);
+              const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
+              const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
+              const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
               __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
               pk[c] = *reinterpret_cast<uint32_t*>(&h0);
               pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
@@ -466,10 +472,11 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
             for (int c = 0; c < 16; ++c) pk[c] = 0u;               // rows outside the frame: post-ReLU zeros never win a max
           }
           uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)j * ST_C);
-          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-          o[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+          const int sw = (j >> 1) & 3;
+          o[0 ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1 ^ sw] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          o[2 ^ sw] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+          o[3 ^ sw] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
         }
       }
       acc_cnt += sub;
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
             for (int bb = 0; bb < 3; ++bb) {
               const int ww = 2 * pw - 1 + bb;
               if ((unsigned)ww >= (unsigned)g.Wo) continue;
-              const uint4 tv = *reinterpret_cast<const uint4*>(rowp + (size_t)ww * ST_C + cg * 8);
+              const uint4 tv = *reinterpret_cast<const uint4*>(rowp + (size_t)ww * ST_C + ((cg ^ ((ww >> 1) & 3)) * 8));
               const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&tv);
 #pragma unroll
               for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], tp[i]);
