@@ -10,6 +10,7 @@ Public surface (mirrors the reference's Python seam):
   md.VideoAutoEncoder / md.train_model / md.calculate_anomaly_scores         causal_anomaly_detection1.py
   me.CausalAnomalyDetector / me.predict_anomaly_for_clip / me.score_windows  avenue_training_script_bbox.py
   train.train_improved_minicausal_vad (s2:339-468 driver with real resume, async checkpoints, history JSON)
+  frames.DeviceFrames (uint8 frame cache on the device: cv2-exact bilinear resize, clip / sliding-window gather)
   evaltail (device-side percentile / AUC / evaluation metrics / smoothing: the numpy + sklearn code after the hot path)
   ops (autograd glue over include/cvad_b200.h), arena.FusedAdam, parallel.DataParallel
 There is no CPU fallback: importing the package loads libcvad_b200.so and raises if it is missing.
@@ -18,6 +19,6 @@ from . import _lib
 
 _lib.lib()   # fail loudly when the CUDA extension has not been built
 
-from . import arena, evaltail, graphs, ma, ma_ops, mb, mc, md, me, noise, ops, parallel, tc, train  # noqa: E402,F401
+from . import arena, evaltail, frames, graphs, ma, ma_ops, mb, mc, md, me, noise, ops, parallel, tc, train  # noqa: E402,F401
 
-__all__ = ["arena", "evaltail", "graphs", "ma", "ma_ops", "mb", "mc", "md", "me", "noise", "ops", "parallel", "tc", "train"]
+__all__ = ["arena", "evaltail", "frames", "graphs", "ma", "ma_ops", "mb", "mc", "md", "me", "noise", "ops", "parallel", "tc", "train"]

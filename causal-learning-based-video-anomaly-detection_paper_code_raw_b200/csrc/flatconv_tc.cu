@@ -138,7 +138,9 @@ __device__ __forceinline__ void warp_colsum16_pair(const float (&a)[16], const f
   sum_b = vv + __shfl_xor_sync(0xffffffffu, vv, 1);
 }
 
-template <int ROWB, int N>
+// BW: the instance that also takes the BatchNorm-backward reductions in its epilogue (FcParams::bw_raw).  A separate instantiation: the
+// epilogue of the plain kernels is timing-critical (8 warps against the MMA stream) and must not carry that code.
+template <int ROWB, int N, bool BW>
 __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_tail,
                                                           const __grid_constant__ CUtensorMap map_w, const FcParams p,
                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out) {
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   __shared__ float s_stat[2 * N];          // fused BatchNorm statistics of this CTA's rows (fp32 partial sums, flushed once at the end)
   __shared__ float s_ga[N], s_gb[N];       // fused BatchNorm-backward reductions: the forward's per-channel scale / shift
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) s_stat[i] = 0.f;
-  if (p.bw_raw)
+  if (BW)
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       const float ga = p.bw_gamma[i] * p.bw_invstd[i];
       s_ga[i] = ga;
@@ -329,7 +331,6 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
     uint32_t acc_cnt = 0;
     int cur_nb = -1;
-    float rbias[N <= 64 ? N : 1];
     float st_s[N / 16], st_q[N / 16];          // fused statistics: this lane's column of every 16-column chunk, over all its tiles
 #pragma unroll
     for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
@@ -342,10 +343,6 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         cur_nb = nb;
-        if (N <= 64) {                          // narrow layers: the bias lives in registers (the MMAs of these layers are bound by the
-#pragma unroll                                  // shared-memory operand stream; N broadcast loads per thread and sub-tile compete with it)
-          for (int i = 0; i < (N <= 64 ? N : 1); ++i) rbias[i] = s_bias[i];
-        }
       }
       for (int s = eg; s < sub; s += 2) {
         const uint32_t use = acc_cnt + s;
@@ -356,14 +353,14 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         const uint32_t taddr = tmem_base + slot * N + ((uint32_t)(ew * 32) << 16);
         __nv_bfloat16* orow = out + (p.out_row_base + pl * p.plane_out_stride + q) * (long long)p.ld_out + nb * N;
         bool keep = false;                    // interior pixel (the only ones BatchNorm statistics run over)
-        const bool bw = p.bw_raw != nullptr;
+        constexpr bool bw = BW;
         const __nv_bfloat16* rrow = nullptr;  // bw: this row's pixel in raw
         if (p.st_out && q < p.rows) {
           const int qi = (int)q;
           const int n = fast_div(qi, p.st_mul_img, p.st_shr_img);
           const int r = qi - n * ((p.st_h + 2) * (p.st_w + 2));
           const int i = fast_div(r, p.st_mul_row, p.st_shr_row), j = r - i * (p.st_w + 2);
-          if (!p.bw_planes) {
+          if (!BW || !p.bw_planes) {
             keep = i >= 1 && i <= p.st_h && j >= 1 && j <= p.st_w;
             if (bw) rrow = p.bw_raw + q * (long long)N;
           } else {
@@ -373,16 +370,18 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           }
         }
         constexpr int NCH = N / 16;
-        constexpr int PF = NCH < 4 ? NCH : 4;             // 16-column chunks of raw in flight per thread (a ring of 2*PF 16-byte registers)
+        constexpr int PF = !BW ? 1 : (NCH < 4 ? NCH : 4);  // 16-column chunks of raw in flight per thread (a ring of 2*PF 16-byte registers)
         uint4 rq[PF][2];
         const bool bwk = bw && keep;
+        if (BW) {
 #pragma unroll
-        for (int c = 0; c < PF; ++c) {
-          rq[c][0] = make_uint4(0, 0, 0, 0);
-          rq[c][1] = make_uint4(0, 0, 0, 0);
-          if (bwk) {
-            rq[c][0] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16));
-            rq[c][1] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16 + 8));
+          for (int c = 0; c < PF; ++c) {
+            rq[c][0] = make_uint4(0, 0, 0, 0);
+            rq[c][1] = make_uint4(0, 0, 0, 0);
+            if (bwk) {
+              rq[c][0] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16));
+              rq[c][1] = __ldg(reinterpret_cast<const uint4*>(rrow + c * 16 + 8));
+            }
           }
         }
         mbar_wait(&bar_acc_full[slot], (use / NSLOT) & 1);
@@ -393,21 +392,11 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
           uint32_t pk[8];
-          if (bias) {                         // (uniform) the data-gradient has none: no shared-memory reads beside the MMAs' operand stream
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float b0 = N <= 64 ? rbias[(c0 + 2 * i) % (N <= 64 ? N : 1)] : s_bias[c0 + 2 * i];
-              const float b1 = N <= 64 ? rbias[(c0 + 2 * i + 1) % (N <= 64 ? N : 1)] : s_bias[c0 + 2 * i + 1];
-              const float a = __uint_as_float(v[2 * i]) + b0, b = __uint_as_float(v[2 * i + 1]) + b1;
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
           }
           if (q < p.rows) {
             *reinterpret_cast<uint4*>(orow + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -424,7 +413,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
             warp_colsum16_sq(x, lane, cs, cq);
             st_s[c0 / 16] += cs;
             st_q[c0 / 16] += cq;
-          } else if (p.st_out) {              // BatchNorm-backward sums over g = dact * relu'(bn(raw)) and g * raw, from the bf16 values just stored
+          } else if (BW && p.st_out) {        // BatchNorm-backward sums over g = dact * relu'(bn(raw)) and g * raw, from the bf16 values just stored
             uint4 rv[2] = {rq[(c0 / 16) % PF][0], rq[(c0 / 16) % PF][1]};
             if (c0 / 16 + PF < NCH) {         // refill the ring slot just consumed
               rq[(c0 / 16) % PF][0] = make_uint4(0, 0, 0, 0);
@@ -470,9 +459,9 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
-  if (p.st_out && !p.bw_raw)
+  if (p.st_out && !BW)
     for (int i = tid; i < 2 * N; i += blockDim.x) atomicAdd(p.st_out + i, (double)s_stat[i]);
-  if (p.st_out && p.bw_raw)               // sum g*xhat = invstd * (sum g*x - mean * sum g), combined in fp64 (as pad_reduce_kernel does)
+  if (BW && p.st_out)                     // sum g*xhat = invstd * (sum g*x - mean * sum g), combined in fp64 (as pad_reduce_kernel does)
     for (int i = tid; i < N; i += blockDim.x) {
       const double a0 = (double)s_stat[i], a1 = (double)s_stat[N + i];
       atomicAdd(p.st_out + i, a0);
@@ -491,7 +480,7 @@ bool g_dgrad_one_launch = true;        // cvad_flat_dgrad_mode(0): one launch pe
 // (profiles/r01g_flatconv_L0_ncu_full.md), so it is operand-bound below N = 256: take the widest N the layer allows.
 inline int n_block_of(int nout) { return nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32)); }
 
-template <int ROWB, int N>
+template <int ROWB, int N, bool BW>
 int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk, long long w_rows, FcParams& p, const float* bias,
                     __nv_bfloat16* out, cudaStream_t st) {
   constexpr int TPO = FC_BOX / N;
@@ -531,12 +520,12 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   e = make_tmap_2d(&mw, wpk, w_rows, K, FC_BOX, ROWB / 2, ROWB);
   if (e) return e;
   static size_t configured[CVAD_MAX_DEVICES] = {};
-  const cudaError_t ce = cvad_ensure_dyn_smem(flatconv_kernel<ROWB, N>, smem, configured);
+  const cudaError_t ce = cvad_ensure_dyn_smem(flatconv_kernel<ROWB, N, BW>, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
   const long long MT = 128LL * p.sub;
   const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks * (p.n_planes > 1 ? p.n_planes : 1);
   const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
-  flatconv_kernel<ROWB, N><<<grid, 384, smem, st>>>(ms, mt, mw, p, bias, out);
+  flatconv_kernel<ROWB, N, BW><<<grid, 384, smem, st>>>(ms, mt, mw, p, bias, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -551,16 +540,19 @@ int run_flat(const void* src, long long src_rows, int K, const void* wpk, int No
   p.ld_out = Nout;
   const long long w_rows = 9LL * Nout;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
+#define CVAD_FC(R, NN) (p.bw_raw ? launch_flatconv<R, NN, true>(src, src_rows, K, wpk, w_rows, p, bias, o, st) \
+                                 : launch_flatconv<R, NN, false>(src, src_rows, K, wpk, w_rows, p, bias, o, st))
   if (rowb == 64) {
-    if (n == 32) return launch_flatconv<64, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-    if (n == 64) return launch_flatconv<64, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-    if (n == 256) return launch_flatconv<64, 256>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-    return launch_flatconv<64, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+    if (n == 32) return CVAD_FC(64, 32);
+    if (n == 64) return CVAD_FC(64, 64);
+    if (n == 256) return CVAD_FC(64, 256);
+    return CVAD_FC(64, 128);
   }
-  if (n == 32) return launch_flatconv<128, 32>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-  if (n == 64) return launch_flatconv<128, 64>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-  if (n == 256) return launch_flatconv<128, 256>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
-  return launch_flatconv<128, 128>(src, src_rows, K, wpk, w_rows, p, bias, o, st);
+  if (n == 32) return CVAD_FC(128, 32);
+  if (n == 64) return CVAD_FC(128, 64);
+  if (n == 256) return CVAD_FC(128, 256);
+  return CVAD_FC(128, 128);
+#undef CVAD_FC
 }
 
 // packed tap order: stride 1 natural; stride 2 grouped by phase plane (kh&1, kw&1) so every unit's taps are contiguous rows

@@ -313,6 +313,19 @@ int cvad_linear_fwd_tf32x3(const float* x, const float* w, float* y, int M, int 
 int cvad_bn_fold_conv_f32(const float* w, const float* b, const float* gamma, const float* beta, const float* running_mean,
                           const float* running_var, float eps, int Cout, int per_out, float* w_out, float* b_out, void* stream);
 
+/* ---- frame preparation on the device (frames.cu): a video's raw uint8 frames are uploaded once, clips are cut, resized and
+ * laid out on the GPU instead of crossing PCIe as fp32 per clip.
+ * cvad_resize_bilinear_u8     cv2.resize(img, (dst_w, dst_h)) with INTER_LINEAR on 8-bit images (cad:92, the Avenue loaders, bbox:399), BIT-EXACT:
+ *                             OpenCV's 11-bit fixed-point coefficients, its two-pass rounding and its border rules.  src (N,src_h,src_w,C)
+ *                             interleaved uint8 (C = 1..4) -> dst (N,dst_h,dst_w,C).
+ * cvad_clips_from_frames_f32  clips (B,C,T,H,W) fp32 = frames[starts[b] + t*frame_stride] * scale, channels optionally reversed (BGR -> RGB):
+ *                             cvtColor + /255 + permute of the Avenue loaders and the stride-4 window gather of bbox:392-411 in one pass.
+ * cvad_clips_from_frames_u8   clips (B,T,1,H,W) uint8 from grayscale frames (F,H,W): M-A's sequence windows (cad:57), normalised by the stem. */
+int cvad_resize_bilinear_u8(const void* src, int N, int src_h, int src_w, int C, void* dst, int dst_h, int dst_w, void* stream);
+int cvad_clips_from_frames_f32(const void* frames, int F, int H, int W, int C, const int* starts, int B, int T, int frame_stride, float scale,
+                               int reverse_channels, float* out, void* stream);
+int cvad_clips_from_frames_u8(const void* frames, int F, int H, int W, const int* starts, int B, int T, int frame_stride, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
