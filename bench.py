@@ -336,7 +336,7 @@ def profile_calls(tr, x_dev, y_dev, path, reps=5):
         return lambda: gp(x_dev, y_dev)
     profile_graph(make, path, "M-A train-step graph (batch 32)", reps,
                   spans=[("cvad_pad_avgpool_bf16_fwd", "cvad_pad_avgpool_bf16_bwd", "dense tail on the critical path (detector ... loss ... classifier backward)"),
-                         ("cvad_stem_space_to_depth_u8", "cvad_pad_maxpool3x3s2_bf16", "stem passes"),
+                         ("cvad_stem_space_to_depth_u8", "cvad_flat_conv3x3_fwd_stats_bf16", "stem (both passes + max-pool)"),
                          ("cvad_pad_avgpool_bf16_bwd", "cvad_sumsq_f32", "backbone backward")])
 
 
