@@ -68,7 +68,7 @@ def _worker(rank, world, port, q):
             dp.broadcast_parameters(tr.optimizer.arena, model=tr.model)
             gs = tr.graphed_train_step(x, y)
             assert len(gs.stages) == (2 if mode == "1" else 1), len(gs.stages)
-            comp = gs(x, y)[0]
+            first_loss = float(gs(x, y)[0][0])        # read now: the outputs are static buffers that the next replay overwrites
             torch.cuda.synchronize()
             g = tr.optimizer.arena.g
             err = float((g - gsum).abs().max() / gsum.abs().max())
@@ -84,7 +84,7 @@ def _worker(rank, world, port, q):
             if not torch.equal(p, ref):
                 ok = False
                 msg.append(f"mode {mode}: parameters differ across ranks after 3 steps")
-            results[mode] = (p, float(comp[0]))
+            results[mode] = (p, first_loss)
             del gs
         # the two exchanges see the same gradients (checked above against the hand-made sum), so they start the same trajectory: equal
         # first-step loss; after three Adam steps the parameters agree to within what atomics-order round-off in a near-zero gradient
