@@ -36,6 +36,7 @@ using namespace cvad_tc;
 constexpr int FC_MAX_UNITS = 16;
 constexpr int FC_WST_MAX = 8;        // maximum weight ring depth
 constexpr int FC_MAX_SLOTS = 16;     // TMEM accumulator ring
+constexpr int FC_SRC_MAX = 3;        // activation-segment ring depth (2 or 3 stages, FcParams::nsrc)
 constexpr int FC_BOX = 256;          // rows per big TMA box
 constexpr size_t FC_SMEM_BUDGET = 222 * 1024;   // dynamic; the static part (barriers, bias, statistics) stays below 5 KB of the 227 KB
 
@@ -56,6 +57,8 @@ struct FcUnit {
   int ntaps;
   int w_row0;           // first packed weight row of the unit's first tap (n-block 0); tap i follows at + i*N
   int tap_delta[9];     // row shift of tap i inside the segment (>= 0)
+  unsigned char tap_acc[9];           // accumulator set of tap i (0 unless one item fills several output planes)
+  unsigned short first_mask, last_mask;   // bit i: tap i is the first / last tap of its accumulator set inside this unit
 };
 
 struct FcParams {
@@ -63,11 +66,12 @@ struct FcParams {
   long long out_row_base;
   int n_units, seg_rows, sub, n_blocks, ld_out, wst, w_resident;
   int big_boxes, tail_rows;      // segment = big_boxes x 256 rows + one exact tail box (0 = none)
-  // "planes": independent sub-problems walked by ONE launch (the four phase planes of a stride-2 data-gradient).  Plane pl uses units
-  // [plane_unit0[pl], + plane_nunits[pl]) and writes its rows at out_row_base + pl * plane_out_stride.  n_planes <= 1: a single plane
-  // made of units [0, n_units).
-  int n_planes;
-  int plane_unit0[4], plane_nunits[4];
+  // "groups": independent sub-problems per row tile walked by ONE launch (work item = tile x group x n-block).  Group g uses units
+  // [group_unit0[g], + group_nunits[g]) and fills acc_sets accumulator sets (the same number in every group); set a of group g writes its
+  // rows at out_row_base + group_plane[g][a] * plane_out_stride.  A stride-2 data-gradient is ONE group of four sets (the four phase
+  // planes of dx computed from ONE fetch of the dy segment) or two groups of two; everything else is one group with one set.
+  int n_groups, acc_sets, nsrc;
+  int group_unit0[4], group_nunits[4], group_plane[4][4];
   long long plane_out_stride;
   // fused BatchNorm statistics (forward only, n_blocks == 1): per-channel sum / sum of squares of the bf16-rounded outputs over the
   // interior pixels (1..st_h, 1..st_w of every (st_h+2) x (st_w+2) image), added to st_out[0..N) / st_out[N..2N) (fp64, zeroed by the caller)
@@ -153,7 +157,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   constexpr int LAYOUT = ROWB == 128 ? UMMA_SW128 : UMMA_SW64;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_src_full[2], bar_src_empty[2], bar_w_full[FC_WST_MAX], bar_w_empty[FC_WST_MAX], bar_acc_full[FC_MAX_SLOTS],
+  __shared__ uint64_t bar_src_full[FC_SRC_MAX], bar_src_empty[FC_SRC_MAX], bar_w_full[FC_WST_MAX], bar_w_empty[FC_WST_MAX], bar_acc_full[FC_MAX_SLOTS],
       bar_acc_empty[FC_MAX_SLOTS];
   __shared__ uint32_t tmem_base_sh;
   __shared__ float s_bias[N];
@@ -171,18 +175,34 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t seg_bytes = (uint32_t)p.seg_rows * ROWB;
   const uint32_t s_src = smem_base;
-  const uint32_t s_w = smem_base + 2 * seg_bytes;
+  const int nsrc = p.nsrc;
+  const uint32_t s_w = smem_base + nsrc * seg_bytes;
 
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int sub = p.sub, n_units = p.n_units, n_blocks = p.n_blocks, wst = p.wst, resident = p.w_resident;
   const int MT = 128 * sub;
   const long long n_tiles = (p.rows + MT - 1) / MT;
-  const long long per_plane = n_tiles * n_blocks;
-  const int n_planes = p.n_planes > 1 ? p.n_planes : 1;
-  const long long total = per_plane * n_planes;
+  const int n_groups = p.n_groups, acc_sets = p.acc_sets;
+  const long long total = n_tiles * n_blocks * n_groups;
+  const int item_slots = acc_sets * sub;            // accumulators one work item fills
+  // work item -> (tile, group, n-block).  The groups of one tile are consecutive items, i.e. they run on neighbouring CTAs at the same
+  // time and share their source segment through L2; the group index is rotated by the round (wi / gridDim.x, gridDim.x is a multiple of
+  // n_groups) so that every CTA sees all groups, whose tap counts differ.
+#define FC_DECODE(wi, g, q0, nb)                                                        \
+  int g = 0, nb;                                                                          \
+  long long q0;                                                                           \
+  {                                                                                       \
+    long long rest = (wi);                                                                \
+    if (n_groups > 1) {                                                                   \
+      g = (int)(((wi) + (wi) / gridDim.x) % n_groups);                                    \
+      rest = (wi) / n_groups;                                                             \
+    }                                                                                     \
+    q0 = (rest / n_blocks) * MT;                                                          \
+    nb = (int)(rest % n_blocks);                                                          \
+  }
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
+    for (int i = 0; i < FC_SRC_MAX; ++i) { mbar_init(&bar_src_full[i], 1); mbar_init(&bar_src_empty[i], 1); }
     for (int i = 0; i < FC_WST_MAX; ++i) { mbar_init(&bar_w_full[i], 1); mbar_init(&bar_w_empty[i], 1); }
     for (int i = 0; i < FC_MAX_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
     fence_barrier_init();
@@ -200,12 +220,12 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     // ------------------------------------------------------------------ TMA producer: activation segments
     uint32_t src_cnt = 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const int pl = (int)(wi / per_plane);
-      const long long q0 = ((wi % per_plane) / n_blocks) * MT;
-      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      FC_DECODE(wi, g, q0, nb)
+      (void)nb;
+      const int u0 = p.group_unit0[g], nu = p.group_nunits[g];
       for (int u = u0; u < u0 + nu; ++u) {
-        const int st = src_cnt & 1;
-        mbar_wait(&bar_src_empty[st], ((src_cnt >> 1) & 1) ^ 1);
+        const int st = (int)(src_cnt % nsrc);
+        mbar_wait(&bar_src_empty[st], ((src_cnt / nsrc) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(&bar_src_full[st], seg_bytes);
           const int r0 = (int)(q0 + p.units[u].row_off), col = p.units[u].col;
@@ -222,10 +242,10 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     uint32_t w_cnt = 0;
     bool first_item = true;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const int pl = (int)(wi / per_plane);
-      const int nb = (int)((wi % per_plane) % n_blocks);
+      FC_DECODE(wi, g, q0, nb)
+      (void)q0;
       if (resident && !first_item) break;
-      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      const int u0 = p.group_unit0[g], nu = p.group_nunits[g];
       for (int u = u0; u < u0 + nu; ++u) {
         const int ntaps = p.units[u].ntaps, col = p.units[u].col;
         const int row0 = p.units[u].w_row0 + nb * 9 * N;
@@ -253,13 +273,16 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     const long long t_loop_ns = dbg ? (long long)globaltimer_ns() : 0;
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       ++n_items;
-      const int pl = (int)(wi / per_plane);
-      const int u0 = p.n_planes > 1 ? p.plane_unit0[pl] : 0, nu = p.n_planes > 1 ? p.plane_nunits[pl] : n_units;
+      FC_DECODE(wi, g, q0, nb)
+      (void)q0;
+      (void)nb;
+      const int u0 = p.group_unit0[g], nu = p.group_nunits[g];
       for (int u = u0; u < u0 + nu; ++u) {
         const int ntaps = p.units[u].ntaps;
-        const int st = src_cnt & 1;
+        const uint32_t first_mask = u == u0 ? p.units[u].first_mask : 0u, last_mask = u == u0 + nu - 1 ? p.units[u].last_mask : 0u;
+        const int st = (int)(src_cnt % nsrc);
         long long tq = dbg ? clock64() : 0;
-        mbar_wait(&bar_src_full[st], (src_cnt >> 1) & 1);
+        mbar_wait(&bar_src_full[st], (src_cnt / nsrc) & 1);
         if (dbg) t_src += clock64() - tq;
         tc_fence_after();
         const uint32_t a_seg = s_src + st * seg_bytes;
@@ -272,15 +295,16 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           const int tin = ntaps - c * TPO < TPO ? ntaps - c * TPO : TPO;
           for (int j = 0; j < tin; ++j) {
             const int t = c * TPO + j;
-            const bool first = (u == u0 && t == 0);
-            const bool last = (u == u0 + nu - 1 && t == ntaps - 1);
+            const bool first = (first_mask >> t) & 1u;          // overwrite: the first tap of its accumulator set in the item's first unit
+            const bool last = (last_mask >> t) & 1u;
+            const uint32_t acc0 = acc_cnt + p.units[u].tap_acc[t] * sub;
             // descriptors advance by plain adds: (bytes >> 4) never carries out of the 14-bit address field (smem < 256 KiB)
             const uint64_t db0 = desc_hi | (uint64_t)(((s_w + ws * WBOX_BYTES + j * (N * ROWB)) >> 4) & 0x3FFF);
             const uint64_t da0 = desc_hi | (uint64_t)(((a_seg + (uint32_t)p.units[u].tap_delta[t] * ROWB) >> 4) & 0x3FFF);
             if (first) {
               // first tap of a tile: each accumulator slot must have been drained by the epilogue (overwrite, no accumulate)
               for (int s = 0; s < sub; ++s) {
-                const uint32_t use = acc_cnt + s;
+                const uint32_t use = acc0 + s;
                 const int slot = use % NSLOT;
                 tq = dbg ? clock64() : 0;
                 mbar_wait(&bar_acc_empty[slot], ((use / NSLOT) & 1) ^ 1);
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
               }
             } else {
               if (elect_one()) {
-                uint32_t slot = acc_cnt % NSLOT;
+                uint32_t slot = acc0 % NSLOT;
                 uint64_t da = da0;
                 for (int s = 0; s < sub; ++s) {
 #pragma unroll
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         __syncwarp();
         ++src_cnt;
       }
-      acc_cnt += sub;
+      acc_cnt += item_slots;
     }
     if (dbg && lane == 0) {
       long long* d = dbg + (long long)blockIdx.x * 8;
@@ -334,18 +358,19 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     float st_s[N / 16], st_q[N / 16];          // fused statistics: this lane's column of every 16-column chunk, over all its tiles
 #pragma unroll
     for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
+
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
-      const int pl = (int)(wi / per_plane);
-      const long long q0 = ((wi % per_plane) / n_blocks) * MT;
-      const int nb = (int)((wi % per_plane) % n_blocks);
+      FC_DECODE(wi, g, q0, nb)
       if (nb != cur_nb) {                       // stage this n-block's bias once (epilogue warps only: named barrier 1)
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         cur_nb = nb;
       }
-      for (int s = eg; s < sub; s += 2) {
-        const uint32_t use = acc_cnt + s;
+      for (int idx = eg; idx < item_slots; idx += 2) {        // accumulator sets in the order the MMA warp completes them
+        const int a = idx / sub, s = idx - a * sub;
+        const int pl = p.group_plane[g][a];
+        const uint32_t use = acc_cnt + idx;
         const int slot = use % NSLOT;
         // row bookkeeping first: none of it depends on the accumulator, and the raw loads of the fused BatchNorm-backward reductions
         // are issued BEFORE the wait so that their latency hides behind the MMAs still running for this slot
@@ -445,7 +470,7 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         tc_fence_before();
         mbar_arrive(&bar_acc_empty[slot]);
       }
-      acc_cnt += sub;
+      acc_cnt += item_slots;
     }
     if (p.st_out && !(lane & 1)) {            // one shared-memory add per warp and column, once per kernel
       const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
@@ -471,32 +496,75 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
     atomicMin((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8, (unsigned long long)t_entry);
     atomicMax((unsigned long long*)g_fc_debug + FC_DBG_CTAS * 8 + 1, globaltimer_ns());
   }
+#undef FC_DECODE
 }
 
 // ---------------------------------------------------------------------------------------------- host side
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-bool g_dgrad_one_launch = true;        // cvad_flat_dgrad_mode(0): one launch per phase plane (A/B measurements)
+// Stride-2 data-gradient: 2 = one launch, one work item per row tile fills all four phase planes of dx from ONE fetch of the dy segment
+// (two items of two planes when four accumulator sets would leave the TMEM ring without a second buffer); 1 = one launch, one item per
+// (tile, plane): dy is fetched four times; 0 = one launch per plane.  cvad_flat_dgrad_mode() switches (A/B measurements).
+int g_dgrad_mode = 2;
+// development knobs (cvad_flat_tune): [0] cap on the 128-row sub-tiles per work item for N = 128 (4 fills the whole accumulator ring,
+// 2 leaves a second buffer for the epilogue); [1] activation-segment ring depth for items with several units (3 = a third stage when
+// shared memory allows, 2 = always double buffering)
+int g_fc_tune[4] = {2, 3, 0, 0};
 // Output-channel block = the MMA's N.  One M128 x N x K16 MMA streams 4 KB of A plus N*32 B of B from shared memory at ~80-90 B/cycle
 // (profiles/r01g_flatconv_L0_ncu_full.md), so it is operand-bound below N = 256: take the widest N the layer allows.
 inline int n_block_of(int nout) { return nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32)); }
+
+// fills the bookkeeping every launch needs from the units' tap lists: a single group / accumulator set unless the caller set them up,
+// and the per-unit first / last masks
+void finish_units(FcParams& p) {
+  if (p.n_groups < 1) {
+    p.n_groups = 1;
+    p.group_unit0[0] = 0;
+    p.group_nunits[0] = p.n_units;
+  }
+  if (p.acc_sets < 1) p.acc_sets = 1;
+  for (int u = 0; u < p.n_units; ++u) {
+    FcUnit& un = p.units[u];
+    un.first_mask = un.last_mask = 0;
+    for (int a = 0; a < p.acc_sets; ++a) {
+      int f = -1, l = -1;
+      for (int t = 0; t < un.ntaps; ++t)
+        if (un.tap_acc[t] == a) {
+          if (f < 0) f = t;
+          l = t;
+        }
+      if (f >= 0) {
+        un.first_mask |= (unsigned short)(1u << f);
+        un.last_mask |= (unsigned short)(1u << l);
+      }
+    }
+  }
+}
 
 template <int ROWB, int N, bool BW>
 int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk, long long w_rows, FcParams& p, const float* bias,
                     __nv_bfloat16* out, cudaStream_t st) {
   constexpr int TPO = FC_BOX / N;
-  int max_delta = 0, max_chunks = 0;
+  constexpr int NSLOT = (512 / N) > FC_MAX_SLOTS ? FC_MAX_SLOTS : (512 / N);
+  finish_units(p);
+  int max_delta = 0, max_chunks = 0, max_group_units = 0;
   for (int u = 0; u < p.n_units; ++u) {
     for (int t = 0; t < p.units[u].ntaps; ++t) max_delta = p.units[u].tap_delta[t] > max_delta ? p.units[u].tap_delta[t] : max_delta;
     const int ch = (p.units[u].ntaps + TPO - 1) / TPO;
     max_chunks = ch > max_chunks ? ch : max_chunks;
   }
-  // rows per work item: as many 128-row sub-tiles as TMEM and shared memory allow while the machine stays filled
+  for (int g = 0; g < p.n_groups; ++g) max_group_units = p.group_nunits[g] > max_group_units ? p.group_nunits[g] : max_group_units;
+  // rows per work item: as many 128-row sub-tiles as TMEM and shared memory allow while the machine stays filled.  TMEM: 512 columns =
+  // NSLOT accumulators; an item fills acc_sets x sub of them, and the epilogue overlaps the next item's MMAs only when that is at most
+  // half the ring.  N = 256 has two slots and keeps sub = 2 without a second buffer: one 128-row sub-tile per 32 KB weight box would
+  // make the weight stream the limiter (measured: 84 -> 92 us at 8x12 256->256)
   static const int cand[] = {8, 6, 4, 3, 2, 1};
-  const int sub_max = N == 32 ? 8 : (N == 256 ? 2 : 4);     // TMEM: 512 columns = sub x N accumulators (x2 when they double-buffer)
+  int sub_max = NSLOT / p.acc_sets;
+  if (NSLOT >= 4 * p.acc_sets && !(N == 128 && p.acc_sets == 1 && g_fc_tune[0] >= 4)) sub_max = NSLOT / (2 * p.acc_sets);
+  if (sub_max < 1) return (int)cudaErrorInvalidValue;
   p.sub = 0;
   for (int sub : cand) {
     if (sub > sub_max) continue;
-    const long long items = ((p.rows + 128LL * sub - 1) / (128LL * sub)) * p.n_blocks * (p.n_planes > 1 ? p.n_planes : 1);
+    const long long items = ((p.rows + 128LL * sub - 1) / (128LL * sub)) * p.n_blocks * p.n_groups;
     if (sub > 1 && items < (3LL * cvad_num_sms()) / 2) continue;
     const int seg = round_up(128 * sub + max_delta, 64);
     if (2 * (size_t)seg * ROWB + 1024 + 2 * (size_t)FC_BOX * ROWB > FC_SMEM_BUDGET) continue;
@@ -505,10 +573,15 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
     break;
   }
   if (!p.sub) return (int)cudaErrorInvalidValue;
-  const size_t fixed = 2 * (size_t)p.seg_rows * ROWB + 1024;
-  long long wst = (long long)((FC_SMEM_BUDGET - fixed) / ((size_t)FC_BOX * ROWB));
+  const size_t seg_bytes = (size_t)p.seg_rows * ROWB, box_bytes = (size_t)FC_BOX * ROWB;
+  // a third segment stage for items made of several short units (the phase planes of a stride-2 forward: 4 / 2 / 2 / 1 taps per fetch),
+  // as long as the weight ring keeps at least three boxes
+  p.nsrc = 2;
+  if (g_fc_tune[1] >= 3 && max_group_units > 1 && 3 * seg_bytes + 1024 + 3 * box_bytes <= FC_SMEM_BUDGET) p.nsrc = 3;
+  const size_t fixed = p.nsrc * seg_bytes + 1024;
+  long long wst = (long long)((FC_SMEM_BUDGET - fixed) / box_bytes);
   p.wst = (int)(wst > FC_WST_MAX ? FC_WST_MAX : wst);
-  p.w_resident = (p.n_units == 1 && p.n_blocks == 1 && p.n_planes <= 1 && max_chunks <= p.wst) ? 1 : 0;
+  p.w_resident = (p.n_units == 1 && p.n_blocks == 1 && p.n_groups == 1 && max_chunks <= p.wst) ? 1 : 0;
   p.big_boxes = p.seg_rows / FC_BOX;
   p.tail_rows = p.seg_rows % FC_BOX;
   const size_t smem = fixed + (size_t)p.wst * FC_BOX * ROWB;
@@ -523,8 +596,9 @@ int launch_flatconv(const void* src, long long src_rows, int K, const void* wpk,
   const cudaError_t ce = cvad_ensure_dyn_smem(flatconv_kernel<ROWB, N, BW>, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
   const long long MT = 128LL * p.sub;
-  const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks * (p.n_planes > 1 ? p.n_planes : 1);
-  const int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
+  const long long total = ((p.rows + MT - 1) / MT) * p.n_blocks * p.n_groups;
+  int grid = (int)(total < cvad_num_sms() ? total : cvad_num_sms());
+  if (grid < total) grid -= grid % p.n_groups;           // the kernel's group rotation needs whole tiles per round
   flatconv_kernel<ROWB, N, BW><<<grid, 384, smem, st>>>(ms, mt, mw, p, bias, out);
   CVAD_LAUNCH_CHECK();
   return 0;
@@ -587,8 +661,14 @@ CVAD_API int cvad_flat_debug_buffer(long long* buf) {
   return (int)cudaMemcpyToSymbol(g_fc_debug, &buf, sizeof(buf));
 }
 
-CVAD_API int cvad_flat_dgrad_mode(int one_launch) {
-  g_dgrad_one_launch = one_launch != 0;
+CVAD_API int cvad_flat_dgrad_mode(int mode) {
+  g_dgrad_mode = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return 0;
+}
+
+CVAD_API int cvad_flat_tune(int key, int value) {
+  if (key < 0 || key >= 4) return (int)cudaErrorInvalidValue;
+  g_fc_tune[key] = value;
   return 0;
 }
 
@@ -724,20 +804,65 @@ int flat_dgrad(const void* dy, const void* w_dgrad, void* dx, int N, int H, int 
   }
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
   const long long rows = (long long)N * (Ho + 2) * Wq;
-  if (g_dgrad_one_launch && 4 * nslab <= FC_MAX_UNITS) {
-    // all four phase planes in one launch: plane pl is a set of work items with its own units (its 4 / 2 / 2 / 1 taps) and its own
-    // output offset; one drain and one pass over dy instead of four
+  // (measured, profiles/r02c_conv_variants.md: the single fetch pays where the nine taps' weights stay resident in shared memory -- one
+  // K slab, N = 32: 102 -> 92 us at 60x90 32->64 -- and loses where four accumulator sets shrink the work item to 128 rows and the weights
+  // have to be streamed again for each of them: 70 -> 88 us at 30x45 64->128)
+  const bool single_fetch = g_dgrad_mode == 2 && (g_fc_tune[2] ? true : (nslab == 1 && nblk == 32));
+  if (single_fetch && 2 * nslab <= FC_MAX_UNITS) {
+    // One launch, and ONE fetch of each dy segment for all four phase planes of dx: a work item walks all nine taps (packed plane by
+    // plane) and keeps one accumulator set per plane.  Four sets need 4 x N columns of TMEM per 128 rows: with N = 128 that is the whole
+    // ring, so the planes are split into two groups of two sets whose packed taps are contiguous: {0,1} (4 + 2 taps), {2,3} (2 + 1).
+    const int ngr = nblk >= 128 ? 2 : 1;
+    static const int grp_planes[2][2][4] = {{{0, 1, 2, 3}, {0, 0, 0, 0}}, {{0, 1, 0, 0}, {2, 3, 0, 0}}};
     FcParams p;
     memset(&p, 0, sizeof(p));
     p.rows = rows;
-    p.n_planes = 4;
+    p.n_groups = ngr;
+    p.acc_sets = 4 / ngr;
+    p.plane_out_stride = rows;
+    p.n_units = ngr * nslab;
+    for (int g = 0; g < ngr; ++g) {
+      p.group_unit0[g] = g * nslab;
+      p.group_nunits[g] = nslab;
+      for (int a = 0; a < p.acc_sets; ++a) p.group_plane[g][a] = grp_planes[ngr - 1][g][a];
+      for (int s = 0; s < nslab; ++s) {
+        FcUnit& u = p.units[g * nslab + s];
+        u.row_off = -(Wq + 1);
+        u.col = s * slab;
+        u.ntaps = 0;
+        for (int a = 0; a < p.acc_sets; ++a) {
+          int first, count;
+          plane_taps(p.group_plane[g][a], first, count);
+          if (a == 0) u.w_row0 = first * nblk;
+          for (int i = 0; i < count; ++i) {
+            const int t = packed_tap(2, first + i), kh = t / 3, kw = t % 3;
+            u.tap_delta[u.ntaps] = (Wq + 1) - ((kh >> 1) * Wq + (kw >> 1));
+            u.tap_acc[u.ntaps] = (unsigned char)a;
+            ++u.ntaps;
+          }
+        }
+      }
+    }
+    if (bw && rows > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    set_bw(p, bw, H, W, 1);
+    return run_flat(dy, rows, Cout, w_dgrad, Cin, nullptr, dx, p, st);
+  }
+  if (g_dgrad_mode >= 1 && 4 * nslab <= FC_MAX_UNITS) {
+    // all four phase planes in one launch: plane pl is a set of work items with its own units (its 4 / 2 / 2 / 1 taps) and its own
+    // output offset; one drain instead of four, but every plane fetches the dy segment again
+    FcParams p;
+    memset(&p, 0, sizeof(p));
+    p.rows = rows;
+    p.n_groups = 4;
+    p.acc_sets = 1;
     p.plane_out_stride = rows;
     p.n_units = 4 * nslab;
     for (int pl = 0; pl < 4; ++pl) {
       int first, count;
       plane_taps(pl, first, count);
-      p.plane_unit0[pl] = pl * nslab;
-      p.plane_nunits[pl] = nslab;
+      p.group_unit0[pl] = pl * nslab;
+      p.group_nunits[pl] = nslab;
+      p.group_plane[pl][0] = pl;
       for (int s = 0; s < nslab; ++s) {
         FcUnit& u = p.units[pl * nslab + s];
         u.row_off = -(Wq + 1);

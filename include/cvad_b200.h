@@ -122,6 +122,30 @@ int cvad_fill_f32(float* x, long long n, float value, void* stream);
 /* out[i] = a*x[i*xs] + b*y[i*ys]   (score fusion 0.6*causal + 0.4*direct[:,1], cad:574) */
 int cvad_lincomb2_f32(float* out, const float* x, long long xs, float a, const float* y, long long ys, float b, long long n, void* stream);
 
+/* ---- M-A0 (video_anomaly_detection.py, "vad"): the pieces that differ from M-A (ma0_tail.cu) ----------------------------
+ * Same dense layout as the M-A causal branch below (5 track slots per clip + counts); vad's detector keeps at most its 3 anchors. */
+/* vad:127-165: the frame's anchors ordered by descending sigmoid(conf_logit) (torch.topk over all 3; equal scores keep anchor order),
+ * those with confidence > 0.5 copied to box (rows,5,4) as raw bbox_head outputs (no squashing, vad:135-141); no survivor -> one all-zero
+ * dummy box (vad:158-160, a constant).  cnt (rows) int32 >= 1; src (rows,5) int32 = anchor of each kept slot or -1; unused slots are
+ * zero.  active_flag (may be NULL) is set to 1 when any real box was kept (bbox_head then receives a gradient; conf_head never does). */
+int cvad_det_topk_decode_f32(const float* bbox, const float* conf_logit, long long rows, float* box, int* cnt, int* src, float* active_flag,
+                             void* stream);
+int cvad_det_topk_decode_bwd_f32(const float* dbox, const int* src, const int* cnt, long long rows, float* dbbox, void* stream);
+/* vad:389-397: out18[row] = [cur | pred | |cur - pred|] per track row (rows = B*5, 6 factors); bwd uses sign(0) = 0 like torch.abs */
+int cvad_score_rows_f32(const float* z, const float* pred, long long rows, float* out18, void* stream);
+int cvad_score_rows_bwd_f32(const float* z, const float* pred, const float* dout18, long long rows, float* dz, float* dpred, void* stream);
+/* vad:398-399: out[b] = mean of s[b, 0..ntr[b]) over the clip's tracks (s is (B,5)) */
+int cvad_masked_mean_f32(const float* s, const int* ntr, int B, float* out, void* stream);
+int cvad_masked_mean_bwd_f32(const float* dout, const int* ntr, int B, float* ds, void* stream);
+/* vad:516-531: out3 = {total, MSE(scores, labels), KL} with KL = sum of the finite kl[b] / their number (0 when none is finite) and
+ * total = MSE + 0.001*KL; gradients may be NULL (both or none) */
+int cvad_ma0_loss_f32(const float* scores, const float* kl, const long long* labels, int B, float* out3, float* dscores, float* dkl,
+                      float* nonfinite_flag, void* stream);
+/* streaming sliding-window inference (bbox:392-430 turned into a service): per-frame backbone features live in a ring of
+ * `capacity` frames x F floats; out (n_windows, T, F) gathers window w = frames first_frame + w*stride + [0,T) (indices modulo capacity) */
+int cvad_window_features_f32(const float* ring, long long capacity, long long first_frame, int stride, int T, int F, long long n_windows,
+                             float* out, void* stream);
+
 /* ---- M-A causal branch, dense masked batched form (ma_tail.cu) -------------------------------------------------------
  * Every clip carries 5 padded track slots (the detector emits <= 5 boxes per frame, cad:178,198) and a per-clip track
  * count; rows = B*T frames.  Replaces the ragged Python-list loops of cad:206-228, 251-272, 290-307, 337-350, 375-396,
@@ -208,8 +232,12 @@ int cvad_flat_conv3x3_dgrad_bnstats_bf16(const void* dy, const void* w_dgrad, vo
 int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in, const float* mean,
                                     const float* invstd, const float* gamma, const float* beta, int training, double* ws, float* dgamma,
                                     float* dbeta, void* stream);
-/* development switch: 1 (default) = a stride-2 data-gradient is one launch walking its four phase planes, 0 = four launches */
-int cvad_flat_dgrad_mode(int one_launch);
+/* development switch for the stride-2 data-gradient: 2 (default) = one launch, one work item per row tile fills all four phase planes of dx
+ * from ONE fetch of the dy segment; 1 = one launch, one work item per (tile, plane); 0 = four launches */
+int cvad_flat_dgrad_mode(int mode);
+/* development knobs of the flat convolution's launch heuristics (A/B measurements): key 0 = sub-tiles per work item for N = 128 (2 default,
+ * 4 = fill the whole accumulator ring), key 1 = activation-segment ring depth for multi-unit items (3 default, 2 = double buffering only) */
+int cvad_flat_tune(int key, int value);
 /* development switch: 1 (default) = stride-1 32->32 / 64->64 weight gradients stack the three kernel rows in the MMA's N dimension,
  * 0 = one kernel row per MMA */
 int cvad_flat_wgrad_mode(int kh_stack);

@@ -31,7 +31,7 @@ VARIANTS = {
 }
 # switches that exist only on some branches are added when the library exports them
 OPTIONAL_LIB_VARIANTS = {"conv_nine_taps": ("cvad_flat_conv_mode", 0), "dgrad_four_launches": ("cvad_flat_dgrad_mode", 0)}
-LIB_DEFAULTS = {"cvad_flat_wgrad_mode": 1, "cvad_flat_conv_mode": 1, "cvad_flat_dgrad_mode": 1}
+LIB_DEFAULTS = {"cvad_flat_wgrad_mode": 1, "cvad_flat_conv_mode": 1, "cvad_flat_dgrad_mode": 2}
 
 
 def apply(switches):

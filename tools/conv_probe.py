@@ -21,6 +21,12 @@ def main():
     only = sys.argv[2] if len(sys.argv) > 2 else ""
     reps = int(os.environ.get("REPS", "10"))
     dev = torch.device("cuda:0")
+    lib = cvad_b200.ops.L()
+    if os.environ.get("CVAD_DGRAD_MODE"):
+        lib.cvad_flat_dgrad_mode(int(os.environ["CVAD_DGRAD_MODE"]))
+    for k in range(4):
+        if os.environ.get(f"CVAD_FC_TUNE{k}"):
+            lib.cvad_flat_tune(k, int(os.environ[f"CVAD_FC_TUNE{k}"]))
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
     bf = torch.bfloat16
     tot = {"fwd+stats": 0.0, "fwd": 0.0, "dgrad": 0.0, "wgrad-staged": 0.0, "wgrad": 0.0}
@@ -73,7 +79,8 @@ def main():
                 entry, l0, l1 = d[live, 5] - t_in, d[live, 6] - t_in, d[live, 7] - t_in
                 line += (f"[{name} MMA-warp cycles/CTA: total {m[0]:.0f} wait src {m[1]:.0f} w {m[2]:.0f} acc {m[3]:.0f} items {m[4]:.1f}; "
                          f"ns from first CTA entry: last entry {int(entry.max())}, loop start mean {int(l0.double().mean())}, loop end mean "
-                         f"{int(l1.double().mean())} max {int(l1.max())}, last exit {t_out - t_in}] ")
+                         f"{int(l1.double().mean())} max {int(l1.max())}, last exit {t_out - t_in}; "
+                         f"SM clock in the loop {float((d[live, 0].double() / (d[live, 7] - d[live, 6]).double()).mean()) * 1e3:.0f} MHz] ")
             ms = 0.0
             for _ in range(reps):
                 flush.fill_(1)
