@@ -276,6 +276,11 @@ class CausalAnomalyDetector(nn.Module):
             leaf = features.detach().requires_grad_(True)
             feature_cut.append((features, leaf))
             features = leaf
+        return self.tail(features)
+
+    def tail(self, features):
+        """Everything behind the backbone: features (B,T,6144) -> the output dict (cad:546-586).  In eval mode a frame's features do not
+        depend on its clip, which is what ma0.StreamingWindowScorer builds on."""
         B, T, _ = features.shape
         dev = features.device
         f_det = self.flags[SLOT_DETECTOR:SLOT_DETECTOR + 1] if self.flags is not None else None

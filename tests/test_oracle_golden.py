@@ -205,6 +205,69 @@ def ma_noise(c):
 
 
 
+# ---- M-A0 (video_anomaly_detection.py) ------------------------------------------------------------------------------
+def ma0_reference_shapes():
+    """state_dict skeleton of video_anomaly_detection.CausalAnomalyDetector (vad:405-417), built without the reference: cad's backbone,
+    tracker, GRU encoder, factor extractor, structure learner and dynamics net around vad's two-head detector and single scorer."""
+    import collections
+    full = ma_reference_shapes()
+    sd = collections.OrderedDict()
+    for k, v in full.items():
+        if k.startswith("detector."):
+            if "detector.bbox_head.weight" not in sd:
+                sd["detector.bbox_head.weight"] = torch.zeros(12, 6144); sd["detector.bbox_head.bias"] = torch.zeros(12)
+                sd["detector.conf_head.weight"] = torch.zeros(3, 6144); sd["detector.conf_head.bias"] = torch.zeros(3)
+            continue
+        if k.startswith("anomaly_scorer.") or k.startswith("direct_classifier."):
+            continue
+        sd[k] = v
+    for idx, (o, i) in zip((0, 2, 4), ((32, 18), (16, 32), (1, 16))):
+        sd[f"anomaly_scorer.score_net.{idx}.weight"] = torch.zeros(o, i)
+        sd[f"anomaly_scorer.score_net.{idx}.bias"] = torch.zeros(o)
+    return sd
+
+
+def ma0_synth_state(seed, margin):
+    P = synth.synth_fill(ma0_reference_shapes(), seed=seed)
+    if not margin:
+        P["detector.conf_head.weight"] = P["detector.conf_head.weight"] * 4.0
+    else:
+        P["detector.conf_head.weight"] = P["detector.conf_head.weight"] * 0.02
+        P["detector.conf_head.bias"] = torch.tensor([1.5, -1.5, 0.8])
+    return P
+
+
+def ma0_input(c):
+    if c.get("stream"):
+        seq = synth.ma_clips(1, c["T"] + 4 * (c["B"] - 1), c["H"], c["W"], c["xseed"], c["wide"])[0]
+        return torch.stack([seq[4 * w: 4 * w + c["T"]] for w in range(c["B"])]), seq
+    return synth.ma_clips(c["B"], c["T"], c["H"], c["W"], c["xseed"], c["wide"]), None
+
+
+def ma0_eps(c):
+    return torch.randn(c["B"], 5, 6, generator=synth.gen(c["xseed"] + 1))
+
+
+def test_ma0_matches_reference(gold):
+    """oracle/ma0.py against the unmodified video_anomaly_detection.py (tests/golden/ma0.pt): ragged detections (0..3 anchors per frame),
+    scores, KL, adjacency, 2-term loss."""
+    from oracle.ma0 import ma0_forward, ma0_loss
+    seen = set()
+    for c in gold("ma0.pt")["cases"]:
+        P = ma0_synth_state(c["seed"], c["margin"])
+        x, _ = ma0_input(c)
+        with torch.no_grad():
+            out = ma0_forward(P, x, ma0_eps(c), c["train"])
+            loss, comps = ma0_loss(out, c["labels"])
+        assert rel(out["anomaly_scores"], c["anomaly_scores"]) < 1e-4
+        assert rel(out["kl_losses"], c["kl_losses"]) < 1e-4
+        assert rel(out["adjacency_matrices"], c["adjacency"]) < 1e-4
+        assert torch.equal(out["det_counts"], c["det_counts"]) and torch.equal(out["det_real"], c["det_real"])
+        assert rel(loss, c["loss"]) < 1e-4
+        seen |= set(c["det_real"].flatten().tolist())
+    assert seen == {0, 1, 2, 3}, seen          # the fixtures cover the dummy box and every anchor count
+
+
 def test_ma_c2_benchmarked_shape_forward_matches_reference(gold):
     """The oracle at the benchmarked shape (32 x 16 x 240 x 360, train-mode BatchNorm, injected dropout / eps): scores and the 4-term
     loss of the unmodified reference (tests/golden/ma_c2.pt).  Forward only here (the backward is asserted when the fixture is made)."""

@@ -24,6 +24,7 @@ import synth  # noqa: E402
 from oracle.ref_harness import NoiseInjector, import_ref  # noqa: E402
 
 from oracle import ma as o_ma  # noqa: E402
+from oracle import ma0 as o_ma0  # noqa: E402
 from oracle import mb as o_mb  # noqa: E402
 from oracle import mc as o_mc  # noqa: E402
 from oracle import md as o_md  # noqa: E402
@@ -358,6 +359,118 @@ def make_ma():
 
 
 
+# --------------------------------------------------------------------------------------------- M-A0
+def ma0_state(vad, seed, margin):
+    torch.manual_seed(0)
+    model = vad.CausalAnomalyDetector()
+    P = synth.synth_fill(model.state_dict(), seed=seed)
+    if not margin:
+        P["detector.conf_head.weight"] = P["detector.conf_head.weight"] * 4.0      # spread the confidences: 0..3 anchors pass per frame
+    if margin:
+        # confidences far from the 0.5 threshold and from each other: anchors 0 and 2 pass (0 first), anchor 1 never does -- the
+        # detection pattern then survives bf16 round-off in the features (the ragged cases keep the natural near-0.5 confidences)
+        P["detector.conf_head.weight"] = P["detector.conf_head.weight"] * 0.02
+        P["detector.conf_head.bias"] = torch.tensor([1.5, -1.5, 0.8])
+    return model, P
+
+
+def ref_ma0_run(vad, model, P, x, labels, eps, ntr, train):
+    """Run the reference model + its loss (vad:516-531, the standard-precision branch) with injected eps."""
+    model.load_state_dict(P, strict=True)
+    vad.apply_memory_efficient_training.__globals__["print"] = lambda *a, **k: None
+    vad.apply_memory_efficient_training(model)
+    model.train(train)
+    B = x.shape[0]
+    with NoiseInjector() as inj:
+        inj.randn = [eps[b, : int(ntr[b])].clone() for b in range(B)]
+        model.zero_grad()
+        with (torch.enable_grad() if train else torch.no_grad()):
+            outputs = model(x)
+            an = torch.nn.functional.mse_loss(outputs["anomaly_scores"], labels.float())
+            valid = [k for k in outputs["kl_losses"] if torch.isfinite(k)]
+            kl = sum(valid) / len(valid) if valid else torch.tensor(0.0)
+            total = an + 0.001 * kl
+        if train:
+            total.backward()
+    return outputs, total, {"anomaly": float(an), "kl": float(kl)}
+
+
+def make_ma0():
+    print("== M-A0 (video_anomaly_detection.py) ==")
+    vad = import_ref("video_anomaly_detection")
+    out = {"cases": []}
+    cases = [
+        dict(name="rag_eval", seed=11, margin=False, B=3, T=4, H=120, W=180, wide=False, train=False, xseed=311),
+        dict(name="rag_train", seed=11, margin=False, B=3, T=4, H=120, W=180, wide=False, train=True, xseed=312),
+        dict(name="margin_eval", seed=12, margin=True, B=2, T=4, H=240, W=360, wide=True, train=False, xseed=313),
+        dict(name="margin_train", seed=12, margin=True, B=2, T=4, H=240, W=360, wide=True, train=True, xseed=314),
+        dict(name="stream", seed=12, margin=True, B=4, T=16, H=120, W=180, wide=False, train=False, xseed=315, stream=True),
+    ]
+    for c in cases:
+        model, P = ma0_state(vad, c["seed"], c["margin"])
+        B, T = c["B"], c["T"]
+        if c.get("stream"):
+            # B overlapping windows (stride 4) of ONE frame sequence: what ma0.StreamingWindowScorer must reproduce clip by clip
+            seq = synth.ma_clips(1, T + 4 * (B - 1), c["H"], c["W"], c["xseed"], c["wide"])[0]
+            x = torch.stack([seq[4 * w: 4 * w + T] for w in range(B)])
+        else:
+            x = synth.ma_clips(B, T, c["H"], c["W"], c["xseed"], c["wide"])
+        labels = (torch.rand(B, generator=synth.gen(c["xseed"] + 9)) < 0.5).long()
+        eps = torch.randn(B, 5, 6, generator=synth.gen(c["xseed"] + 1))
+        Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in P.items()}
+        ns = {}
+        oo = o_ma0.ma0_forward(Pg, x, eps, c["train"], ns)
+        lo, co = o_ma0.ma0_loss(oo, labels)
+        if c["train"]:
+            lo.backward()
+        ro, rl, rc = ref_ma0_run(vad, model, P, x, labels, eps, oo["n_tracks"], c["train"])
+        print(f" case {c['name']}: tracks/clip {oo['n_tracks'].tolist()} real detections {oo['det_real'].flatten().tolist()}")
+        close(oo["anomaly_scores"], ro["anomaly_scores"], 1e-5, "anomaly_scores")
+        close(oo["kl_losses"], torch.stack(ro["kl_losses"]), 1e-5, "kl_losses")
+        close(oo["adjacency_matrices"], torch.stack(ro["adjacency_matrices"]), 1e-5, "adjacency")
+        for b in range(B):
+            n = int(oo["n_tracks"][b])
+            assert ro["causal_factors"][b].shape[0] == n
+            close(oo["causal_factors"][b, :n], ro["causal_factors"][b], 1e-5, f"causal_factors[{b}]")
+            for t in range(T):
+                m = int(oo["det_counts"][b, t])
+                assert ro["detections"][b][t].shape[0] == m, (ro["detections"][b][t].shape, m)
+                assert float((oo["detections"][b, t, :m] - ro["detections"][b][t]).abs().max()) <= 1e-5 * max(1.0, float(ro["detections"][b][t].abs().max()))
+        close(lo, rl, 1e-5, "total loss")
+        rec = {**c, "labels": labels, "loss": rl.detach().clone(), "comps": rc, "anomaly_scores": ro["anomaly_scores"].detach().clone(),
+               "kl_losses": torch.stack(ro["kl_losses"]).detach().clone(), "adjacency": torch.stack(ro["adjacency_matrices"]).detach().clone(),
+               "causal_factors": oo["causal_factors"].detach().clone(), "n_tracks": oo["n_tracks"].clone(),
+               "detections": oo["detections"].detach().clone(), "det_counts": oo["det_counts"].clone(), "det_real": oo["det_real"].clone(),
+               "features_summary": synth.summarize(oo["features"])}
+        if c["train"]:
+            gs, has = {}, {}
+            gnorm = max(float(p.grad.norm()) for p in model.parameters() if p.grad is not None)
+            for k, p in model.named_parameters():
+                has[k] = p.grad is not None
+                if p.grad is not None:
+                    og = Pg[k].grad
+                    if float(p.grad.norm()) > 1e-5 * gnorm:
+                        rel = float((og - p.grad).double().norm() / p.grad.double().norm())
+                        print(f"   {'ok ' if rel < 5e-3 else 'BAD'} grad {k}: rel-L2 {rel:.2e} |g| {float(p.grad.norm()):.3e}")
+                        assert rel < 5e-3, k
+                    gs[k] = synth.summarize(p.grad)
+                    if p.grad.numel() <= 4096:
+                        gs[k]["full"] = p.grad.clone()
+                elif "backbone.conv1" in k or "backbone.bn1" in k:
+                    pass
+                else:
+                    og = Pg[k].grad
+                    assert og is None or float(og.abs().max()) == 0.0, f"oracle grad for {k} should be none/zero"
+            rec["grad_summary"] = gs
+            rec["has_grad"] = has
+            rec["new_stats"] = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+            for k, v in rec["new_stats"].items():
+                close(ns[k], v, 1e-5, f"stat {k}") if "conv" not in k else None
+        out["cases"].append(rec)
+    torch.save(out, os.path.join(GOLD, "ma0.pt"))
+    print("   wrote ma0.pt", os.path.getsize(os.path.join(GOLD, "ma0.pt")) // 1024, "KiB")
+
+
 def _ma_noise_for(B, T, xseed):
     eps = torch.randn(B, 5, 6, generator=synth.gen(xseed + 1))
     keep = {"det0": synth.keep_mask((B, T, 512), 0.3, xseed + 2), "det1": synth.keep_mask((B, T, 256), 0.2, xseed + 3),
@@ -597,7 +710,7 @@ def make_me():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mb", "mc", "ma", "ma_c2", "ma_traj", "md", "me"]
+    which = sys.argv[1:] or ["mb", "mc", "ma", "ma0", "ma_c2", "ma_traj", "md", "me"]
     os.makedirs(GOLD, exist_ok=True)
     if "mb" in which:
         make_mb()
@@ -605,6 +718,8 @@ if __name__ == "__main__":
         make_mc()
     if "ma" in which:
         make_ma()
+    if "ma0" in which:
+        make_ma0()
     if "ma_c2" in which:
         make_ma_c2()
     if "ma_traj" in which:
