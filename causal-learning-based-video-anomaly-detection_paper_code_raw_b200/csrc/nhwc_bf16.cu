@@ -93,18 +93,71 @@ __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, i
 // Block = 256 threads, two 16-byte vectors per thread and pass (v = tid, tid + 256): every padded row of the backbone
 // (368..448 vectors) is one pass with all loads issued before the first use.  PHASE=1 handles the two column-phase planes
 // (a,0) and (a,1) of one plane row in the same block, so the raw row both of them sample is fetched from HBM once.
-template <int PHASE, int R>
+// FIN: the batch statistics are still the raw fp64 sums in fin.ws (left there by the convolution's epilogue): every thread finalises its own
+// eight channels (the arithmetic of bn_finalize_nhwc_kernel, so the result is bit-identical), block 0 also publishes mean / invstd for
+// the backward and updates the running statistics, and the last block past this prologue re-zeroes the sums -- one launch instead of
+// two on the critical path of every layer.
+struct BnFin {
+  double* ws;
+  double count;
+  float eps, momentum;
+  float *mean_out, *invstd_out, *running_mean, *running_var;
+  long long* nbt;
+};
+__device__ unsigned int g_bn_fold_ticket = 0u;
+
+// after every thread of the block has consumed its ws values: the last block of the grid to get here zeroes ws[0, 2C)
+__device__ __forceinline__ void bn_fold_release(double* ws, int C) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&g_bn_fold_ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    for (int j = threadIdx.x; j < 2 * C; j += blockDim.x) ws[j] = 0.0;
+    if (threadIdx.x == 0) g_bn_fold_ticket = 0u;
+  }
+}
+
+template <int PHASE, int R, bool FIN>
 __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloat16* __restrict__ raw, __nv_bfloat16* __restrict__ act, PadGeo g,
                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                                const float* __restrict__ gamma, const float* __restrict__ beta) {
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta, BnFin fin) {
   const int groups = 1 << g.lg;
   const int cg = threadIdx.x & (groups - 1);
   float sc[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = cg * 8 + i;
-    sc[i] = invstd[c] * gamma[c];
-    sh[i] = beta[c] - mean[c] * sc[i];
+    float mu, is;
+    if (FIN) {
+      const double m = fin.ws[c] / fin.count;
+      double var = fin.ws[g.C + c] / fin.count - m * m;
+      if (var < 0.0) var = 0.0;
+      mu = (float)m;
+      is = (float)(1.0 / sqrt(var + (double)fin.eps));
+    } else {
+      mu = mean[c];
+      is = invstd[c];
+    }
+    sc[i] = is * gamma[c];
+    sh[i] = beta[c] - mu * sc[i];
+  }
+  if (FIN) {
+    if (blockIdx.x == 0)
+      for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+        const double m = fin.ws[c] / fin.count;
+        double var = fin.ws[g.C + c] / fin.count - m * m;
+        if (var < 0.0) var = 0.0;
+        fin.mean_out[c] = (float)m;
+        fin.invstd_out[c] = (float)(1.0 / sqrt(var + (double)fin.eps));
+        if (fin.running_mean) {
+          const double unbiased = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+          fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)m;
+          fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unbiased;
+        }
+        if (c == 0 && fin.nbt) *fin.nbt += 1;
+      }
+    bn_fold_release(fin.ws, g.C);
   }
   const int Hp = g.H + 2, Wp = g.W + 2;
   const int items = PHASE ? 2 * g.N * g.Hq : g.N * Hp;          // PHASE: (a, n, i) with both b planes per item
@@ -283,12 +336,14 @@ __global__ void __launch_bounds__(256, 3) pad_reduce_kernel(const __nv_bfloat16*
 }
 
 // ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)
-template <int PHASE, int R>
+// FOLD: block 0 also adds the two sums into dgamma / dbeta and the last block past the prologue re-zeroes ws (bn_bwd_params_nhwc_kernel's
+// work): no third launch.
+template <int PHASE, int R, bool FOLD>
 __global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
                                                                     __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                    const float* __restrict__ beta, const double* __restrict__ ws, double count,
-                                                                    int training) {
+                                                                    const float* __restrict__ beta, double* __restrict__ ws, double count,
+                                                                    int training, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int groups = 1 << g.lg;
   const int cg = threadIdx.x & (groups - 1);
   // With a = gamma*invstd, b = beta - mean*a (the forward's scale/shift), g = dact*(x*a + b > 0), mg = mean(g), mgx = mean(g*xhat):
@@ -304,6 +359,14 @@ __global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_b
     const float mgx = training ? (float)(ws[g.C + c] / count) : 0.f;
     k1[i] = ca[i] * mgx * is;
     k0[i] = ca[i] * mg - k1[i] * mu;
+  }
+  if (FOLD) {
+    if (blockIdx.x == 0)
+      for (int c = threadIdx.x; c < g.C; c += blockDim.x) {
+        if (dgamma) dgamma[c] += (float)ws[g.C + c];
+        if (dbeta) dbeta[c] += (float)ws[c];
+      }
+    bn_fold_release(ws, g.C);
   }
   const int Hp = g.H + 2, Wp = g.W + 2;
   const int rows = g.N * Hp, rowlen = Wp << g.lg;
@@ -484,17 +547,59 @@ inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   return 0;
 }
 
+template <bool BWD>
+void launch_reduce(const __nv_bfloat16* r, const __nv_bfloat16* d, const PadGeo& g, int N, int H, int phase_in, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, double* ws, cudaStream_t st) {
+  const size_t sm = 256 * 16 * sizeof(float);
+  // (a row-structured variant of this reduction -- fixed channel group per thread, no per-element index division -- measured 5-10 % SLOWER
+  // at every backbone shape: the kernel is not instruction-bound)
+  const int per_sm = BWD ? 3 : 4;                         // one wave (the kernel's launch bounds)
+  const int blocks = N * H < per_sm * cvad_num_sms() ? N * H : per_sm * cvad_num_sms();
+  if (BWD && phase_in) pad_reduce_kernel<BWD, 1><<<blocks, 256, sm, st>>>(r, d, g, mean, invstd, gamma, beta, ws);
+  else pad_reduce_kernel<BWD, 0><<<blocks, 256, sm, st>>>(r, d, g, mean, invstd, gamma, beta, ws);
+}
+
+int launch_apply(const __nv_bfloat16* r, __nv_bfloat16* a, const PadGeo& g, int N, int H, int phase_out, const float* mean, const float* invstd,
+                 const float* gamma, const float* beta, bool finalize, const BnFin& fin, cudaStream_t st) {
+  const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
+  const int R = bn_rows_per_iter() == 4 ? 4 : 2;
+  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
+  const int blocks = want < cap ? want : cap;
+#define CVAD_APPLY(PH, RR, FI) pad_bn_apply_relu_kernel<PH, RR, FI><<<blocks, 256, 0, st>>>(r, a, g, mean, invstd, gamma, beta, fin)
+#define CVAD_APPLY2(PH, FI) { if (R == 2) CVAD_APPLY(PH, 2, FI); else CVAD_APPLY(PH, 4, FI); }
+  if (phase_out) { if (finalize) CVAD_APPLY2(1, true) else CVAD_APPLY2(1, false) }
+  else { if (finalize) CVAD_APPLY2(0, true) else CVAD_APPLY2(0, false) }
+#undef CVAD_APPLY2
+#undef CVAD_APPLY
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+// 1 (default): the finalize / parameter-gradient kernels are folded into the apply kernels; 0: separate launches
+inline int bn_fold() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVAD_BN_FOLD");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// apply pass of the backward; with dgamma / dbeta it also performs the parameter-gradient update and re-zeroes ws (FOLD)
 int launch_bwd_apply(const __nv_bfloat16* r, const __nv_bfloat16* d, __nv_bfloat16* draw, const PadGeo& g, int N, int H, int W, int phase_in,
-                     const float* mean, const float* invstd, const float* gamma, const float* beta, const double* ws, int training,
-                     cudaStream_t st) {
+                     const float* mean, const float* invstd, const float* gamma, const float* beta, double* ws, int training, bool fold,
+                     float* dgamma, float* dbeta, cudaStream_t st) {
   const int rows = N * (H + 2);
-  const int R = bn_rows_per_iter();
+  const int R = bn_rows_per_iter() == 4 ? 4 : 2;
   const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
   const int ab = want < cap ? want : cap;
   const double count = (double)N * H * W;
-#define CVAD_BAPPLY(PH, RR) pad_bn_relu_bwd_apply_kernel<PH, RR><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training)
-  if (phase_in) { if (R == 1) CVAD_BAPPLY(1, 1); else if (R == 2) CVAD_BAPPLY(1, 2); else CVAD_BAPPLY(1, 4); }
-  else { if (R == 1) CVAD_BAPPLY(0, 1); else if (R == 2) CVAD_BAPPLY(0, 2); else CVAD_BAPPLY(0, 4); }
+#define CVAD_BAPPLY(PH, RR, FO) \
+  pad_bn_relu_bwd_apply_kernel<PH, RR, FO><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training, dgamma, dbeta)
+#define CVAD_BAPPLY2(PH, FO) { if (R == 2) CVAD_BAPPLY(PH, 2, FO); else CVAD_BAPPLY(PH, 4, FO); }
+  if (phase_in) { if (fold) CVAD_BAPPLY2(1, true) else CVAD_BAPPLY2(1, false) }
+  else { if (fold) CVAD_BAPPLY2(0, true) else CVAD_BAPPLY2(0, false) }
+#undef CVAD_BAPPLY2
 #undef CVAD_BAPPLY
   CVAD_LAUNCH_CHECK();
   return 0;
@@ -508,9 +613,7 @@ CVAD_API int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C,
   PadGeo g;
   if (make_geo(g, N, H, W, C, 0)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  int blocks = N * H < 4 * cvad_num_sms() ? N * H : 4 * cvad_num_sms();      // one wave (launch bounds: 4 CTAs per SM)
-  pad_reduce_kernel<false, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>((const __nv_bfloat16*)raw, nullptr, g, nullptr, nullptr, nullptr,
-                                                                              nullptr, ws);
+  launch_reduce<false>((const __nv_bfloat16*)raw, nullptr, g, N, H, 0, nullptr, nullptr, nullptr, nullptr, ws, st);
   CVAD_LAUNCH_CHECK();
   bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, (double)N * H * W, eps, momentum, mean, invstd, running_mean, running_var,
                                                            num_batches_tracked);
@@ -532,18 +635,28 @@ CVAD_API int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int 
   PadGeo g;
   if (make_geo(g, N, H, W, C, phase_out)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
-  const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
-  const int R = bn_rows_per_iter();
-  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
-  const int blocks = want < cap ? want : cap;
-  const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
-  __nv_bfloat16* a = (__nv_bfloat16*)act;
-#define CVAD_APPLY(PH, RR) pad_bn_apply_relu_kernel<PH, RR><<<blocks, 256, 0, st>>>(r, a, g, mean, invstd, gamma, beta)
-  if (phase_out) { if (R == 1) CVAD_APPLY(1, 1); else if (R == 2) CVAD_APPLY(1, 2); else CVAD_APPLY(1, 4); }
-  else { if (R == 1) CVAD_APPLY(0, 1); else if (R == 2) CVAD_APPLY(0, 2); else CVAD_APPLY(0, 4); }
-#undef CVAD_APPLY
-  CVAD_LAUNCH_CHECK();
-  return 0;
+  BnFin fin;
+  memset(&fin, 0, sizeof(fin));
+  return launch_apply((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, N, H, phase_out, mean, invstd, gamma, beta, false, fin, st);
+}
+
+CVAD_API int cvad_pad_bn_finalize_apply_relu_bf16(const void* raw, void* act, int N, int H, int W, int C, int phase_out, double* ws, float eps,
+                                                  float momentum, const float* gamma, const float* beta, float* mean, float* invstd,
+                                                  float* running_mean, float* running_var, long long* num_batches_tracked, void* stream) {
+  PadGeo g;
+  if (make_geo(g, N, H, W, C, phase_out) || !ws || !mean || !invstd) return (int)cudaErrorInvalidValue;
+  cudaStream_t st = (cudaStream_t)stream;
+  const double count = (double)N * H * W;
+  if (!bn_fold()) {
+    bn_finalize_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, count, eps, momentum, mean, invstd, running_mean, running_var,
+                                                             num_batches_tracked);
+    CVAD_LAUNCH_CHECK();
+    BnFin none;
+    memset(&none, 0, sizeof(none));
+    return launch_apply((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, N, H, phase_out, mean, invstd, gamma, beta, false, none, st);
+  }
+  BnFin fin = {ws, count, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked};
+  return launch_apply((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, N, H, phase_out, nullptr, nullptr, gamma, beta, true, fin, st);
 }
 
 CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* draw, int N, int H, int W, int C, int phase_in,
@@ -553,15 +666,12 @@ CVAD_API int cvad_pad_bn_relu_bwd_bf16(const void* raw, const void* dact, void* 
   if (make_geo(g, N, H, W, C, phase_in)) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  int blocks = N * H < 3 * cvad_num_sms() ? N * H : 3 * cvad_num_sms();      // one wave (launch bounds: 3 CTAs per SM)
-  if (phase_in)
-    pad_reduce_kernel<true, 1><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
-  else
-    pad_reduce_kernel<true, 0><<<blocks, 256, 256 * 16 * sizeof(float), st>>>(r, d, g, mean, invstd, gamma, beta, ws);
+  launch_reduce<true>(r, d, g, N, H, phase_in, mean, invstd, gamma, beta, ws, st);
   CVAD_LAUNCH_CHECK();
   if (draw) {
-    int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, st);
-    if (e) return e;
+    const bool fold = bn_fold() != 0;
+    int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, fold, dgamma, dbeta, st);
+    if (e || fold) return e;
   }
   bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
   CVAD_LAUNCH_CHECK();
@@ -577,8 +687,9 @@ CVAD_API int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, 
   if (make_geo(g, N, H, W, C, phase_in) || !draw) return (int)cudaErrorInvalidValue;
   cudaStream_t st = (cudaStream_t)stream;
   const __nv_bfloat16 *r = (const __nv_bfloat16*)raw, *d = (const __nv_bfloat16*)dact;
-  int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, st);
-  if (e) return e;
+  const bool fold = bn_fold() != 0;
+  int e = launch_bwd_apply(r, d, (__nv_bfloat16*)draw, g, N, H, W, phase_in, mean, invstd, gamma, beta, ws, training, fold, dgamma, dbeta, st);
+  if (e || fold) return e;
   bn_bwd_params_nhwc_kernel<<<(C + 127) / 128, 128, 0, st>>>(ws, C, dgamma, dbeta);
   CVAD_LAUNCH_CHECK();
   return 0;

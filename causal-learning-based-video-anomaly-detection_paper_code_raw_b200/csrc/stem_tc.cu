@@ -430,8 +430,11 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
     uint32_t acc_cnt = 0;
     const int groups = ST_C / 8;                                    // 16-byte vectors per pixel
     // BatchNorm scale / shift in registers (see stem_tf32_kernel): the epilogue's shared-memory traffic competes with the MMAs' operand
-    // stream, so it is kept to the parked band itself -- stored with the pixel's four 16-byte vectors XOR-swizzled by (column >> 1) & 3,
-    // which makes both the parking stores (lane = column, 64-byte pitch) and the pooling reads bank-conflict free
+    // stream, so it is kept to the parked band itself.  Band layout: column j lives in the 64-byte slot j ^ ((j >> 1) & 1) of its row (the
+    // second pair of every four columns is swapped) and its four 16-byte vectors are XOR-swizzled by (j >> 1) & 3.  The parking stores
+    // (lane = column) and the pooling reads are then both bank-conflict free: the pooling reads walk columns two apart, which without
+    // the slot swap all fall into the same 16 banks (a 64-byte pixel covers half of them) -- ncu showed 2.76 M wavefronts where 1.40 M
+    // suffice on every one of the nine pooling loads (profiles/r02c_stem_pool_ncu_full.md)
     float rs[ST_C], rq[ST_C];
 #pragma unroll
     for (int c = 0; c < ST_C; ++c) { rs[c] = s_sc[c]; rq[c] = s_sh[c]; }
@@ -471,7 +474,7 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
 #pragma unroll
             for (int c = 0; c < 16; ++c) pk[c] = 0u;               // rows outside the frame: post-ReLU zeros never win a max
           }
-          uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)j * ST_C);
+          uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)(j ^ ((j >> 1) & 1)) * ST_C);
           const int sw = (j >> 1) & 3;
           o[0 ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           o[1 ^ sw] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
@@ -491,22 +494,25 @@ __global__ void __launch_bounds__(384, 1) stem_pool_kernel(const __grid_constant
         uint4 o = make_uint4(0, 0, 0, 0);
         if (pwp >= 1 && pwp <= pg.PW) {
           const int pw = pwp - 1;
+          // all nine loads are issued before the first max (a branch per tap made the compiler chain them: load, use, load ...).  A window
+          // column outside the frame is clamped onto its in-frame neighbour, which the window holds anyway: the max is unchanged
+          uint4 tv[9];
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) {
+            int ww = 2 * pw - 1 + bb;
+            ww = ww < 0 ? 0 : (ww >= g.Wo ? g.Wo - 1 : ww);
+            const int off = (ww ^ ((ww >> 1) & 1)) * ST_C + ((cg ^ ((ww >> 1) & 3)) * 8);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+              tv[a * 3 + bb] = *reinterpret_cast<const uint4*>(band + (size_t)(2 * k + a) * pg.tile_pitch + off);
+          }
           __nv_bfloat162 best[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) best[i] = __floats2bfloat162_rn(0.f, 0.f);
+          for (int i = 0; i < 4; ++i) best[i] = reinterpret_cast<const __nv_bfloat162*>(&tv[0])[i];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            const __nv_bfloat16* rowp = band + (size_t)(2 * k + a) * pg.tile_pitch;
+          for (int t9 = 1; t9 < 9; ++t9)
 #pragma unroll
-            for (int bb = 0; bb < 3; ++bb) {
-              const int ww = 2 * pw - 1 + bb;
-              if ((unsigned)ww >= (unsigned)g.Wo) continue;
-              const uint4 tv = *reinterpret_cast<const uint4*>(rowp + (size_t)ww * ST_C + ((cg ^ ((ww >> 1) & 3)) * 8));
-              const __nv_bfloat162* tp = reinterpret_cast<const __nv_bfloat162*>(&tv);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], tp[i]);
-            }
-          }
+            for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], reinterpret_cast<const __nv_bfloat162*>(&tv[t9])[i]);
           o = *reinterpret_cast<uint4*>(best);
         }
         reinterpret_cast<uint4*>(out)[((n * (pg.PH + 2) + ph + 1) * (long long)rowlen) + vv] = o;
@@ -645,7 +651,7 @@ int stem_pool_launch(const float* x4, const float* w, const float* bias, const S
   pg.sub = (SP_ROWS * g.Wq + 127) / 128;
   const int seg_px = 128 * pg.sub + 3 * g.Wq + 3 + 8;              // + the pixel remainder of the box's 128-byte alignment
   pg.seg_rows = (seg_px + 7) / 8;
-  pg.tile_pitch = g.Wo * ST_C;
+  pg.tile_pitch = ((g.Wo + 3) & ~3) * ST_C;                       // whole groups of four columns: the slot swap stays inside the row
   const size_t band_bytes = (size_t)SP_ROWS * pg.tile_pitch * sizeof(__nv_bfloat16);
   const size_t smem = ST_W_BYTES + 2 * (size_t)pg.seg_rows * 128 + band_bytes + 1024;
   if (pg.seg_rows > 256 || pg.sub > ST_SLOTS || smem > 220 * 1024) return (int)cudaErrorNotSupported;

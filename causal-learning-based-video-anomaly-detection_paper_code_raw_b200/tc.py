@@ -144,12 +144,11 @@ class _BackboneBF16(torch.autograd.Function):
             raw = torch.empty((N, ho + 2, wo + 2, cout), device=dev, dtype=BF16)
             mean = torch.empty(cout, device=dev, dtype=torch.float32)
             invstd = torch.empty_like(mean)
-            if bn.training and FUSED_STATS and cout in (32, 64, 128, 256):
-                # batch statistics straight from the convolution's epilogue (no second pass over raw), then the tiny finalize
+            fused = bn.training and FUSED_STATS and cout in (32, 64, 128, 256)
+            if fused:
+                # batch statistics straight from the convolution's epilogue (no second pass over raw); the finalize rides in the apply pass
                 ws = ops.bn_workspace(dev, cout)
                 _call("cvad_flat_conv3x3_fwd_stats_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, _ptr(ws), st)
-                _call("cvad_bn_finalize_f64", _ptr(ws), cout, float(N * ho * wo), float(bn.eps), float(bn.momentum), _ptr(mean), _ptr(invstd),
-                      _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(bn.num_batches_tracked), st)
             elif bn.training:
                 _call("cvad_flat_conv3x3_fwd_bf16", _ptr(a), _ptr(wf), _ptr(conv.bias), _ptr(raw), N, h, w, cin, cout, stride, st)
                 _call("cvad_pad_bn_stats_bf16", _ptr(raw), N, ho, wo, cout, _ptr(ops.bn_workspace(dev, cout)), float(bn.eps), float(bn.momentum),
@@ -159,8 +158,13 @@ class _BackboneBF16(torch.autograd.Function):
                 _call("cvad_bn_eval_prepare_f32", cout, float(bn.eps), _ptr(bn.running_mean), _ptr(bn.running_var), _ptr(mean), _ptr(invstd), st)
             phase_out = i + 1 < len(layers) and strides[i + 1] == 2
             act = torch.empty(act_shape(N, ho, wo, cout, phase_out), device=dev, dtype=BF16)
-            _call("cvad_pad_bn_apply_relu_bf16", _ptr(raw), _ptr(act), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd), _ptr(bn.weight),
-                  _ptr(bn.bias), st)
+            if fused:
+                _call("cvad_pad_bn_finalize_apply_relu_bf16", _ptr(raw), _ptr(act), N, ho, wo, cout, int(phase_out), _ptr(ws), float(bn.eps),
+                      float(bn.momentum), _ptr(bn.weight), _ptr(bn.bias), _ptr(mean), _ptr(invstd), _ptr(bn.running_mean), _ptr(bn.running_var),
+                      _ptr(bn.num_batches_tracked), st)
+            else:
+                _call("cvad_pad_bn_apply_relu_bf16", _ptr(raw), _ptr(act), N, ho, wo, cout, int(phase_out), _ptr(mean), _ptr(invstd),
+                      _ptr(bn.weight), _ptr(bn.bias), st)
             if need_bwd:
                 saved.append((a, raw, mean, invstd, wd, (h, w, cin, cout, stride, ho, wo), bn.training, phase_out))
             a, h, w, cin = act, ho, wo, cout

@@ -244,6 +244,13 @@ int cvad_flat_wgrad_mode(int kh_stack);
 /* batch statistics over the interior of a padded-flat raw tensor (N,H,W,C interior geometry) */
 int cvad_pad_bn_stats_bf16(const void* raw, int N, int H, int W, int C, double* ws, float eps, float momentum, float* mean, float* invstd,
                            float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+/* The finalize step (cvad_bn_finalize_f64) folded into the apply pass: ws still holds the raw fp64 sums of the batch (left by
+ * cvad_flat_conv3x3_fwd_stats_bf16); the kernel derives mean / invstd from them (same arithmetic, bit-identical activations), publishes
+ * them for the backward, updates the running statistics (cad:116,131-136 train-mode nn.BatchNorm2d) and re-zeroes ws -- one launch on the
+ * critical path of every layer instead of two. */
+int cvad_pad_bn_finalize_apply_relu_bf16(const void* raw, void* act, int N, int H, int W, int C, int phase_out, double* ws, float eps,
+                                         float momentum, const float* gamma, const float* beta, float* mean, float* invstd,
+                                         float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
 /* act = relu(bn(raw)) written padded-flat with zero border (phase_out = 0) or as the four phase planes (phase_out = 1) */
 int cvad_pad_bn_apply_relu_bf16(const void* raw, void* act, int N, int H, int W, int C, int phase_out, const float* mean, const float* invstd,
                                 const float* gamma, const float* beta, void* stream);
