@@ -1,0 +1,592 @@
+// Stem of the M-A backbone, second formulation: conv 7x7 stride 2 pad 3, 1 -> 32 channels (cad:115, 145) as a tcgen05 kind::f16 implicit
+// GEMM over a 2x4 space-to-depth of the frames, fused with the BatchNorm batch statistics (pass 1) or with BN + ReLU + MaxPool2d(3,2,1)
+// (pass 2, cad:116-118, 146-148).  Frames whose width is a multiple of 4 take this path; stem_tc.cu (kind::tf32 over a 2x2
+// space-to-depth) stays the general one.
+//
+// Why.  The tf32 form issues, per 128 output pixels, 8 MMAs of M128 x N32 x K8 whose operands (5 KB each) stream from shared memory:
+// 66 cycles apiece against 16 of math, and in pass 2 that stream plus the max-pool's parked band saturate the shared-memory pipe
+// (profiles/r02c_stem_pool_ncu_full.md).  Here X8[n][i][J][a*4+b] = x[n][2(i-2)+a][4(J-1)+b] (zero outside the frame) is an NHWC tensor
+// of fp16 with 8 channels = one 16-byte "pixel" that covers a 2 x 4 patch of the frame, i.e. TWO horizontally adjacent outputs of the
+// stride-2 convolution.  An accumulator row is such a pixel and carries N = 64 columns = (output parity p, channel), and over the flat
+// pixel index q of X8 (geometry (Ho+3) x (Wo/2+2) per frame)
+//        out[q][p*32 + c] = sum_{u<4, v<3} X8[q + u*Wq + v][0:8] * W8[u][v][p][c]      (kh = 2u+a-1, kw = 4v+b-2p-1)
+// is 6 MMAs of M128 x N64 x K16 per 128 pixels = 256 outputs (the two 16-byte K chunks of an MMA are the pixel rows u and u+1: LBO = one
+// row of X8): 2.3x fewer tensor-core cycles and 2.2x fewer operand bytes than the tf32 form.  Inputs are exact in fp16 whenever they are
+// exact in tf32 (both keep 11 significant bits; the loader's 0..255 grayscale values through Normalize(0.5, 0.5) are odd integers below
+// 512); weights are rounded to nearest fp16 where the tf32 MMA truncates.
+//
+// Kernels: persistent and warp-specialised like stem_tc.cu (warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM owner, warps 4-11
+// epilogue in two groups on alternate sub-tiles).  The pixel stream is copied by TMA as is; tcgen05.mma performs the im2col through its
+// no-swizzle K-major descriptors.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "cvad_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace cvad_tc;
+
+constexpr int S8_C = 32;              // output channels
+constexpr int S8_N = 64;              // accumulator columns: (parity, channel)
+constexpr int S8_K = 7;               // kernel size
+constexpr int S8_SLOTS = 8;           // TMEM accumulator ring (8 x 64 columns)
+constexpr int S8_SUB = 4;             // 128-pixel sub-tiles per tile (pass 1)
+constexpr int S8_MMAS = 6;            // (u0 in {0,2}) x (v in {0,1,2})
+constexpr int S8_W_BYTES = S8_MMAS * 2048;   // [mma][2 K chunks][64 rows][16 B]
+constexpr int S8_P = 4;               // pooled rows per band (pass 2)
+constexpr int S8_ROWS = 2 * S8_P + 1; // convolution rows per band
+
+struct Geo8 {
+  int N, H, W, Ho, Wo, Wh, Hq, Wq;    // Wh = outputs pairs per row, Wq = Wh + 2
+  long long np;                        // N*Hq*Wq pixels of X8 (= GEMM rows incl. junk)
+  long long n_tiles;
+  int seg_rows;                        // 128-byte rows (8 pixels) per stream segment of pass 1
+};
+
+struct Pool8 {
+  int PH, PW, bands_per_frame, sub, seg_rows, tile_pitch;
+  long long n_items;
+};
+
+// x (N,1,H,W) fp32 or uint8 -> X8 (N,Hq,Wq,8) fp16: one 16-byte pixel per thread; W % 4 == 0, so a pixel's four columns are one aligned
+// 16-byte (fp32) / 4-byte (uint8) load per frame row.  uint8: x = (float(v) - mean) / std as torchvision's Normalize computes it.
+template <bool U8>
+__global__ void stem8_s2d_kernel(const void* __restrict__ xin, Geo8 g, float mean, float stdv, uint4* __restrict__ x8) {
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.np; t += (long long)gridDim.x * blockDim.x) {
+    const int J = (int)(t % g.Wq);
+    const long long r = t / g.Wq;
+    const int i = (int)(r % g.Hq), n = (int)(r / g.Hq);
+    const int h0 = 2 * (i - 2), w0 = 4 * (J - 1);
+    float v[8];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int h = h0 + a;
+      const bool ok = (unsigned)h < (unsigned)g.H && w0 >= 0 && w0 < g.W;
+      if (!ok) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[a * 4 + b] = 0.f;
+      } else if (U8) {
+        const unsigned q = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(xin) + ((long long)n * g.H + h) * g.W + w0));
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[a * 4 + b] = ((float)((q >> (8 * b)) & 255u) - mean) / stdv;
+      } else {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + ((long long)n * g.H + h) * g.W + w0));
+        v[a * 4 + 0] = q.x; v[a * 4 + 1] = q.y; v[a * 4 + 2] = q.z; v[a * 4 + 3] = q.w;
+      }
+    }
+    uint4 o;
+    __half2* hp = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) hp[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    x8[t] = o;
+  }
+}
+
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// conv1 weights (32,1,7,7) fp32 -> shared memory [mma = (u0/2)*3 + v][chunk c][n = p*32 + cout][e = a*4 + b] fp16
+__device__ __forceinline__ void stage_weights8(const float* __restrict__ w, uint8_t* smem_w) {
+  __half* dst = reinterpret_cast<__half*>(smem_w);
+  for (int i = threadIdx.x; i < S8_MMAS * 2 * S8_N * 8; i += blockDim.x) {
+    const int e = i & 7, n = (i >> 3) & 63, c = (i >> 9) & 1, m = i >> 10;
+    const int u = 2 * (m / 3) + c, v = m % 3, a = e >> 2, b = e & 3, p = n >> 5, co = n & 31;
+    const int kh = 2 * u + a - 1, kw = 4 * v + b - 2 * p - 1;
+    const float val = ((unsigned)kh < (unsigned)S8_K && (unsigned)kw < (unsigned)S8_K) ? w[co * S8_K * S8_K + kh * S8_K + kw] : 0.f;
+    dst[i] = __float2half_rn(val);
+  }
+}
+
+__device__ __forceinline__ uint32_t idesc_f16_m128_n64() {
+  uint32_t d = 0;
+  d |= 1u << 4;                         // D = f32; A = B = f16 (format 0), both K-major
+  d |= (uint32_t)(S8_N >> 3) << 17;
+  d |= (uint32_t)(128 >> 4) << 24;
+  return d;
+}
+
+// the six MMAs of one 128-pixel sub-tile whose first pixel sits at shared-memory address a0 (16-byte pixels)
+__device__ __forceinline__ void issue_subtile8(uint32_t tmem_acc, uint32_t a0, uint32_t s_w, int Wq, uint64_t da_hi, uint64_t db_hi, uint32_t idesc) {
+#pragma unroll
+  for (int m = 0; m < S8_MMAS; ++m) {
+    const uint32_t a_addr = a0 + (uint32_t)(2 * (m / 3) * Wq + (m % 3)) * 16;
+    const uint64_t da = da_hi | (uint64_t)((a_addr >> 4) & 0x3FFF);
+    const uint64_t db = db_hi | (uint64_t)(((s_w + m * 2048) >> 4) & 0x3FFF);
+    tc_mma_f16(tmem_acc, da, db, idesc, m != 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pass 1: batch statistics
+__global__ void __launch_bounds__(384, 1) stem8_stats_kernel(const __grid_constant__ CUtensorMap map_x8, const float* __restrict__ w, Geo8 g,
+                                                             double* __restrict__ ws) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_seg_full[2], bar_seg_empty[2], bar_acc_full[S8_SLOTS], bar_acc_empty[S8_SLOTS];
+  __shared__ uint32_t tmem_base_sh;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t seg_bytes = (uint32_t)g.seg_rows * 128;
+  const uint32_t s_w = smem_base, s_seg = smem_base + S8_W_BYTES;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  constexpr int MT = 128 * S8_SUB;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_seg_full[i], 1); mbar_init(&bar_seg_empty[i], 1); }
+    for (int i = 0; i < S8_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+    fence_barrier_init();
+    prefetch_tmap(&map_x8);
+  }
+  stage_weights8(w, smem_gen);
+  if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    uint32_t cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_empty[st], ((cnt >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&bar_seg_full[st], seg_bytes);
+        tma_load_2d(s_seg + st * seg_bytes, &map_x8, 0, (int)(t * (MT / 8)), &bar_seg_full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_f16_m128_n64();
+    const uint64_t da_hi = make_smem_desc(0, (uint32_t)g.Wq * 16, 128, UMMA_NOSW);    // K chunk 1 = the pixel one X8 row below
+    const uint64_t db_hi = make_smem_desc(0, 1024, 128, UMMA_NOSW);
+    uint32_t cnt = 0, acc_cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_full[st], (cnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t seg = s_seg + st * seg_bytes;
+      for (int s = 0; s < S8_SUB; ++s) {
+        const uint32_t use = acc_cnt + s;
+        const int slot = use % S8_SLOTS;
+        mbar_wait(&bar_acc_empty[slot], ((use / S8_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_subtile8(tmem_base + slot * S8_N, seg + (uint32_t)(s * 128) * 16, s_w, g.Wq, da_hi, db_hi, idesc);
+          tc_commit(&bar_acc_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&bar_seg_empty[st]);
+      __syncwarp();
+      acc_cnt += S8_SUB;
+    }
+  } else if (warp >= 4) {
+    const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
+    float s[S8_C], q[S8_C];                    // per-channel sum / sum of squares over this thread's valid outputs
+#pragma unroll
+    for (int c = 0; c < S8_C; ++c) { s[c] = 0.f; q[c] = 0.f; }
+    const int frame = g.Hq * g.Wq;
+    uint32_t acc_cnt = 0;
+    for (long long t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+      for (int sb = eg; sb < S8_SUB; sb += 2) {
+        const uint32_t use = acc_cnt + sb;
+        const int slot = use % S8_SLOTS;
+        mbar_wait(&bar_acc_full[slot], (use / S8_SLOTS) & 1);
+        tc_fence_after();
+        uint32_t a[4][16];
+        const uint32_t taddr = tmem_base + slot * S8_N + ((uint32_t)(ew * 32) << 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_ld16(taddr + 16 * k, a[k]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_acc_empty[slot]);
+        const uint32_t qq = (uint32_t)(t * MT) + sb * 128 + ew * 32 + lane;
+        const uint32_t n = qq / (uint32_t)frame;
+        const uint32_t rem = qq - n * (uint32_t)frame;
+        const int i = (int)(rem / (uint32_t)g.Wq), J = (int)(rem - (uint32_t)i * (uint32_t)g.Wq);
+        if ((long long)qq < g.np && i < g.Ho && J < g.Wh) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float y0 = __uint_as_float(a[0][c]), y1 = __uint_as_float(a[1][c]);
+            s[c] += y0; q[c] = fmaf(y0, y0, q[c]);
+            s[16 + c] += y1; q[16 + c] = fmaf(y1, y1, q[16 + c]);
+          }
+          if (2 * J + 1 < g.Wo) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float y0 = __uint_as_float(a[2][c]), y1 = __uint_as_float(a[3][c]);
+              s[c] += y0; q[c] = fmaf(y0, y0, q[c]);
+              s[16 + c] += y1; q[16 + c] = fmaf(y1, y1, q[16 + c]);
+            }
+          }
+        }
+      }
+      acc_cnt += S8_SUB;
+    }
+    // CTA reduction over the 256 row-threads (the stream segments are free: every MMA retired before its acc_full fired)
+    float* red = reinterpret_cast<float*>(smem_gen + S8_W_BYTES);          // [256][65]
+    const int r = tid - 128;
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < S8_C; ++c) { red[r * 65 + c] = s[c]; red[r * 65 + 32 + c] = q[c]; }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    if (r < 64) {
+      double acc = 0.0;
+      for (int k = 0; k < 256; ++k) acc += (double)red[k * 65 + r];
+      atomicAdd(ws + r, acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ pass 2: BN + ReLU + MaxPool2d(3,2,1)
+// A work item is a BAND of one frame: S8_P pooled rows = the 2*S8_P + 1 convolution rows 2*S8_P*b - 1 .. 2*S8_P*b + 2*S8_P - 1 (one row of
+// overlap with the next band).  Its pixels are contiguous in the flat X8 index: one TMA box per band, `sub` sub-tiles of 128 pixels,
+// six MMAs each.  The epilogue applies BN + ReLU and parks the band as bf16 [row][column][32] in shared memory; when the band is complete
+// the eight epilogue warps pool it (post-ReLU values: an absent neighbour is a 0) and write the padded-flat rows of layer1's input.
+// Band layout: column wo lives in the 64-byte slot wo ^ ((wo >> 1) & 1) of its row and its four 16-byte vectors are XOR-swizzled by
+// (wo >> 2) & 3: the parking stores (lanes = pixels = columns two apart, one parity at a time) and the pooling reads (columns two apart)
+// are both bank-conflict free.
+__global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constant__ CUtensorMap map_x8, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, Geo8 g, Pool8 pg, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_seg_full[2], bar_seg_empty[2], bar_acc_full[S8_SLOTS], bar_acc_empty[S8_SLOTS];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float s_sc[S8_C], s_sh[S8_C];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t seg_bytes = (uint32_t)pg.seg_rows * 128;
+  const uint32_t s_w = smem_base, s_seg = smem_base + S8_W_BYTES;
+  __nv_bfloat16* band = reinterpret_cast<__nv_bfloat16*>(smem_gen + S8_W_BYTES + 2 * seg_bytes);       // [S8_ROWS][tile_pitch]
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int sub = pg.sub;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_seg_full[i], 1); mbar_init(&bar_seg_empty[i], 1); }
+    for (int i = 0; i < S8_SLOTS; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 128); }
+    fence_barrier_init();
+    prefetch_tmap(&map_x8);
+  }
+  if (tid < S8_C) {
+    const float sc = invstd[tid] * gamma[tid];
+    s_sc[tid] = sc;
+    s_sh[tid] = (bias[tid] - mean[tid]) * sc + beta[tid];
+  }
+  stage_weights8(w, smem_gen);
+  if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  // first flat X8 pixel of work item t (negative for the first band of the first frame: TMA zero-fills)
+  auto item_start = [&](long long t) -> long long {
+    const long long n = t / pg.bands_per_frame;
+    const int b = (int)(t - n * pg.bands_per_frame);
+    return (n * g.Hq + (2 * S8_P * b - 1)) * (long long)g.Wq;
+  };
+
+  if (warp == 0) {
+    uint32_t cnt = 0;
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      mbar_wait(&bar_seg_empty[st], ((cnt >> 1) & 1) ^ 1);
+      if (elect_one()) {
+        const long long p0 = item_start(t);
+        const long long row = p0 >= 0 ? p0 / 8 : -((-p0 + 7) / 8);          // floor(p0 / 8)
+        mbar_expect_tx(&bar_seg_full[st], seg_bytes);
+        tma_load_2d(s_seg + st * seg_bytes, &map_x8, 0, (int)row, &bar_seg_full[st]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_f16_m128_n64();
+    const uint64_t da_hi = make_smem_desc(0, (uint32_t)g.Wq * 16, 128, UMMA_NOSW);
+    const uint64_t db_hi = make_smem_desc(0, 1024, 128, UMMA_NOSW);
+    uint32_t cnt = 0, acc_cnt = 0;
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x, ++cnt) {
+      const int st = cnt & 1;
+      const long long p0 = item_start(t);
+      const long long row = p0 >= 0 ? p0 / 8 : -((-p0 + 7) / 8);
+      const int off = (int)(p0 - row * 8);                          // 0..7 pixels into the box
+      mbar_wait(&bar_seg_full[st], (cnt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t seg = s_seg + st * seg_bytes;
+      for (int s = 0; s < sub; ++s) {
+        const uint32_t use = acc_cnt + s;
+        const int slot = use % S8_SLOTS;
+        mbar_wait(&bar_acc_empty[slot], ((use / S8_SLOTS) & 1) ^ 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_subtile8(tmem_base + slot * S8_N, seg + (uint32_t)(off + s * 128) * 16, s_w, g.Wq, da_hi, db_hi, idesc);
+          tc_commit(&bar_acc_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tc_commit(&bar_seg_empty[st]);
+      __syncwarp();
+      acc_cnt += sub;
+    }
+  } else if (warp >= 4) {
+    const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
+    const int et = tid - 128;                                       // 0..255 among the epilogue threads
+    uint32_t acc_cnt = 0;
+    const int groups = S8_C / 8;                                    // 16-byte vectors per pixel
+    float rs[S8_C], rq[S8_C];                                       // BatchNorm scale / shift in registers
+#pragma unroll
+    for (int c = 0; c < S8_C; ++c) { rs[c] = s_sc[c]; rq[c] = s_sh[c]; }
+    for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x) {
+      const long long n = t / pg.bands_per_frame;
+      const int b = (int)(t - n * pg.bands_per_frame);
+      const int i0 = 2 * S8_P * b - 1;                              // first convolution row of the band
+      for (int sb = eg; sb < sub; sb += 2) {
+        const uint32_t use = acc_cnt + sb;
+        const int slot = use % S8_SLOTS;
+        mbar_wait(&bar_acc_full[slot], (use / S8_SLOTS) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + slot * S8_N + ((uint32_t)(ew * 32) << 16);
+        const int ql = sb * 128 + ew * 32 + lane;                   // pixel inside the band
+        const int r = ql / g.Wq, J = ql - r * g.Wq;
+        const bool row_in = r < S8_ROWS && J < g.Wh;
+        const bool live = row_in && i0 + r >= 0 && i0 + r < g.Ho;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {                               // the pixel's two outputs, one after the other (register budget)
+          uint32_t a0[16], a1[16];
+          tmem_ld16(taddr + 32 * p, a0);
+          tmem_ld16(taddr + 32 * p + 16, a1);
+          tmem_ld_wait();
+          if (p == 1) {
+            tc_fence_before();
+            mbar_arrive(&bar_acc_empty[slot]);
+          }
+          const int wo = 2 * J + p;
+          if (row_in && wo < g.Wo) {
+            uint32_t pk[16];
+            if (live) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), rs[2 * c], rq[2 * c]), 0.f);
+                const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
+                const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
+                const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
+                pk[c] = *reinterpret_cast<uint32_t*>(&h0);
+                pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) pk[c] = 0u;             // rows outside the frame: post-ReLU zeros never win a max
+            }
+            uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)(wo ^ ((wo >> 1) & 1)) * S8_C);
+            const int sw = (wo >> 2) & 3;
+            o[0 ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1 ^ sw] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            o[2 ^ sw] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+            o[3 ^ sw] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+          }
+        }
+      }
+      acc_cnt += sub;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band is complete
+      // ---- pool: pooled rows S8_P*b .. S8_P*b + S8_P - 1 (band rows 2k, 2k+1, 2k+2 for the k-th of them), padded-flat output
+      const int rowlen = (pg.PW + 2) * groups;                       // vectors per padded output row
+      for (int v = et; v < S8_P * rowlen; v += 256) {
+        const int k = v / rowlen, vv = v - k * rowlen;
+        const int ph = S8_P * b + k;
+        if (ph >= pg.PH) continue;
+        const int pwp = vv / groups, cg = vv - pwp * groups;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (pwp >= 1 && pwp <= pg.PW) {
+          const int pw = pwp - 1;
+          // all nine loads before the first max; a window column outside the frame is clamped onto its in-frame neighbour
+          uint4 tv[9];
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb) {
+            int ww = 2 * pw - 1 + bb;
+            ww = ww < 0 ? 0 : (ww >= g.Wo ? g.Wo - 1 : ww);
+            const int off = (ww ^ ((ww >> 1) & 1)) * S8_C + ((cg ^ ((ww >> 2) & 3)) * 8);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) tv[a * 3 + bb] = *reinterpret_cast<const uint4*>(band + (size_t)(2 * k + a) * pg.tile_pitch + off);
+          }
+          __nv_bfloat162 best[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) best[i] = reinterpret_cast<const __nv_bfloat162*>(&tv[0])[i];
+#pragma unroll
+          for (int t9 = 1; t9 < 9; ++t9)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], reinterpret_cast<const __nv_bfloat162*>(&tv[t9])[i]);
+          o = *reinterpret_cast<uint4*>(best);
+        }
+        reinterpret_cast<uint4*>(out)[((n * (pg.PH + 2) + ph + 1) * (long long)rowlen) + vv] = o;
+      }
+      // the frame's top / bottom border rows belong to its first / last band
+      if (b == 0)
+        for (int v = et; v < rowlen; v += 256) reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2)) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
+      if (b == pg.bands_per_frame - 1)
+        for (int v = et; v < rowlen; v += 256)
+          reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2) + pg.PH + 1) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band buffer may be overwritten
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ws holds sum / sum of squares of the RAW accumulator; y = acc + bias: mean_y = mean_acc + b, var_y = var_acc
+__global__ void stem8_finalize_kernel(double* __restrict__ ws, const float* __restrict__ bias, double count, float eps, float momentum,
+                                      float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                      float* __restrict__ running_var, long long* __restrict__ nbt) {
+  const int c = threadIdx.x;
+  if (c < S8_C) {
+    const double ma = ws[c] / count;
+    double var = ws[S8_C + c] / count - ma * ma;
+    if (var < 0.0) var = 0.0;
+    const double m = ma + (double)bias[c];
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+    ws[c] = 0.0;
+    ws[S8_C + c] = 0.0;
+  }
+  if (c == 0 && nbt) *nbt += 1;
+}
+
+int geo8(Geo8& g, int N, int H, int W) {
+  if (N <= 0 || H <= 0 || W <= 0 || (W & 3)) return 1;
+  g.N = N; g.H = H; g.W = W;
+  g.Ho = (H - 1) / 2 + 1;
+  g.Wo = (W - 1) / 2 + 1;
+  g.Wh = (g.Wo + 1) / 2;
+  g.Hq = g.Ho + 3;
+  g.Wq = g.Wh + 2;
+  g.np = (long long)N * g.Hq * g.Wq;
+  const int MT = 128 * S8_SUB;
+  g.n_tiles = (g.np + MT - 1) / MT;
+  const int seg_px = MT + 3 * g.Wq + 2;
+  g.seg_rows = (seg_px + 7) / 8;
+  if (g.seg_rows > 256 || g.np + MT > 0x7fffffffLL) return 1;
+  return 0;
+}
+
+int make_map8(CUtensorMap* mx, const void* x8, const Geo8& g, int box_rows) {
+  // X8 as a matrix of 128-byte rows (8 pixels); the last partial row is covered by the buffer's slack
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return (int)cudaErrorNotSupported;
+  memset(mx, 0, sizeof(*mx));
+  cuuint64_t dims[2] = {32, (cuuint64_t)((g.np + 7) / 8)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(x8), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+// pass-2 geometry; false when a band does not fit one TMA box / the accumulator ring / shared memory (very wide frames)
+bool pool8_geo(const Geo8& g, Pool8& pg, size_t& smem) {
+  pg.PH = (g.Ho - 1) / 2 + 1;
+  pg.PW = (g.Wo - 1) / 2 + 1;
+  pg.bands_per_frame = (pg.PH + S8_P - 1) / S8_P;
+  pg.n_items = (long long)g.N * pg.bands_per_frame;
+  pg.sub = (S8_ROWS * g.Wq + 127) / 128;
+  const int seg_px = 128 * pg.sub + 3 * g.Wq + 2 + 8;              // + the pixel remainder of the box's 128-byte alignment
+  pg.seg_rows = (seg_px + 7) / 8;
+  pg.tile_pitch = ((g.Wo + 3) & ~3) * S8_C;
+  const size_t band_bytes = (size_t)S8_ROWS * pg.tile_pitch * sizeof(__nv_bfloat16);
+  smem = S8_W_BYTES + 2 * (size_t)pg.seg_rows * 128 + band_bytes + 1024;
+  return pg.seg_rows <= 256 && pg.sub <= S8_SLOTS && smem <= 220 * 1024;
+}
+
+}  // namespace
+
+// bytes of the X8 buffer for (N,1,H,W) frames (incl. the slack the last TMA row needs), or -1 when the shape is outside this path's range
+// (W not a multiple of 4, very wide frames): callers then use the tf32 stem
+CVAD_API long long cvad_stem8_bytes(int N, int H, int W) {
+  Geo8 g;
+  Pool8 pg;
+  size_t smem;
+  if (geo8(g, N, H, W) || !pool8_geo(g, pg, smem)) return -1;
+  return ((g.np + 7) / 8) * 128 + 128;
+}
+
+CVAD_API int cvad_stem8_space_to_depth_f32(const float* x, int N, int H, int W, void* x8, void* stream) {
+  Geo8 g;
+  if (geo8(g, N, H, W) || ((uintptr_t)x & 15)) return (int)cudaErrorInvalidValue;
+  long long blocks = (g.np + 255) / 256;
+  if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
+  stem8_s2d_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, g, 0.f, 1.f, reinterpret_cast<uint4*>(x8));
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_stem8_space_to_depth_u8(const void* x, int N, int H, int W, float mean, float stdv, void* x8, void* stream) {
+  Geo8 g;
+  if (geo8(g, N, H, W) || stdv == 0.f || ((uintptr_t)x & 3)) return (int)cudaErrorInvalidValue;
+  long long blocks = (g.np + 255) / 256;
+  if (blocks > 16LL * cvad_num_sms()) blocks = 16LL * cvad_num_sms();
+  stem8_s2d_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, g, mean, stdv, reinterpret_cast<uint4*>(x8));
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_stem8_f16_stats(const void* x8, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
+                                  float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                                  void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  Geo8 g;
+  if (geo8(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  CUtensorMap mx;
+  int e = make_map8(&mx, x8, g, g.seg_rows);
+  if (e) return e;
+  size_t smem = S8_W_BYTES + 2 * (size_t)g.seg_rows * 128 + 1024;
+  const size_t red = S8_W_BYTES + 256 * 65 * 4 + 1024;
+  if (smem < red) smem = red;
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(stem8_stats_kernel, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
+  long long grid = cvad_num_sms();
+  if (grid > g.n_tiles) grid = g.n_tiles;
+  stem8_stats_kernel<<<(unsigned)grid, 384, smem, st>>>(mx, w, g, ws);
+  CVAD_LAUNCH_CHECK();
+  stem8_finalize_kernel<<<1, 32, 0, st>>>(ws, bias, (double)N * g.Ho * g.Wo, eps, momentum, mean, invstd, running_mean, running_var,
+                                          num_batches_tracked);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}
+
+CVAD_API int cvad_stem8_f16_bn_relu_maxpool(const void* x8, const float* w, const float* bias, int N, int H, int W, const float* mean,
+                                            const float* invstd, const float* gamma, const float* beta, void* out, void* stream) {
+  Geo8 g;
+  if (geo8(g, N, H, W)) return (int)cudaErrorInvalidValue;
+  Pool8 pg;
+  size_t smem;
+  if (!pool8_geo(g, pg, smem)) return (int)cudaErrorNotSupported;
+  CUtensorMap mx;
+  int e = make_map8(&mx, x8, g, pg.seg_rows);
+  if (e) return e;
+  static size_t configured[CVAD_MAX_DEVICES] = {};
+  const cudaError_t ce = cvad_ensure_dyn_smem(stem8_pool_kernel, smem, configured);
+  if (ce != cudaSuccess) return (int)ce;
+  long long grid = cvad_num_sms();
+  if (grid > pg.n_items) grid = pg.n_items;
+  stem8_pool_kernel<<<(unsigned)grid, 384, smem, (cudaStream_t)stream>>>(mx, w, bias, g, pg, mean, invstd, gamma, beta, (__nv_bfloat16*)out);
+  CVAD_LAUNCH_CHECK();
+  return 0;
+}

@@ -39,6 +39,7 @@ def _wgrad_scratch(device, cin, cout):
 
 
 STEM_FUSED_POOL = os.environ.get("CVAD_STEM_FUSED_POOL", "1") != "0"   # stem pass 2 + max-pool as one kernel
+STEM_F16 = os.environ.get("CVAD_STEM_F16", "1") != "0"                 # fp16 stem over a 2x4 space-to-depth (frame width % 4 == 0)
 FUSED_STATS = os.environ.get("CVAD_FUSED_BN_STATS", "1") != "0"     # BatchNorm batch statistics from the convolution epilogue
 # weight-gradient GEMMs on a side stream: wgrad_i needs only draw_i and a_{i-1}, so it can run beside the HBM-bound BatchNorm backward of
 # the next layer down instead of in front of it (a parallel branch of the captured step graph)
@@ -106,34 +107,53 @@ class _BackboneBF16(torch.autograd.Function):
         mean = torch.empty(C1, device=dev, dtype=torch.float32)
         invstd = torch.empty_like(mean)
         w1, b1 = conv1.weight.detach(), conv1.bias.detach()
-        n4 = int(ops.L().cvad_stem_x4_floats(N, H, W))
-        if n4 < 0:
-            raise RuntimeError(f"frame size {H}x{W} is outside the tensor-core stem's range")
-        x4 = torch.empty(n4, device=dev, dtype=torch.float32)       # 2x2 space-to-depth of the batch: 16-byte pixels
-        if x.dtype == torch.uint8:      # raw frames: Normalize(mean, std) of cad:1177-1179 applied on the fly
-            _call("cvad_stem_space_to_depth_u8", _ptr(x), N, H, W, float(bb.input_mean), float(bb.input_std), _ptr(x4), st)
-        else:
-            _call("cvad_stem_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x4), st)
-        x = x4
-        if bn1.training:
-            _call("cvad_stem_tf32_stats", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps),
-                  float(bn1.momentum), _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
-        else:
-            _call("cvad_bn_eval_prepare_f32", C1, float(bn1.eps), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(mean), _ptr(invstd), st)
         h, w = out_hw(H1, W1, 2)
         a = torch.empty(act_shape(N, h, w, C1, False), device=dev, dtype=BF16)
-        fused = 801
-        if STEM_FUSED_POOL:
-            # pass 2 and MaxPool(3,2,1) in one kernel: the 708 MB tensor between them stays in shared memory (801 = a band does not fit)
-            fused = _call("cvad_stem_tf32_bn_relu_maxpool", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight),
-                          _ptr(bn1.bias), _ptr(a), st, accept=(801,))
-        y1 = None
-        if fused == 801:
-            y1 = torch.empty((N, H1, W1, C1), device=dev, dtype=BF16)
-            _call("cvad_stem_tf32_bn_relu", _ptr(x), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
-                  _ptr(y1), st)
-            _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
-        del y1, x4, x
+
+        def bn1_statistics(entry, xs):
+            if bn1.training:
+                _call(entry, _ptr(xs), _ptr(w1), _ptr(b1), N, H, W, _ptr(ops.bn_workspace(dev, C1)), float(bn1.eps), float(bn1.momentum),
+                      _ptr(mean), _ptr(invstd), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(bn1.num_batches_tracked), st)
+            else:
+                _call("cvad_bn_eval_prepare_f32", C1, float(bn1.eps), _ptr(bn1.running_mean), _ptr(bn1.running_var), _ptr(mean), _ptr(invstd), st)
+
+        done = False
+        n8 = int(ops.L().cvad_stem8_bytes(N, H, W)) if (STEM_F16 and STEM_FUSED_POOL) else -1
+        if n8 >= 0:
+            # fp16 stem over a 2x4 space-to-depth (frame width a multiple of 4): 6 MMAs of N = 64 per 256 outputs, pass 2 fused with the pool
+            x8 = torch.empty(n8, device=dev, dtype=torch.uint8)
+            if x.dtype == torch.uint8:  # raw frames: Normalize(mean, std) of cad:1177-1179 applied on the fly
+                _call("cvad_stem8_space_to_depth_u8", _ptr(x), N, H, W, float(bb.input_mean), float(bb.input_std), _ptr(x8), st)
+            else:
+                _call("cvad_stem8_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x8), st)
+            bn1_statistics("cvad_stem8_f16_stats", x8)
+            _call("cvad_stem8_f16_bn_relu_maxpool", _ptr(x8), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight),
+                  _ptr(bn1.bias), _ptr(a), st)
+            done = True
+            del x8
+        if not done:
+            n4 = int(ops.L().cvad_stem_x4_floats(N, H, W))
+            if n4 < 0:
+                raise RuntimeError(f"frame size {H}x{W} is outside the tensor-core stem's range")
+            x4 = torch.empty(n4, device=dev, dtype=torch.float32)       # 2x2 space-to-depth of the batch: 16-byte pixels
+            if x.dtype == torch.uint8:
+                _call("cvad_stem_space_to_depth_u8", _ptr(x), N, H, W, float(bb.input_mean), float(bb.input_std), _ptr(x4), st)
+            else:
+                _call("cvad_stem_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x4), st)
+            bn1_statistics("cvad_stem_tf32_stats", x4)
+            fused = 801
+            if STEM_FUSED_POOL:
+                # pass 2 and MaxPool(3,2,1) in one kernel: the 708 MB tensor between them stays in shared memory (801 = a band does not fit)
+                fused = _call("cvad_stem_tf32_bn_relu_maxpool", _ptr(x4), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight),
+                              _ptr(bn1.bias), _ptr(a), st, accept=(801,))
+            if fused == 801:
+                y1 = torch.empty((N, H1, W1, C1), device=dev, dtype=BF16)
+                _call("cvad_stem_tf32_bn_relu", _ptr(x4), _ptr(w1), _ptr(b1), N, H, W, _ptr(mean), _ptr(invstd), _ptr(bn1.weight), _ptr(bn1.bias),
+                      _ptr(y1), st)
+                _call("cvad_pad_maxpool3x3s2_bf16", _ptr(y1), N, H1, W1, C1, _ptr(a), st)
+                del y1
+            del x4
+        del x
         cur.wait_stream(side)
         saved = []
         cin = C1

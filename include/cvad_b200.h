@@ -284,6 +284,19 @@ int cvad_stem_tf32_bn_relu(const float* x4, const float* w, const float* bias, i
  * frame does not fit in shared memory: use the two calls above / below instead. */
 int cvad_stem_tf32_bn_relu_maxpool(const float* x4, const float* w, const float* bias, int N, int H, int W, const float* mean,
                                    const float* invstd, const float* gamma, const float* beta, void* out, void* stream);
+
+/* The stem's second formulation (stem_f16_tc.cu): tcgen05 kind::f16 over a 2x4 space-to-depth X8 of the frames (fp16, one 16-byte pixel =
+ * a 2 x 4 patch = two adjacent outputs of the stride-2 convolution; accumulator rows carry N = 64 columns = (output parity, channel)):
+ * 6 MMAs of M128 x N64 x K16 per 256 outputs instead of 16 of M128 x N32 x K8.  For frames whose width is a multiple of 4;
+ * cvad_stem8_bytes returns the size of the X8 buffer or -1 when the shape is outside this path (callers then use the tf32 entries above).
+ * Same contracts as cvad_stem_space_to_depth_*, cvad_stem_tf32_stats and cvad_stem_tf32_bn_relu_maxpool (cad:115-118, 145-148). */
+long long cvad_stem8_bytes(int N, int H, int W);
+int cvad_stem8_space_to_depth_f32(const float* x, int N, int H, int W, void* x8, void* stream);
+int cvad_stem8_space_to_depth_u8(const void* x, int N, int H, int W, float mean, float stdv, void* x8, void* stream);
+int cvad_stem8_f16_stats(const void* x8, const float* w, const float* bias, int N, int H, int W, double* ws, float eps, float momentum,
+                         float* mean, float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked, void* stream);
+int cvad_stem8_f16_bn_relu_maxpool(const void* x8, const float* w, const float* bias, int N, int H, int W, const float* mean,
+                                   const float* invstd, const float* gamma, const float* beta, void* out, void* stream);
 int cvad_pad_maxpool3x3s2_bf16(const void* y, int N, int H, int W, int C, void* out, void* stream);
 
 /* ---- M-D: conv autoencoder + LSTM + memory bank (md_kernels.cu), causal_anomaly_detection1.py --------------------------------

