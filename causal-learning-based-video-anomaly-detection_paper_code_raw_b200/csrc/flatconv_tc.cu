@@ -359,6 +359,12 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
 #pragma unroll
     for (int i = 0; i < N / 16; ++i) { st_s[i] = 0.f; st_q[i] = 0.f; }
 
+    // The bias add reads its operand from shared memory as a broadcast: N wavefronts per warp and sub-tile on the pipe that also
+    // feeds the MMAs their operands (+18 % at N = 32).  Data-gradients have no bias (has_bias = false skips the reads); at N = 32 the
+    // bias lives in registers.
+    const bool has_bias = bias != nullptr;
+    constexpr bool BIAS_REGS = N == 32;
+    float rb[BIAS_REGS ? N : 1];
     for (long long wi = blockIdx.x; wi < total; wi += gridDim.x) {
       FC_DECODE(wi, g, q0, nb)
       if (nb != cur_nb) {                       // stage this n-block's bias once (epilogue warps only: named barrier 1)
@@ -366,6 +372,10 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
         for (int i = tid - 128; i < N; i += 256) s_bias[i] = bias ? __ldg(bias + nb * N + i) : 0.f;
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         cur_nb = nb;
+        if (BIAS_REGS) {
+#pragma unroll
+          for (int i = 0; i < (BIAS_REGS ? N : 1); ++i) rb[i] = s_bias[i];
+        }
       }
       for (int idx = eg; idx < item_slots; idx += 2) {        // accumulator sets in the order the MMA warp completes them
         const int a = idx / sub, s = idx - a * sub;
@@ -419,7 +429,14 @@ __global__ void __launch_bounds__(384, 1) flatconv_kernel(const __grid_constant_
           uint32_t pk[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float a = __uint_as_float(v[2 * i]) + s_bias[c0 + 2 * i], b = __uint_as_float(v[2 * i + 1]) + s_bias[c0 + 2 * i + 1];
+            float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+            if (BIAS_REGS) {
+              a += rb[BIAS_REGS ? c0 + 2 * i : 0];
+              b += rb[BIAS_REGS ? c0 + 2 * i + 1 : 0];
+            } else if (has_bias) {
+              a += s_bias[c0 + 2 * i];
+              b += s_bias[c0 + 2 * i + 1];
+            }
             __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
             pk[i] = *reinterpret_cast<uint32_t*>(&h);
           }

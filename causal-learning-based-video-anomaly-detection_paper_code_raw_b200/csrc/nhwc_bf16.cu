@@ -445,6 +445,43 @@ __global__ void avgpool_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int 
     for (int i = 0; i < 8; ++i) out[(((long long)n * C + cg * 8 + i) * OH + oh) * OW + ow] = s[i] * inv;
   }
 }
+// The same, one block per frame: the (C, OH, OW) outputs of a frame are contiguous in the result, so they are collected in shared memory
+// ([bin][channel], pitch C + 4) and written as one coalesced run -- the kernel above writes eight 4-byte values 4*OH*OW bytes apart per
+// thread (one 32-byte sector per value: 31 -> 12 us at 512 x 8x12x256).
+__global__ void avgpool_pad_fwd_frame_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int OH, int OW,
+                                             float* __restrict__ out) {
+  extern __shared__ __align__(16) float sp[];             // [OH*OW][C + 4]
+  const int bins = OH * OW, groups = C >> 3, Wp = W + 2, Hp = H + 2, pitch = C + 4;
+  for (int n = blockIdx.x; n < N; n += gridDim.x) {
+    for (int t = threadIdx.x; t < bins * groups; t += blockDim.x) {
+      const int cg = t % groups, b = t / groups;
+      const int oh = b / OW, ow = b - oh * OW;
+      const int h0 = bstart(oh, H, OH), h1 = bend(oh, H, OH), w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
+      float s[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = 0.f;
+      for (int h = h0; h < h1; ++h)
+        for (int w = w0; w < w1; ++w) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(x) + (((long long)n * Hp + h + 1) * Wp + w + 1) * groups + cg), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s[i] += f[i];
+        }
+      const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
+      float4* d = reinterpret_cast<float4*>(sp + b * pitch + cg * 8);
+      d[0] = make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+      d[1] = make_float4(s[4] * inv, s[5] * inv, s[6] * inv, s[7] * inv);
+    }
+    __syncthreads();
+    float* dst = out + (long long)n * C * bins;
+    for (int i = threadIdx.x; i < C * bins; i += blockDim.x) {
+      const int c = i / bins, b = i - c * bins;
+      dst[i] = sp[b * pitch + c];
+    }
+    __syncthreads();
+  }
+}
+
 // dout (N,C,OH,OW) fp32 -> dx padded-flat bf16 (interior only; the border is never read).  One thread = one pixel x 8 channels;
 // a pixel lies in at most a 3x3 neighbourhood of (possibly overlapping) adaptive bins.
 __global__ void avgpool_pad_bwd_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
@@ -481,18 +518,30 @@ __global__ void avgpool_pad_bwd_kernel(const float* __restrict__ dout, int N, in
 // strided fp32 reads of the kernel above (32 sectors per warp load) become one coalesced pass, and all index math is 32-bit.
 __global__ void avgpool_pad_bwd_frame_kernel(const float* __restrict__ dout, int N, int H, int W, int C, int OH, int OW,
                                              __nv_bfloat16* __restrict__ dx) {
-  extern __shared__ float sd[];              // [OH*OW][C]
-  const int bins = OH * OW, groups = C >> 3, Wp = W + 2, Hp = H + 2;
+  extern __shared__ __align__(16) float sd[];              // [OH*OW][C + 4]
+  const int bins = OH * OW, groups = C >> 3, Wp = W + 2, Hp = H + 2, pitch = C + 4;
+  const bool uniform = H % OH == 0 && W % OW == 0;          // disjoint bins of equal size: every pixel lies in exactly one
+  const int kh = H / OH, kw = W / OW;
   for (int n = blockIdx.x; n < N; n += gridDim.x) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const float* src = dout + ((long long)n * C + c) * bins;
-      for (int b = 0; b < bins; ++b) sd[b * C + c] = __ldg(src + b);
+    const float* src = dout + (long long)n * C * bins;       // the frame's (C, OH, OW) gradients are one contiguous run: coalesced reads
+    for (int i = threadIdx.x; i < C * bins; i += blockDim.x) {
+      const int c = i / bins, b = i - c * bins;
+      sd[b * pitch + c] = __ldg(src + i);
     }
     __syncthreads();
     for (int t = threadIdx.x; t < H * W * groups; t += blockDim.x) {
       const int cg = t % groups, pix = t / groups;
       const int w = pix % W, h = pix / W;
       float s[8];
+      if (uniform) {
+        const float inv = 1.f / (float)(kh * kw);
+        const float* q = sd + ((h / kh) * OW + w / kw) * pitch + cg * 8;
+        const float4 lo = *reinterpret_cast<const float4*>(q), hi = *reinterpret_cast<const float4*>(q + 4);
+        s[0] = lo.x * inv; s[1] = lo.y * inv; s[2] = lo.z * inv; s[3] = lo.w * inv;
+        s[4] = hi.x * inv; s[5] = hi.y * inv; s[6] = hi.z * inv; s[7] = hi.w * inv;
+        reinterpret_cast<uint4*>(dx)[(((long long)n * Hp + h + 1) * Wp + w + 1) * groups + cg] = pack8(s);
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = 0.f;
       const int ohc = (h * OH) / H, owc = (w * OW) / W;
@@ -503,8 +552,8 @@ __global__ void avgpool_pad_bwd_frame_kernel(const float* __restrict__ dout, int
           const int w0 = bstart(ow, W, OW), w1 = bend(ow, W, OW);
           if (w < w0 || w >= w1) continue;
           const float inv = 1.f / (float)((h1 - h0) * (w1 - w0));
-          const float4 lo = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * C + cg * 8);
-          const float4 hi = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * C + cg * 8 + 4);
+          const float4 lo = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * pitch + cg * 8);
+          const float4 hi = *reinterpret_cast<const float4*>(sd + (oh * OW + ow) * pitch + cg * 8 + 4);
           s[0] = fmaf(lo.x, inv, s[0]); s[1] = fmaf(lo.y, inv, s[1]); s[2] = fmaf(lo.z, inv, s[2]); s[3] = fmaf(lo.w, inv, s[3]);
           s[4] = fmaf(hi.x, inv, s[4]); s[5] = fmaf(hi.y, inv, s[5]); s[6] = fmaf(hi.z, inv, s[6]); s[7] = fmaf(hi.w, inv, s[7]);
         }
@@ -698,7 +747,12 @@ CVAD_API int cvad_pad_bn_relu_bwd_apply_bf16(const void* raw, const void* dact, 
 CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C, int OH, int OW, float* out, void* stream) {
   long long total = (long long)N * OH * OW * (C / 8);
   if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;
-  avgpool_pad_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
+  const size_t frame_smem = (size_t)OH * OW * (C + 4) * sizeof(float);
+  if (frame_smem <= 48 * 1024)
+    avgpool_pad_fwd_frame_kernel<<<N < 8 * cvad_num_sms() ? N : 8 * cvad_num_sms(), 256, frame_smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
+  else
+    avgpool_pad_fwd_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, N, H, W, C, OH, OW, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -706,7 +760,7 @@ CVAD_API int cvad_pad_avgpool_bf16_fwd(const void* x, int N, int H, int W, int C
 CVAD_API int cvad_pad_avgpool_bf16_bwd(const float* dout, int N, int H, int W, int C, int OH, int OW, void* dx, void* stream) {
   long long total = (long long)N * H * W * (C / 8);
   if (total <= 0 || C % 8) return total <= 0 ? 0 : (int)cudaErrorInvalidValue;
-  const size_t frame_smem = (size_t)OH * OW * C * sizeof(float);
+  const size_t frame_smem = (size_t)OH * OW * (C + 4) * sizeof(float);
   if (frame_smem <= 48 * 1024)
     avgpool_pad_bwd_frame_kernel<<<N < 8 * cvad_num_sms() ? N : 8 * cvad_num_sms(), 256, frame_smem, (cudaStream_t)stream>>>(
         dout, N, H, W, C, OH, OW, (__nv_bfloat16*)dx);

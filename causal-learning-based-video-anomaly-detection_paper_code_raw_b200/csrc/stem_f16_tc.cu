@@ -54,33 +54,58 @@ struct Pool8 {
 // 16-byte (fp32) / 4-byte (uint8) load per frame row.  uint8: x = (float(v) - mean) / std as torchvision's Normalize computes it.
 template <bool U8>
 __global__ void stem8_s2d_kernel(const void* __restrict__ xin, Geo8 g, float mean, float stdv, uint4* __restrict__ x8) {
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < g.np; t += (long long)gridDim.x * blockDim.x) {
-    const int J = (int)(t % g.Wq);
-    const long long r = t / g.Wq;
-    const int i = (int)(r % g.Hq), n = (int)(r / g.Hq);
-    const int h0 = 2 * (i - 2), w0 = 4 * (J - 1);
-    float v[8];
+  // np < 2^31 (geo8): 32-bit index arithmetic.  Four pixels per thread and iteration, their eight loads issued before the first is
+  // consumed: with one pixel per iteration the kernel ran at 2.2 TB/s, latency-bound on two 4-byte loads per thread.
+  constexpr int U = 4;
+  const unsigned np = (unsigned)g.np, step = gridDim.x * blockDim.x;
+  for (unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x; t0 < np; t0 += U * step) {
+    uint4 raw[U][2];               // fp32: the four columns of one frame row; uint8: .x holds them
+    bool ok[U][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const int h = h0 + a;
-      const bool ok = (unsigned)h < (unsigned)g.H && w0 >= 0 && w0 < g.W;
-      if (!ok) {
+    for (int k = 0; k < U; ++k) {
+      const unsigned t = t0 + k * step;
+      const unsigned r = t / (unsigned)g.Wq;
+      const int J = (int)(t - r * (unsigned)g.Wq);
+      const unsigned nn = r / (unsigned)g.Hq;
+      const int i = (int)(r - nn * (unsigned)g.Hq);
+      const int h0 = 2 * (i - 2), w0 = 4 * (J - 1);
 #pragma unroll
-        for (int b = 0; b < 4; ++b) v[a * 4 + b] = 0.f;
-      } else if (U8) {
-        const unsigned q = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(xin) + ((long long)n * g.H + h) * g.W + w0));
-#pragma unroll
-        for (int b = 0; b < 4; ++b) v[a * 4 + b] = ((float)((q >> (8 * b)) & 255u) - mean) / stdv;
-      } else {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + ((long long)n * g.H + h) * g.W + w0));
-        v[a * 4 + 0] = q.x; v[a * 4 + 1] = q.y; v[a * 4 + 2] = q.z; v[a * 4 + 3] = q.w;
+      for (int a = 0; a < 2; ++a) {
+        const int h = h0 + a;
+        ok[k][a] = t < np && (unsigned)h < (unsigned)g.H && w0 >= 0 && w0 < g.W;
+        raw[k][a] = make_uint4(0, 0, 0, 0);
+        if (ok[k][a]) {
+          const long long off = ((long long)nn * g.H + h) * g.W + w0;
+          if (U8) raw[k][a].x = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const uint8_t*>(xin) + off));
+          else raw[k][a] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(xin) + off));
+        }
       }
     }
-    uint4 o;
-    __half2* hp = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) hp[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-    x8[t] = o;
+    for (int k = 0; k < U; ++k) {
+      const unsigned t = t0 + k * step;
+      if (t >= np) break;
+      float v[8];
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (!ok[k][a]) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) v[a * 4 + b] = 0.f;
+        } else if (U8) {
+          const unsigned q = raw[k][a].x;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) v[a * 4 + b] = ((float)((q >> (8 * b)) & 255u) - mean) / stdv;
+        } else {
+          v[a * 4 + 0] = __uint_as_float(raw[k][a].x); v[a * 4 + 1] = __uint_as_float(raw[k][a].y);
+          v[a * 4 + 2] = __uint_as_float(raw[k][a].z); v[a * 4 + 3] = __uint_as_float(raw[k][a].w);
+        }
+      }
+      uint4 o;
+      __half2* hp = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hp[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+      x8[t] = o;
+    }
   }
 }
 
@@ -253,9 +278,11 @@ __global__ void __launch_bounds__(384, 1) stem8_stats_kernel(const __grid_consta
 // overlap with the next band).  Its pixels are contiguous in the flat X8 index: one TMA box per band, `sub` sub-tiles of 128 pixels,
 // six MMAs each.  The epilogue applies BN + ReLU and parks the band as bf16 [row][column][32] in shared memory; when the band is complete
 // the eight epilogue warps pool it (post-ReLU values: an absent neighbour is a 0) and write the padded-flat rows of layer1's input.
-// Band layout: column wo lives in the 64-byte slot wo ^ ((wo >> 1) & 1) of its row and its four 16-byte vectors are XOR-swizzled by
-// (wo >> 2) & 3: the parking stores (lanes = pixels = columns two apart, one parity at a time) and the pooling reads (columns two apart)
-// are both bank-conflict free.
+// A thread holds BOTH outputs of its pixel, so the horizontal part of the pooling window starts in registers: per band row it parks
+// M[J] = max(y[2J], y[2J+1]) and X[J] = y[2J+1] (two planes of Wo/2 pixels; Wo is even on this path), and a pooled value is the maximum
+// over three rows of max(M[pw], X[pw-1]) -- six shared-memory loads instead of nine, on the pipe the MMAs stream their operands through.
+// A pixel's four 16-byte vectors are XOR-swizzled by (J >> 1) & 3: parking stores (lanes = consecutive pixels) and pooling reads are both
+// bank-conflict free.
 __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constant__ CUtensorMap map_x8, const float* __restrict__ w,
                                                             const float* __restrict__ bias, Geo8 g, Pool8 pg, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -361,6 +388,7 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
         const int r = ql / g.Wq, J = ql - r * g.Wq;
         const bool row_in = r < S8_ROWS && J < g.Wh;
         const bool live = row_in && i0 + r >= 0 && i0 + r < g.Ho;
+        uint32_t pk0[16], pk1[16];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {                               // the pixel's two outputs, one after the other (register budget)
           uint32_t a0[16], a1[16];
@@ -371,31 +399,39 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
             tc_fence_before();
             mbar_arrive(&bar_acc_empty[slot]);
           }
-          const int wo = 2 * J + p;
-          if (row_in && wo < g.Wo) {
-            uint32_t pk[16];
-            if (live) {
+          uint32_t* pk = p ? pk1 : pk0;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), rs[2 * c], rq[2 * c]), 0.f);
-                const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
-                const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
-                const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
-                pk[c] = *reinterpret_cast<uint32_t*>(&h0);
-                pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) pk[c] = 0u;             // rows outside the frame: post-ReLU zeros never win a max
-            }
-            uint4* o = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)(wo ^ ((wo >> 1) & 1)) * S8_C);
-            const int sw = (wo >> 2) & 3;
-            o[0 ^ sw] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o[1 ^ sw] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            o[2 ^ sw] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
-            o[3 ^ sw] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
+          for (int c = 0; c < 8; ++c) {
+            const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), rs[2 * c], rq[2 * c]), 0.f);
+            const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
+            const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
+            const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
+            pk[c] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
           }
+        }
+        if (row_in) {
+          if (!live) {                                               // rows outside the frame: post-ReLU zeros never win a max
+#pragma unroll
+            for (int c = 0; c < 16; ++c) { pk0[c] = 0u; pk1[c] = 0u; }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&pk0[c]), *reinterpret_cast<__nv_bfloat162*>(&pk1[c]));
+            pk0[c] = *reinterpret_cast<const uint32_t*>(&m);
+          }
+          const int sw = (J >> 1) & 3;
+          uint4* om = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)J * S8_C);
+          uint4* ox = reinterpret_cast<uint4*>(band + (size_t)r * pg.tile_pitch + (size_t)(g.Wh + J) * S8_C);
+          om[0 ^ sw] = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+          om[1 ^ sw] = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
+          om[2 ^ sw] = make_uint4(pk0[8], pk0[9], pk0[10], pk0[11]);
+          om[3 ^ sw] = make_uint4(pk0[12], pk0[13], pk0[14], pk0[15]);
+          ox[0 ^ sw] = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+          ox[1 ^ sw] = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
+          ox[2 ^ sw] = make_uint4(pk1[8], pk1[9], pk1[10], pk1[11]);
+          ox[3 ^ sw] = make_uint4(pk1[12], pk1[13], pk1[14], pk1[15]);
         }
       }
       acc_cnt += sub;
@@ -410,23 +446,23 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
         uint4 o = make_uint4(0, 0, 0, 0);
         if (pwp >= 1 && pwp <= pg.PW) {
           const int pw = pwp - 1;
-          // all nine loads before the first max; a window column outside the frame is clamped onto its in-frame neighbour
-          uint4 tv[9];
+          // window columns 2pw-1, 2pw, 2pw+1 = X[pw-1], M[pw]; all six loads before the first max.  pw = 0 has no left neighbour: X[0]
+          // stands in (column 1, which M[0] covers anyway)
+          uint4 tv[6];
+          const int jx = pw > 0 ? pw - 1 : 0;
+          const int offm = pw * S8_C + ((cg ^ ((pw >> 1) & 3)) * 8), offx = (g.Wh + jx) * S8_C + ((cg ^ ((jx >> 1) & 3)) * 8);
 #pragma unroll
-          for (int bb = 0; bb < 3; ++bb) {
-            int ww = 2 * pw - 1 + bb;
-            ww = ww < 0 ? 0 : (ww >= g.Wo ? g.Wo - 1 : ww);
-            const int off = (ww ^ ((ww >> 1) & 1)) * S8_C + ((cg ^ ((ww >> 2) & 3)) * 8);
-#pragma unroll
-            for (int a = 0; a < 3; ++a) tv[a * 3 + bb] = *reinterpret_cast<const uint4*>(band + (size_t)(2 * k + a) * pg.tile_pitch + off);
+          for (int a = 0; a < 3; ++a) {
+            tv[2 * a] = *reinterpret_cast<const uint4*>(band + (size_t)(2 * k + a) * pg.tile_pitch + offm);
+            tv[2 * a + 1] = *reinterpret_cast<const uint4*>(band + (size_t)(2 * k + a) * pg.tile_pitch + offx);
           }
           __nv_bfloat162 best[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) best[i] = reinterpret_cast<const __nv_bfloat162*>(&tv[0])[i];
 #pragma unroll
-          for (int t9 = 1; t9 < 9; ++t9)
+          for (int t6 = 1; t6 < 6; ++t6)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], reinterpret_cast<const __nv_bfloat162*>(&tv[t9])[i]);
+            for (int i = 0; i < 4; ++i) best[i] = __hmax2(best[i], reinterpret_cast<const __nv_bfloat162*>(&tv[t6])[i]);
           o = *reinterpret_cast<uint4*>(best);
         }
         reinterpret_cast<uint4*>(out)[((n * (pg.PH + 2) + ph + 1) * (long long)rowlen) + vv] = o;
