@@ -136,6 +136,7 @@ __global__ void ma_loss_kernel(const float* __restrict__ probs, const float* __r
                                const float* __restrict__ kl, const long long* __restrict__ labels, int B, float* __restrict__ out,
                                float* __restrict__ dprobs, float* __restrict__ dfin, float* __restrict__ dcausal,
                                float* __restrict__ dkl, float* __restrict__ flag) {
+  cvad_pdl_enter();
   __shared__ float sh[32];
   float ce = 0.f, mf = 0.f, mc = 0.f, ks = 0.f;
   const float invB = 1.f / (float)B;
@@ -261,6 +262,7 @@ __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
 // out[i] = a * x[i*xs] + b * y[i*ys]
 __global__ void lincomb2_kernel(float* __restrict__ out, const float* __restrict__ x, long long xs, float a, const float* __restrict__ y,
                                 long long ys, float b, long long n) {
+  cvad_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a * x[i * xs] + b * y[i * ys];
 }
@@ -295,7 +297,7 @@ CVAD_API int cvad_ma_loss_f32(const float* probs, const float* final_scores, con
                               const long long* labels, int B, float* out5, float* dprobs, float* dfinal, float* dcausal, float* dkl,
                               float* nonfinite_flag, void* stream) {
   if (B <= 0) return 0;
-  ma_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(probs, final_scores, causal_scores, kl, labels, B, out5, dprobs, dfinal, dcausal,
+  cvad_launch_pdl(ma_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, probs, final_scores, causal_scores, kl, labels, B, out5, dprobs, dfinal, dcausal,
                                                        dkl, nonfinite_flag);
   CVAD_LAUNCH_CHECK();
   return 0;
@@ -340,7 +342,7 @@ CVAD_API int cvad_lincomb2_f32(float* out, const float* x, long long xs, float a
   if (n <= 0) return 0;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 8 * cvad_num_sms()) blocks = 8 * cvad_num_sms();
-  lincomb2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(out, x, xs, a, y, ys, b, n);
+  cvad_launch_pdl(lincomb2_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, out, x, xs, a, y, ys, b, n);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

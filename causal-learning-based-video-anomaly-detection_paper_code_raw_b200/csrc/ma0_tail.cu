@@ -19,6 +19,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 
 __global__ void det_topk_decode_kernel(const float* __restrict__ bbox, const float* __restrict__ conf_logit, long long R, float* __restrict__ box,
                                        int* __restrict__ cnt, int* __restrict__ src, float* __restrict__ flag) {
+  cvad_pdl_enter();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
     float c[NA];
     int order[NA];
@@ -63,6 +64,7 @@ __global__ void det_topk_decode_kernel(const float* __restrict__ bbox, const flo
 
 __global__ void det_topk_decode_bwd_kernel(const float* __restrict__ dbox, const int* __restrict__ src, const int* __restrict__ cnt, long long R,
                                            float* __restrict__ dbbox) {
+  cvad_pdl_enter();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
     float g[NA][4];
 #pragma unroll
@@ -86,6 +88,7 @@ __global__ void det_topk_decode_bwd_kernel(const float* __restrict__ dbox, const
 }
 
 __global__ void score_rows_kernel(const float* __restrict__ z, const float* __restrict__ pred, long long rows, float* __restrict__ out) {
+  cvad_pdl_enter();
   const long long total = rows * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(t % NF);
@@ -99,6 +102,7 @@ __global__ void score_rows_kernel(const float* __restrict__ z, const float* __re
 
 __global__ void score_rows_bwd_kernel(const float* __restrict__ z, const float* __restrict__ pred, const float* __restrict__ dout, long long rows,
                                       float* __restrict__ dz, float* __restrict__ dpred) {
+  cvad_pdl_enter();
   const long long total = rows * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(t % NF);
@@ -111,6 +115,7 @@ __global__ void score_rows_bwd_kernel(const float* __restrict__ z, const float* 
 }
 
 __global__ void masked_mean_kernel(const float* __restrict__ s, const int* __restrict__ ntr, int B, float* __restrict__ out) {
+  cvad_pdl_enter();
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
     const int n = ntr[b];
     float a = 0.f;
@@ -120,6 +125,7 @@ __global__ void masked_mean_kernel(const float* __restrict__ s, const int* __res
 }
 
 __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ ntr, int B, float* __restrict__ ds) {
+  cvad_pdl_enter();
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < B * MAXDET; t += gridDim.x * blockDim.x) {
     const int b = t / MAXDET, k = t - b * MAXDET;
     const int n = ntr[b];
@@ -129,6 +135,7 @@ __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, const int
 
 __global__ void ma0_loss_kernel(const float* __restrict__ scores, const float* __restrict__ kl, const long long* __restrict__ labels, int B,
                                 float* __restrict__ out, float* __restrict__ dscores, float* __restrict__ dkl, float* __restrict__ flag) {
+  cvad_pdl_enter();
   __shared__ float sh[32];
   float mse = 0.f, ks = 0.f, nfin = 0.f;
   const float invB = 1.f / (float)B;
@@ -159,6 +166,7 @@ __global__ void ma0_loss_kernel(const float* __restrict__ scores, const float* _
 // out[w][t][:] = ring[(first + w*stride + t) % cap][:]  (F floats per frame, 16-byte vectors)
 __global__ void window_features_kernel(const float4* __restrict__ ring, long long cap, long long first, int stride, int T, int F4, long long n_win,
                                        float4* __restrict__ out) {
+  cvad_pdl_enter();
   const long long total = n_win * T * F4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % F4);
@@ -181,21 +189,21 @@ inline int blocks_of(long long n) {
 CVAD_API int cvad_det_topk_decode_f32(const float* bbox, const float* conf_logit, long long rows, float* box, int* cnt, int* src, float* flag,
                                       void* stream) {
   if (rows <= 0) return 0;
-  det_topk_decode_kernel<<<blocks_of(rows), 256, 0, (cudaStream_t)stream>>>(bbox, conf_logit, rows, box, cnt, src, flag);
+  cvad_launch_pdl(det_topk_decode_kernel, dim3(blocks_of(rows)), dim3(256), 0, (cudaStream_t)stream, bbox, conf_logit, rows, box, cnt, src, flag);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_det_topk_decode_bwd_f32(const float* dbox, const int* src, const int* cnt, long long rows, float* dbbox, void* stream) {
   if (rows <= 0) return 0;
-  det_topk_decode_bwd_kernel<<<blocks_of(rows), 256, 0, (cudaStream_t)stream>>>(dbox, src, cnt, rows, dbbox);
+  cvad_launch_pdl(det_topk_decode_bwd_kernel, dim3(blocks_of(rows)), dim3(256), 0, (cudaStream_t)stream, dbox, src, cnt, rows, dbbox);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_score_rows_f32(const float* z, const float* pred, long long rows, float* out18, void* stream) {
   if (rows <= 0) return 0;
-  score_rows_kernel<<<blocks_of(rows * NF), 256, 0, (cudaStream_t)stream>>>(z, pred, rows, out18);
+  cvad_launch_pdl(score_rows_kernel, dim3(blocks_of(rows * NF)), dim3(256), 0, (cudaStream_t)stream, z, pred, rows, out18);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -203,21 +211,21 @@ CVAD_API int cvad_score_rows_f32(const float* z, const float* pred, long long ro
 CVAD_API int cvad_score_rows_bwd_f32(const float* z, const float* pred, const float* dout18, long long rows, float* dz, float* dpred,
                                      void* stream) {
   if (rows <= 0) return 0;
-  score_rows_bwd_kernel<<<blocks_of(rows * NF), 256, 0, (cudaStream_t)stream>>>(z, pred, dout18, rows, dz, dpred);
+  cvad_launch_pdl(score_rows_bwd_kernel, dim3(blocks_of(rows * NF)), dim3(256), 0, (cudaStream_t)stream, z, pred, dout18, rows, dz, dpred);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_masked_mean_f32(const float* s, const int* ntr, int B, float* out, void* stream) {
   if (B <= 0) return 0;
-  masked_mean_kernel<<<blocks_of(B), 256, 0, (cudaStream_t)stream>>>(s, ntr, B, out);
+  cvad_launch_pdl(masked_mean_kernel, dim3(blocks_of(B)), dim3(256), 0, (cudaStream_t)stream, s, ntr, B, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_masked_mean_bwd_f32(const float* dout, const int* ntr, int B, float* ds, void* stream) {
   if (B <= 0) return 0;
-  masked_mean_bwd_kernel<<<blocks_of((long long)B * MAXDET), 256, 0, (cudaStream_t)stream>>>(dout, ntr, B, ds);
+  cvad_launch_pdl(masked_mean_bwd_kernel, dim3(blocks_of((long long)B * MAXDET)), dim3(256), 0, (cudaStream_t)stream, dout, ntr, B, ds);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -225,7 +233,7 @@ CVAD_API int cvad_masked_mean_bwd_f32(const float* dout, const int* ntr, int B, 
 CVAD_API int cvad_ma0_loss_f32(const float* scores, const float* kl, const long long* labels, int B, float* out3, float* dscores, float* dkl,
                                float* nonfinite_flag, void* stream) {
   if (B <= 0) return 0;
-  ma0_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(scores, kl, labels, B, out3, dscores, dkl, nonfinite_flag);
+  cvad_launch_pdl(ma0_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, scores, kl, labels, B, out3, dscores, dkl, nonfinite_flag);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -234,7 +242,7 @@ CVAD_API int cvad_window_features_f32(const float* ring, long long capacity, lon
                                       float* out, void* stream) {
   if (n_windows <= 0) return 0;
   if (F % 4 || capacity <= 0 || stride <= 0 || T <= 0 || first_frame < 0) return (int)cudaErrorInvalidValue;
-  window_features_kernel<<<blocks_of(n_windows * T * (F / 4)), 256, 0, (cudaStream_t)stream>>>(
+  cvad_launch_pdl(window_features_kernel, dim3(blocks_of(n_windows * T * (F / 4))), dim3(256), 0, (cudaStream_t)stream, 
       reinterpret_cast<const float4*>(ring), capacity, first_frame, stride, T, F / 4, n_windows, reinterpret_cast<float4*>(out));
   CVAD_LAUNCH_CHECK();
   return 0;

@@ -25,6 +25,7 @@ __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-
 // ------------------------------------------------------------------------------------------------ detector decode
 __global__ void det_decode_kernel(const float* __restrict__ raw, long long R, float* __restrict__ box, int* __restrict__ cnt,
                                   int* __restrict__ src, float* __restrict__ flag) {
+  cvad_pdl_enter();
   const float scale[4] = {360.f, 240.f, 80.f, 120.f}, off[4] = {0.f, 0.f, 15.f, 25.f};
   const float lo[4] = {10.f, 10.f, 10.f, 20.f}, hi[4] = {350.f, 230.f, 100.f, 150.f};
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
@@ -60,6 +61,7 @@ __global__ void det_decode_kernel(const float* __restrict__ raw, long long R, fl
 
 __global__ void det_decode_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ dbox, const int* __restrict__ src,
                                       long long R, float* __restrict__ draw) {
+  cvad_pdl_enter();
   const float scale[4] = {360.f, 240.f, 80.f, 120.f};
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
     for (int k = 0; k < MAXDET * 4; ++k) draw[r * MAXDET * 4 + k] = 0.f;
@@ -78,6 +80,7 @@ __global__ void det_decode_bwd_kernel(const float* __restrict__ raw, const float
 // one block per clip; box (B,T,5,4), reid (B,T,5,64) -> traj (B,5,T,68); ntr[b] = max_t cnt[b,t]
 __global__ void traj_assemble_kernel(const float* __restrict__ box, const float* __restrict__ reid, const int* __restrict__ cnt, int T,
                                      int reid_dim, float* __restrict__ traj, int* __restrict__ ntr, float* __restrict__ multi_flag) {
+  cvad_pdl_enter();
   const int b = blockIdx.x;
   const int F = 4 + reid_dim;
   __shared__ int smax;
@@ -101,6 +104,7 @@ __global__ void traj_assemble_kernel(const float* __restrict__ box, const float*
 
 __global__ void traj_assemble_bwd_kernel(const float* __restrict__ dtraj, const int* __restrict__ cnt, int T, int reid_dim,
                                          float* __restrict__ dbox, float* __restrict__ dreid) {
+  cvad_pdl_enter();
   const int b = blockIdx.x;
   const int F = 4 + reid_dim;
   const int total = MAXDET * T * F;
@@ -119,6 +123,7 @@ __global__ void traj_assemble_bwd_kernel(const float* __restrict__ dtraj, const 
 __global__ void __launch_bounds__(192) gru_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ w_hh,
                                                       const float* __restrict__ b_hh, const int* __restrict__ ntr, int T,
                                                       float* __restrict__ hT, float* __restrict__ saved) {
+  cvad_pdl_enter();
   const int n = blockIdx.x, g = threadIdx.x;
   const int b = n / MAXDET, k = n % MAXDET;
   __shared__ float h[HID];
@@ -161,6 +166,7 @@ __global__ void __launch_bounds__(192) gru_fwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(192) gru_bwd_kernel(const float* __restrict__ dhT, const float* __restrict__ saved,
                                                       const float* __restrict__ w_hh, const int* __restrict__ ntr, int T,
                                                       float* __restrict__ dgi, float* __restrict__ dw_hh, float* __restrict__ db_hh) {
+  cvad_pdl_enter();
   const int n = blockIdx.x, g = threadIdx.x;
   const int b = n / MAXDET, k = n % MAXDET;
   extern __shared__ float sm[];
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(192) gru_bwd_kernel(const float* __restrict__ 
 // one block per clip, threads over (track, factor)
 __global__ void reparam_kl_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
                                   const int* __restrict__ ntr, float* __restrict__ z, float* __restrict__ kl) {
+  cvad_pdl_enter();
   const int b = blockIdx.x, i = threadIdx.x;   // 32 threads, 30 used
   const int k = i / NF;
   const int nt = ntr[b];
@@ -241,6 +248,7 @@ __global__ void reparam_kl_kernel(const float* __restrict__ mu, const float* __r
 __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
                                       const int* __restrict__ ntr, const float* __restrict__ dz, const float* __restrict__ dkl,
                                       float* __restrict__ dmu, float* __restrict__ dlv) {
+  cvad_pdl_enter();
   const int b = blockIdx.x, i = threadIdx.x;
   if (i >= MAXDET * NF) return;
   const int k = i / NF;
@@ -260,6 +268,7 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float*
 
 // ------------------------------------------------------------------------------------------------ structure learner
 __global__ void pair_concat_kernel(const float* __restrict__ node, int B, int Hn, float* __restrict__ pair) {
+  cvad_pdl_enter();
   long long total = (long long)B * MAXDET * MAXDET * 2 * Hn;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int f = (int)(t % (2 * Hn));
@@ -270,6 +279,7 @@ __global__ void pair_concat_kernel(const float* __restrict__ node, int B, int Hn
   }
 }
 __global__ void pair_concat_bwd_kernel(const float* __restrict__ dpair, int B, int Hn, float* __restrict__ dnode) {
+  cvad_pdl_enter();
   long long total = (long long)B * MAXDET * Hn;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int f = (int)(t % Hn);
@@ -287,6 +297,7 @@ __global__ void pair_concat_bwd_kernel(const float* __restrict__ dpair, int B, i
 // e (B,5,5) -> adj (B,6,6) (bwd: dadj -> de), masked by i != j and i,j < ntr[b]
 __global__ void adj_assemble_kernel(const float* __restrict__ src, const int* __restrict__ ntr, int B, float* __restrict__ dst,
                                     int backward) {
+  cvad_pdl_enter();
   long long total = (long long)B * NF * NF;
   if (!backward) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -310,6 +321,7 @@ __global__ void adj_assemble_kernel(const float* __restrict__ src, const int* __
 
 // structured[b,k,i] = sum_j adj[b,i,j] z[b,k,j]
 __global__ void structured_kernel(const float* __restrict__ adj, const float* __restrict__ z, int B, float* __restrict__ out) {
+  cvad_pdl_enter();
   long long total = (long long)B * MAXDET * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int i = (int)(t % NF), k = (int)((t / NF) % MAXDET);
@@ -321,6 +333,7 @@ __global__ void structured_kernel(const float* __restrict__ adj, const float* __
 }
 __global__ void structured_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ z, const float* __restrict__ dout, int B,
                                       float* __restrict__ dadj, float* __restrict__ dz) {
+  cvad_pdl_enter();
   long long na = (long long)B * NF * NF, nz = (long long)B * MAXDET * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < na + nz; t += (long long)gridDim.x * blockDim.x) {
     if (t < na) {
@@ -344,6 +357,7 @@ __global__ void structured_bwd_kernel(const float* __restrict__ adj, const float
 // cin (B,18) = [cur | prd | |cur-prd|], min (B,12) = [cur | prd], tin (B,6) = cur   (means over the clip's tracks)
 __global__ void scorer_inputs_kernel(const float* __restrict__ z, const float* __restrict__ pred, const int* __restrict__ ntr, int B,
                                      float* __restrict__ cin, float* __restrict__ min_, float* __restrict__ tin) {
+  cvad_pdl_enter();
   long long total = (long long)B * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int f = (int)(t % NF);
@@ -364,6 +378,7 @@ __global__ void scorer_inputs_kernel(const float* __restrict__ z, const float* _
 __global__ void scorer_inputs_bwd_kernel(const float* __restrict__ cin, const int* __restrict__ ntr, int B, const float* __restrict__ dcin,
                                          const float* __restrict__ dmin, const float* __restrict__ dtin, float* __restrict__ dz,
                                          float* __restrict__ dpred) {
+  cvad_pdl_enter();
   long long total = (long long)B * NF;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int f = (int)(t % NF);
@@ -383,12 +398,14 @@ __global__ void scorer_inputs_bwd_kernel(const float* __restrict__ cin, const in
 
 __global__ void lincomb3_kernel(float* __restrict__ out, const float* __restrict__ x, float a, const float* __restrict__ y, float b,
                                 const float* __restrict__ z, float c, long long n) {
+  cvad_pdl_enter();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a * x[i] + b * y[i] + c * z[i];
 }
 
 // ------------------------------------------------------------------------------------------------ softmax over small rows
 __global__ void softmax_rows_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ y) {
+  cvad_pdl_enter();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
     float m = -INFINITY;
     for (int c = 0; c < C; ++c) m = fmaxf(m, x[r * C + c]);
@@ -399,6 +416,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ x, long long rows,
 }
 __global__ void softmax_rows_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, long long rows, int C,
                                         float* __restrict__ dx) {
+  cvad_pdl_enter();
   for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows; r += (long long)gridDim.x * blockDim.x) {
     float dot = 0.f;
     for (int c = 0; c < C; ++c) dot += y[r * C + c] * dy[r * C + c];
@@ -416,34 +434,34 @@ inline int nb(long long n) {
 
 CVAD_API int cvad_det_decode_f32(const float* raw, long long rows, float* box, int* cnt, int* src, float* active_flag, void* stream) {
   if (rows <= 0) return 0;
-  det_decode_kernel<<<nb(rows), 128, 0, (cudaStream_t)stream>>>(raw, rows, box, cnt, src, active_flag);
+  cvad_launch_pdl(det_decode_kernel, dim3(nb(rows)), dim3(128), 0, (cudaStream_t)stream, raw, rows, box, cnt, src, active_flag);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_det_decode_bwd_f32(const float* raw, const float* dbox, const int* src, long long rows, float* draw, void* stream) {
   if (rows <= 0) return 0;
-  det_decode_bwd_kernel<<<nb(rows), 128, 0, (cudaStream_t)stream>>>(raw, dbox, src, rows, draw);
+  cvad_launch_pdl(det_decode_bwd_kernel, dim3(nb(rows)), dim3(128), 0, (cudaStream_t)stream, raw, dbox, src, rows, draw);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_traj_assemble_f32(const float* box, const float* reid, const int* cnt, int B, int T, int reid_dim, float* traj, int* ntr,
                                     float* multi_flag, void* stream) {
   if (B <= 0) return 0;
-  traj_assemble_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(box, reid, cnt, T, reid_dim, traj, ntr, multi_flag);
+  cvad_launch_pdl(traj_assemble_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, box, reid, cnt, T, reid_dim, traj, ntr, multi_flag);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_traj_assemble_bwd_f32(const float* dtraj, const int* cnt, int B, int T, int reid_dim, float* dbox, float* dreid,
                                         void* stream) {
   if (B <= 0) return 0;
-  traj_assemble_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dtraj, cnt, T, reid_dim, dbox, dreid);
+  cvad_launch_pdl(traj_assemble_bwd_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, dtraj, cnt, T, reid_dim, dbox, dreid);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_gru_fwd_f32(const float* gi, const float* w_hh, const float* b_hh, const int* ntr, int B, int T, float* hT, float* saved,
                               void* stream) {
   if (B <= 0) return 0;
-  gru_fwd_kernel<<<B * MAXDET, 192, 0, (cudaStream_t)stream>>>(gi, w_hh, b_hh, ntr, T, hT, saved);
+  cvad_launch_pdl(gru_fwd_kernel, dim3(B * MAXDET), dim3(192), 0, (cudaStream_t)stream, gi, w_hh, b_hh, ntr, T, hT, saved);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
@@ -454,84 +472,84 @@ CVAD_API int cvad_gru_bwd_f32(const float* dhT, const float* saved, const float*
   static size_t configured[CVAD_MAX_DEVICES] = {};
   const cudaError_t ce = cvad_ensure_dyn_smem(gru_bwd_kernel, smem, configured);
   if (ce != cudaSuccess) return (int)ce;
-  gru_bwd_kernel<<<B * MAXDET, 192, smem, (cudaStream_t)stream>>>(dhT, saved, w_hh, ntr, T, dgi, dw_hh, db_hh);
+  cvad_launch_pdl(gru_bwd_kernel, dim3(B * MAXDET), dim3(192), smem, (cudaStream_t)stream, dhT, saved, w_hh, ntr, T, dgi, dw_hh, db_hh);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_reparam_kl_f32(const float* mu, const float* logvar, const float* eps, const int* ntr, int B, float* z, float* kl,
                                  void* stream) {
   if (B <= 0) return 0;
-  reparam_kl_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(mu, logvar, eps, ntr, z, kl);
+  cvad_launch_pdl(reparam_kl_kernel, dim3(B), dim3(32), 0, (cudaStream_t)stream, mu, logvar, eps, ntr, z, kl);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_reparam_kl_bwd_f32(const float* mu, const float* logvar, const float* eps, const int* ntr, int B, const float* dz,
                                      const float* dkl, float* dmu, float* dlogvar, void* stream) {
   if (B <= 0) return 0;
-  reparam_kl_bwd_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(mu, logvar, eps, ntr, dz, dkl, dmu, dlogvar);
+  cvad_launch_pdl(reparam_kl_bwd_kernel, dim3(B), dim3(32), 0, (cudaStream_t)stream, mu, logvar, eps, ntr, dz, dkl, dmu, dlogvar);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_pair_concat_f32(const float* node, int B, int node_dim, float* pair, void* stream) {
   if (B <= 0) return 0;
-  pair_concat_kernel<<<nb((long long)B * 25 * 2 * node_dim), 128, 0, (cudaStream_t)stream>>>(node, B, node_dim, pair);
+  cvad_launch_pdl(pair_concat_kernel, dim3(nb((long long)B * 25 * 2 * node_dim)), dim3(128), 0, (cudaStream_t)stream, node, B, node_dim, pair);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_pair_concat_bwd_f32(const float* dpair, int B, int node_dim, float* dnode, void* stream) {
   if (B <= 0) return 0;
-  pair_concat_bwd_kernel<<<nb((long long)B * 5 * node_dim), 128, 0, (cudaStream_t)stream>>>(dpair, B, node_dim, dnode);
+  cvad_launch_pdl(pair_concat_bwd_kernel, dim3(nb((long long)B * 5 * node_dim)), dim3(128), 0, (cudaStream_t)stream, dpair, B, node_dim, dnode);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_adj_assemble_f32(const float* src, const int* ntr, int B, float* dst, int backward, void* stream) {
   if (B <= 0) return 0;
-  adj_assemble_kernel<<<nb((long long)B * 36), 128, 0, (cudaStream_t)stream>>>(src, ntr, B, dst, backward);
+  cvad_launch_pdl(adj_assemble_kernel, dim3(nb((long long)B * 36)), dim3(128), 0, (cudaStream_t)stream, src, ntr, B, dst, backward);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_structured_f32(const float* adj, const float* z, int B, float* out, void* stream) {
   if (B <= 0) return 0;
-  structured_kernel<<<nb((long long)B * 30), 128, 0, (cudaStream_t)stream>>>(adj, z, B, out);
+  cvad_launch_pdl(structured_kernel, dim3(nb((long long)B * 30)), dim3(128), 0, (cudaStream_t)stream, adj, z, B, out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_structured_bwd_f32(const float* adj, const float* z, const float* dout, int B, float* dadj, float* dz, void* stream) {
   if (B <= 0) return 0;
-  structured_bwd_kernel<<<nb((long long)B * 66), 128, 0, (cudaStream_t)stream>>>(adj, z, dout, B, dadj, dz);
+  cvad_launch_pdl(structured_bwd_kernel, dim3(nb((long long)B * 66)), dim3(128), 0, (cudaStream_t)stream, adj, z, dout, B, dadj, dz);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_scorer_inputs_f32(const float* z, const float* pred, const int* ntr, int B, float* cin, float* min_, float* tin,
                                     void* stream) {
   if (B <= 0) return 0;
-  scorer_inputs_kernel<<<nb((long long)B * 6), 128, 0, (cudaStream_t)stream>>>(z, pred, ntr, B, cin, min_, tin);
+  cvad_launch_pdl(scorer_inputs_kernel, dim3(nb((long long)B * 6)), dim3(128), 0, (cudaStream_t)stream, z, pred, ntr, B, cin, min_, tin);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_scorer_inputs_bwd_f32(const float* cin, const int* ntr, int B, const float* dcin, const float* dmin, const float* dtin,
                                         float* dz, float* dpred, void* stream) {
   if (B <= 0) return 0;
-  scorer_inputs_bwd_kernel<<<nb((long long)B * 6), 128, 0, (cudaStream_t)stream>>>(cin, ntr, B, dcin, dmin, dtin, dz, dpred);
+  cvad_launch_pdl(scorer_inputs_bwd_kernel, dim3(nb((long long)B * 6)), dim3(128), 0, (cudaStream_t)stream, cin, ntr, B, dcin, dmin, dtin, dz, dpred);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_lincomb3_f32(float* out, const float* x, float a, const float* y, float b, const float* z, float c, long long n,
                                void* stream) {
   if (n <= 0) return 0;
-  lincomb3_kernel<<<nb(n), 128, 0, (cudaStream_t)stream>>>(out, x, a, y, b, z, c, n);
+  cvad_launch_pdl(lincomb3_kernel, dim3(nb(n)), dim3(128), 0, (cudaStream_t)stream, out, x, a, y, b, z, c, n);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_softmax_rows_f32(const float* x, long long rows, int C, float* y, void* stream) {
   if (rows <= 0) return 0;
-  softmax_rows_kernel<<<nb(rows), 128, 0, (cudaStream_t)stream>>>(x, rows, C, y);
+  cvad_launch_pdl(softmax_rows_kernel, dim3(nb(rows)), dim3(128), 0, (cudaStream_t)stream, x, rows, C, y);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 CVAD_API int cvad_softmax_rows_bwd_f32(const float* y, const float* dy, long long rows, int C, float* dx, void* stream) {
   if (rows <= 0) return 0;
-  softmax_rows_bwd_kernel<<<nb(rows), 128, 0, (cudaStream_t)stream>>>(y, dy, rows, C, dx);
+  cvad_launch_pdl(softmax_rows_bwd_kernel, dim3(nb(rows)), dim3(128), 0, (cudaStream_t)stream, y, dy, rows, C, dx);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

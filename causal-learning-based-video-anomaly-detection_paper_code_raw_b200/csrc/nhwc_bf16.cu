@@ -98,6 +98,7 @@ __device__ __forceinline__ long long phase_row(const PadGeo& g, int n, int hp, i
 // the backward and updates the running statistics, and the last block past this prologue re-zeroes the sums -- one launch instead of
 // two on the critical path of every layer.
 struct BnFin {
+  int reverse;            // walk the rows back to front (L2 reuse, see the kernel)
   double* ws;
   double count;
   float eps, momentum;
@@ -172,10 +173,13 @@ __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloa
       long long dst[R][2];
 #pragma unroll
       for (int rr = 0; rr < R; ++rr) {
-        const int r = r0 + rr;
+        // fin.reverse: rows are walked from the END of the tensor -- the convolution in front of this kernel wrote raw front to back, so
+        // its last rows are what the 126 MB L2 still holds, and the convolution behind it starts reading act at the front, which this
+        // kernel then wrote last
+        const int r = fin.reverse ? items - 1 - (r0 + rr) : r0 + rr;
         int n = 0, hp = -1, a = 0;
         long long row0 = 0, row1 = 0;                              // first vector of the output row(s)
-        if (r < items) {
+        if (r >= 0 && r < items) {
           if (PHASE) {
             const int i = r % g.Hq;
             const int t = r / g.Hq;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloa
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int v = v0 + u * 256;
-          in[rr][u] = v < span && r < items;
+          in[rr][u] = v < span && r >= 0 && r < items;
           const int b = PHASE && v >= rowlen ? 1 : 0;
           const int vv = v - b * rowlen;
           const int j = vv >> g.lg;
@@ -608,8 +612,19 @@ void launch_reduce(const __nv_bfloat16* r, const __nv_bfloat16* d, const PadGeo&
   else pad_reduce_kernel<BWD, 0><<<blocks, 256, sm, st>>>(r, d, g, mean, invstd, gamma, beta, ws);
 }
 
+inline int bn_apply_reverse() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CVAD_BN_REVERSE");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 int launch_apply(const __nv_bfloat16* r, __nv_bfloat16* a, const PadGeo& g, int N, int H, int phase_out, const float* mean, const float* invstd,
-                 const float* gamma, const float* beta, bool finalize, const BnFin& fin, cudaStream_t st) {
+                 const float* gamma, const float* beta, bool finalize, const BnFin& fin_in, cudaStream_t st) {
+  BnFin fin = fin_in;
+  fin.reverse = bn_apply_reverse();
   const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
   const int R = bn_rows_per_iter() == 4 ? 4 : 2;
   const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
@@ -704,7 +719,7 @@ CVAD_API int cvad_pad_bn_finalize_apply_relu_bf16(const void* raw, void* act, in
     memset(&none, 0, sizeof(none));
     return launch_apply((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, N, H, phase_out, mean, invstd, gamma, beta, false, none, st);
   }
-  BnFin fin = {ws, count, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked};
+  BnFin fin = {0, ws, count, eps, momentum, mean, invstd, running_mean, running_var, num_batches_tracked};
   return launch_apply((const __nv_bfloat16*)raw, (__nv_bfloat16*)act, g, N, H, phase_out, nullptr, nullptr, gamma, beta, true, fin, st);
 }
 

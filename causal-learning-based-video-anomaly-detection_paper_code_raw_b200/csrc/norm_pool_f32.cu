@@ -304,6 +304,7 @@ __global__ void adaptive_avgpool_bwd_kernel(const float* __restrict__ dy, float*
 
 // mean over the middle axis: x (A, T, F) -> y (A, F)  (cad:568 temporal mean of backbone features) and its gradient
 __global__ void mean_mid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long A, int T, long long F) {
+  cvad_pdl_enter();
   long long total = A * F;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     long long a = t / F, f = t - a * F;
@@ -313,6 +314,7 @@ __global__ void mean_mid_fwd_kernel(const float* __restrict__ x, float* __restri
   }
 }
 __global__ void mean_mid_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, long long A, int T, long long F, int accumulate) {
+  cvad_pdl_enter();
   long long total = A * T * F;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     long long f = t % F, a = t / (F * T);
@@ -496,14 +498,14 @@ CVAD_API int cvad_adaptive_avgpool_bwd_f32(const float* dy, float* dx, long long
 
 CVAD_API int cvad_mean_mid_fwd_f32(const float* x, float* y, long long A, int T, long long F, void* stream) {
   if (A * F <= 0) return 0;
-  mean_mid_fwd_kernel<<<ew_blocks(A * F), 256, 0, (cudaStream_t)stream>>>(x, y, A, T, F);
+  cvad_launch_pdl(mean_mid_fwd_kernel, dim3(ew_blocks(A * F)), dim3(256), 0, (cudaStream_t)stream, x, y, A, T, F);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
 
 CVAD_API int cvad_mean_mid_bwd_f32(const float* dy, float* dx, long long A, int T, long long F, int accumulate, void* stream) {
   if (A * F * T <= 0) return 0;
-  mean_mid_bwd_kernel<<<ew_blocks(A * T * F), 256, 0, (cudaStream_t)stream>>>(dy, dx, A, T, F, accumulate);
+  cvad_launch_pdl(mean_mid_bwd_kernel, dim3(ew_blocks(A * T * F)), dim3(256), 0, (cudaStream_t)stream, dy, dx, A, T, F, accumulate);
   CVAD_LAUNCH_CHECK();
   return 0;
 }

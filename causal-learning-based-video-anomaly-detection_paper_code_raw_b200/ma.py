@@ -11,6 +11,7 @@ Python lists; the ragged lists of the output dict are materialised lazily, only 
 from __future__ import annotations
 
 import collections.abc
+import contextlib
 import math
 import os
 
@@ -24,6 +25,7 @@ from .noise import DeviceNoise
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID
 
 SLOT_DETECTOR, SLOT_STRUCTURE, SLOT_NEVER = 1, 2, 3
+TAIL_BRANCHES = os.environ.get("CVAD_TAIL_BRANCHES", "1") != "0"     # direct classifier on a second stream beside the causal branch
 
 
 class ResNetBackbone(nn.Module):
@@ -162,8 +164,16 @@ class CausalFactorExtractor(nn.Module):
 
     def forward(self, enc, ntr, eps):
         h = _mlp(self.encoder, (0, 2), enc, (ACT_RELU, ACT_RELU))
+        cur = torch.cuda.current_stream()
+        side = ops.aux_stream(h.device, 2) if TAIL_BRANCHES else None
+        if side is not None:
+            side.wait_stream(cur)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            lv = ops.linear_act(h, self.logvar_head.weight, self.logvar_head.bias)       # the two heads are independent GEMMs
         mu = ops.linear_act(h, self.mu_head.weight, self.mu_head.bias)
-        lv = ops.linear_act(h, self.logvar_head.weight, self.logvar_head.bias)
+        if side is not None:
+            cur.wait_stream(side)
+            lv.record_stream(cur)
         return ma_ops.reparam_kl(mu, lv, eps, ntr)               # z (B,5,6), kl (B)
 
 
@@ -209,9 +219,22 @@ class EnhancedAnomalyScorer(nn.Module):
         cin, mn, tin = ma_ops.scorer_inputs(z, pred, ntr)
         B = cin.shape[0]
         keeps = [noise.keep_mask("scorer0", (B, 64), 0.2, cin.device), None, None] if training else None
+        # three independent chains: the motion / temporal scorers run on two further streams beside the causal scorer (forward and, through
+        # autograd's stream bookkeeping, backward)
+        cur = torch.cuda.current_stream()
+        sides = [ops.aux_stream(cin.device, 2), ops.aux_stream(cin.device, 3)] if TAIL_BRANCHES else [None, None]
+        for sd in sides:
+            if sd is not None:
+                sd.wait_stream(cur)
+        with (torch.cuda.stream(sides[0]) if sides[0] is not None else contextlib.nullcontext()):
+            ms = _mlp(self.motion_scorer, (0, 2, 4), mn, (ACT_RELU, ACT_RELU, ACT_SIGMOID))
+        with (torch.cuda.stream(sides[1]) if sides[1] is not None else contextlib.nullcontext()):
+            ts = _mlp(self.temporal_scorer, (0, 2, 4), tin, (ACT_RELU, ACT_RELU, ACT_SIGMOID))
         cs = _mlp(self.causal_scorer, (0, 3, 5), cin, (ACT_RELU, ACT_RELU, ACT_SIGMOID), keeps, (0.2, 0, 0))
-        ms = _mlp(self.motion_scorer, (0, 2, 4), mn, (ACT_RELU, ACT_RELU, ACT_SIGMOID))
-        ts = _mlp(self.temporal_scorer, (0, 2, 4), tin, (ACT_RELU, ACT_RELU, ACT_SIGMOID))
+        for sd, t in zip(sides, (ms, ts)):
+            if sd is not None:
+                cur.wait_stream(sd)
+                t.record_stream(cur)
         return ma_ops.lincomb3(cs.reshape(B), 0.5, ms.reshape(B), 0.3, ts.reshape(B), 0.2)
 
 
@@ -285,6 +308,21 @@ class CausalAnomalyDetector(nn.Module):
         dev = features.device
         f_det = self.flags[SLOT_DETECTOR:SLOT_DETECTOR + 1] if self.flags is not None else None
         f_str = self.flags[SLOT_STRUCTURE:SLOT_STRUCTURE + 1] if self.flags is not None else None
+        # The direct classifier (cad:525-538, 568-571) depends on the features only: it runs on a second stream beside the ~35 dependent
+        # launches of the causal branch (autograd replays the fork in the backward: the classifier's data-gradient chain and its 6144-wide
+        # GEMM run beside the causal branch's); in a captured step the two become parallel branches of the graph.
+        cur = torch.cuda.current_stream()
+        side = ops.aux_stream(dev, 1) if TAIL_BRANCHES else None
+        keeps = None
+        if self.training:
+            keeps = [self.noise.keep_mask("cls0", (B, 512), 0.3, dev), self.noise.keep_mask("cls1", (B, 256), 0.2, dev), None, None, None]
+        if side is not None:
+            side.wait_stream(cur)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            pooled = ops.mean_mid(features)
+            logits = _mlp(self.direct_classifier, (0, 3, 6, 8, 10), pooled, (ACT_RELU, ACT_RELU, ACT_RELU, ACT_RELU, ACT_NONE), keeps,
+                          (0.3, 0.2, 0, 0, 0))
+            direct = ma_ops.softmax_rows(logits)
         box, cnt, _src = self.detector(features, self.noise, self.training, f_det)
         traj, ntr = self.tracker(box, cnt, f_str)
         enc = self.traj_encoder(traj, ntr)
@@ -293,13 +331,9 @@ class CausalAnomalyDetector(nn.Module):
         adj = self.structure_learner(z, ntr)
         pred = self.dynamics_predictor(z, adj)
         causal = self.anomaly_scorer(z, pred, ntr, self.noise, self.training)
-        pooled = ops.mean_mid(features)
-        dc = self.direct_classifier
-        keeps = None
-        if self.training:
-            keeps = [self.noise.keep_mask("cls0", (B, 512), 0.3, dev), self.noise.keep_mask("cls1", (B, 256), 0.2, dev), None, None, None]
-        logits = _mlp(dc, (0, 3, 6, 8, 10), pooled, (ACT_RELU, ACT_RELU, ACT_RELU, ACT_RELU, ACT_NONE), keeps, (0.3, 0.2, 0, 0, 0))
-        direct = ma_ops.softmax_rows(logits)
+        if side is not None:
+            cur.wait_stream(side)
+            direct.record_stream(cur)
         final = ops.lincomb2(causal, 0.6, direct, 1, 0.4)       # cad:574
         dense = {"causal_factors": z, "adjacency_matrices": adj, "kl_losses": kl, "detections": box, "det_counts": cnt,
                  "n_tracks": ntr, "features": features}
