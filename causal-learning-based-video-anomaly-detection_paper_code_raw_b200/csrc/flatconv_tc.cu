@@ -525,7 +525,7 @@ int g_dgrad_mode = 2;
 // development knobs (cvad_flat_tune): [0] cap on the 128-row sub-tiles per work item for N = 128 (4 fills the whole accumulator ring,
 // 2 leaves a second buffer for the epilogue); [1] activation-segment ring depth for items with several units (3 = a third stage when
 // shared memory allows, 2 = always double buffering)
-int g_fc_tune[4] = {2, 3, 0, 0};
+int g_fc_tune[4] = {2, 3, 0, 0};      // [2] != 0: single dy fetch for every stride-2 data-gradient; [3] != 0: stride-2 weight gradients with pixel-shift atoms
 // Output-channel block = the MMA's N.  One M128 x N x K16 MMA streams 4 KB of A plus N*32 B of B from shared memory at ~80-90 B/cycle
 // (profiles/r01g_flatconv_L0_ncu_full.md), so it is operand-bound below N = 256: take the widest N the layer allows.
 inline int n_block_of(int nout) { return nout % 256 == 0 ? 256 : (nout % 128 == 0 ? 128 : (nout % 64 == 0 ? 64 : 32)); }
@@ -951,10 +951,13 @@ namespace {
 
 constexpr int WG_MAX_STAGES = 4;
 bool g_wgrad_kh_stack = true;          // cvad_flat_wgrad_mode(0) selects the one-kernel-row-per-MMA form (A/B measurements)
+// stride 2 with 32 / 64 input channels: the M atoms of an MMA are the PHASE PLANES at one pixel shift (9 taps in 4-5 MMAs per 16
+// pixels) instead of pixel shifts inside one plane (6 MMAs); cvad_flat_tune(3, 0) restores the latter
 
 struct WgGroup {
   int seg, delta;
-  int tap[4];            // tap index of each M atom (pixel shift j), -1 = unused lanes
+  int atom_segs;         // 0: the M atoms are consecutive pixel shifts of one segment; k > 0: atom j is segment seg + j*k (phase planes)
+  int tap[4];            // tap index of each M atom, -1 = unused lanes
 };
 struct WgVariant {
   int n_seg, n_groups;
@@ -1055,7 +1058,7 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, NMMA, 1, 1);
     const uint32_t lbo_a = A_SLABS == 2 ? seg1 : ROWB_A;
-    const uint64_t da_hi = make_smem_desc(0, lbo_a, 8 * ROWB_A, LAY_A);
+    const uint64_t da_hi_shift = make_smem_desc(0, lbo_a, 8 * ROWB_A, LAY_A);
     // KH == 3: the N atoms are the same channels b_halo pixel rows apart (atom i = dy[q + (i-1)*halo] <-> kernel row kh = 2 - i)
     const uint64_t db_hi = make_smem_desc(0, KH == 3 ? (uint32_t)p.b_halo * ROWB_B : b1, 8 * ROWB_B, LAY_B);
     const int n_groups = var.n_groups;
@@ -1069,6 +1072,9 @@ __global__ void __launch_bounds__(256, 1) flatwgrad_kernel(const __grid_constant
         for (int g = 0; g < n_groups; ++g) {
           const uint32_t a0 = base + var.groups[g].seg * A_SLABS * seg1 + (uint32_t)var.groups[g].delta * ROWB_A;
           const uint32_t tacc = tmem_base + g * NMMA;
+          const uint64_t da_hi = var.groups[g].atom_segs
+                                     ? make_smem_desc(0, (uint32_t)var.groups[g].atom_segs * A_SLABS * seg1, 8 * ROWB_A, LAY_A)
+                                     : da_hi_shift;
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t da = da_hi | (uint64_t)(((a0 + k * 16 * ROWB_A) >> 4) & 0x3FFF);
             const uint64_t db = db_hi | (uint64_t)(((base + a_bytes_max + k * 16 * ROWB_B) >> 4) & 0x3FFF);
@@ -1282,6 +1288,40 @@ int flat_wgrad(const void* x, const void* dy, float* dw, float* scratch, int N, 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1, Wq = Wo + 2;
   p.rows = (long long)N * (Ho + 2) * Wq;
   if (3 * p.rows > 0x7fffffffLL - (1 << 20)) return (int)cudaErrorInvalidValue;
+  if (apm > 1 && g_fc_tune[3] == 0) {
+    // Narrow layers: all four planes are resident per stage anyway.  A tap (kh,kw) lives in plane (kh&1, kw&1) at pixel shift
+    // (kh>>1, kw>>1); grouping by SHIFT makes the planes the atoms of M: shift (0,0) holds the four taps {0,1}x{0,1}, (0,1) and (1,0) two
+    // each, (1,1) one -- 4 MMAs per 16 pixels at 32 channels (four atoms, LBO = one plane segment) and 5 at 64 channels (two atoms)
+    // instead of 6, 9 of 16 (20) atom slots used instead of 9 of 24 (12 of 24).
+    p.n_variants = 1;
+    WgVariant& v = p.v[0];
+    v.n_seg = 4;
+    for (int pl = 0; pl < 4; ++pl) v.seg_row_off[pl] = (int)(pl * p.rows);
+    auto add = [&](int seg0, int stride, int dh, int dw, int natoms) {
+      WgGroup& g = v.groups[v.n_groups++];
+      g.seg = seg0;
+      g.delta = dh * Wq + dw;
+      g.atom_segs = stride;
+      for (int j = 0; j < 4; ++j) {
+        g.tap[j] = -1;
+        if (j >= natoms) continue;
+        const int pl = seg0 + j * stride;
+        if (pl > 3) continue;
+        const int kh = 2 * dh + (pl >> 1), kw = 2 * dw + (pl & 1);
+        if (kh < 3 && kw < 3) g.tap[j] = kh * 3 + kw;
+      }
+    };
+    if (apm == 4) {
+      for (int dh = 0; dh < 2; ++dh)
+        for (int dw = 0; dw < 2; ++dw) add(0, 1, dh, dw, 4);
+    } else {
+      add(0, 1, 0, 0, 2); add(2, 1, 0, 0, 2);       // shift (0,0): planes {0,1}, {2,3}
+      add(0, 2, 0, 1, 2);                           // shift (0,1): planes 0, 2 (kw = 2)
+      add(0, 1, 1, 0, 2);                           // shift (1,0): planes 0, 1 (kh = 2)
+      add(0, 1, 1, 1, 1);                           // shift (1,1): plane 0
+    }
+    return dispatch_wgrad(x, 4 * p.rows, dy, p, dw, st);
+  }
   // per phase plane (a,b): taps with (kh&1, kw&1) = (a,b), shift (kh>>1)*Wq + (kw>>1); wide layers: one variant per plane
   p.n_variants = apm == 1 ? 4 : 1;
   for (int pl = 0; pl < 4; ++pl) {
