@@ -316,10 +316,13 @@ class CausalAnomalyDetector(nn.Module):
         keeps = None
         if self.training:
             keeps = [self.noise.keep_mask("cls0", (B, 512), 0.3, dev), self.noise.keep_mask("cls1", (B, 256), 0.2, dev), None, None, None]
+        # (a view taken on THIS stream: its backward node -- no kernel -- hands the branch's gradient to the features' accumulation on
+        # the stream the features live on)
+        fsrc = features.view_as(features) if side is not None else features
         if side is not None:
             side.wait_stream(cur)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            pooled = ops.mean_mid(features)
+            pooled = ops.mean_mid(fsrc)
             logits = _mlp(self.direct_classifier, (0, 3, 6, 8, 10), pooled, (ACT_RELU, ACT_RELU, ACT_RELU, ACT_RELU, ACT_NONE), keeps,
                           (0.3, 0.2, 0, 0, 0))
             direct = ma_ops.softmax_rows(logits)
