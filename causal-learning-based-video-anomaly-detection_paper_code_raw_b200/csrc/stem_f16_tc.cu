@@ -388,24 +388,23 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
         const int r = ql / g.Wq, J = ql - r * g.Wq;
         const bool row_in = r < S8_ROWS && J < g.Wh;
         const bool live = row_in && i0 + r >= 0 && i0 + r < g.Ho;
+        // all four 16-column loads of the row (both outputs) in flight before the single wait: one TMEM round trip per sub-tile, not two
+        uint32_t acc[4][16];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tmem_ld16(taddr + 16 * k, acc[k]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bar_acc_empty[slot]);
         uint32_t pk0[16], pk1[16];
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {                               // the pixel's two outputs, one after the other (register budget)
-          uint32_t a0[16], a1[16];
-          tmem_ld16(taddr + 32 * p, a0);
-          tmem_ld16(taddr + 32 * p + 16, a1);
-          tmem_ld_wait();
-          if (p == 1) {
-            tc_fence_before();
-            mbar_arrive(&bar_acc_empty[slot]);
-          }
+        for (int p = 0; p < 2; ++p) {
           uint32_t* pk = p ? pk1 : pk0;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float y0 = fmaxf(fmaf(__uint_as_float(a0[2 * c]), rs[2 * c], rq[2 * c]), 0.f);
-            const float y1 = fmaxf(fmaf(__uint_as_float(a0[2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
-            const float z0 = fmaxf(fmaf(__uint_as_float(a1[2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
-            const float z1 = fmaxf(fmaf(__uint_as_float(a1[2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
+            const float y0 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c]), rs[2 * c], rq[2 * c]), 0.f);
+            const float y1 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
+            const float z0 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
+            const float z1 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
             __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
             pk[c] = *reinterpret_cast<uint32_t*>(&h0);
             pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
