@@ -119,13 +119,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uin
 }
 
 // conv1 weights (32,1,7,7) fp32 -> shared memory [mma = (u0/2)*3 + v][chunk c][n = p*32 + cout][e = a*4 + b] fp16
-__device__ __forceinline__ void stage_weights8(const float* __restrict__ w, uint8_t* smem_w) {
+// chan_scale (shared memory, may be NULL): a per-output-channel factor folded into the weights before they are rounded
+__device__ __forceinline__ void stage_weights8(const float* __restrict__ w, uint8_t* smem_w, const float* chan_scale) {
   __half* dst = reinterpret_cast<__half*>(smem_w);
   for (int i = threadIdx.x; i < S8_MMAS * 2 * S8_N * 8; i += blockDim.x) {
     const int e = i & 7, n = (i >> 3) & 63, c = (i >> 9) & 1, m = i >> 10;
     const int u = 2 * (m / 3) + c, v = m % 3, a = e >> 2, b = e & 3, p = n >> 5, co = n & 31;
     const int kh = 2 * u + a - 1, kw = 4 * v + b - 2 * p - 1;
-    const float val = ((unsigned)kh < (unsigned)S8_K && (unsigned)kw < (unsigned)S8_K) ? w[co * S8_K * S8_K + kh * S8_K + kw] : 0.f;
+    float val = ((unsigned)kh < (unsigned)S8_K && (unsigned)kw < (unsigned)S8_K) ? w[co * S8_K * S8_K + kh * S8_K + kw] : 0.f;
+    if (chan_scale) val *= chan_scale[co];
     dst[i] = __float2half_rn(val);
   }
 }
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(384, 1) stem8_stats_kernel(const __grid_consta
     fence_barrier_init();
     prefetch_tmap(&map_x8);
   }
-  stage_weights8(w, smem_gen);
+  stage_weights8(w, smem_gen, nullptr);
   if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   tc_fence_before();
@@ -283,7 +285,8 @@ __global__ void __launch_bounds__(384, 1) stem8_stats_kernel(const __grid_consta
 // over three rows of max(M[pw], X[pw-1]) -- six shared-memory loads instead of nine, on the pipe the MMAs stream their operands through.
 // A pixel's four 16-byte vectors are XOR-swizzled by (J >> 1) & 3: parking stores (lanes = consecutive pixels) and pooling reads are both
 // bank-conflict free.
-__global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constant__ CUtensorMap map_x8, const float* __restrict__ w,
+constexpr int S8_EG = 3;              // epilogue groups of pass 2 (4 warps each): 128 + 3 * 128 = 512 threads
+__global__ void __launch_bounds__(128 + 128 * S8_EG, 1) stem8_pool_kernel(const __grid_constant__ CUtensorMap map_x8, const float* __restrict__ w,
                                                             const float* __restrict__ bias, Geo8 g, Pool8 pg, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
@@ -305,12 +308,22 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
     fence_barrier_init();
     prefetch_tmap(&map_x8);
   }
-  if (tid < S8_C) {
-    const float sc = invstd[tid] * gamma[tid];
-    s_sc[tid] = sc;
-    s_sh[tid] = (bias[tid] - mean[tid]) * sc + beta[tid];
+  // The BatchNorm scale gamma * invstd goes INTO the weights (times a power of two that brings the largest scale to ~1, so that small
+  // weights do not fall into fp16's subnormals): the epilogue is then relu(acc * 2^-k + shift) with ONE scalar instead of 32 per-channel
+  // scales -- the 32 registers that let the kernel run three epilogue groups (512 threads: 128 registers per thread).
+  __shared__ float s_kinv;
+  if (warp == 0) {
+    const float sc = invstd[lane] * gamma[lane];
+    float mx = fabsf(sc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float k = mx > 0.f ? exp2f(-rintf(log2f(mx))) : 1.f;
+    s_sc[lane] = sc * k;
+    s_sh[lane] = (bias[lane] - mean[lane]) * sc + beta[lane];
+    if (lane == 0) s_kinv = 1.f / k;
   }
-  stage_weights8(w, smem_gen);
+  __syncthreads();
+  stage_weights8(w, smem_gen, s_sc);
   if (warp == 2) tmem_alloc<512>(&tmem_base_sh);
   asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
   tc_fence_before();
@@ -368,17 +381,19 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
     }
   } else if (warp >= 4) {
     const int ew = (warp - 4) & 3, eg = (warp - 4) >> 2;
-    const int et = tid - 128;                                       // 0..255 among the epilogue threads
+    const int et = tid - 128;                                       // 0 .. 128*S8_EG - 1 among the epilogue threads
+    constexpr int ET = 128 * S8_EG;
     uint32_t acc_cnt = 0;
     const int groups = S8_C / 8;                                    // 16-byte vectors per pixel
-    float rs[S8_C], rq[S8_C];                                       // BatchNorm scale / shift in registers
+    float rq[S8_C];                                                 // BatchNorm shift in registers (the scale sits in the weights)
 #pragma unroll
-    for (int c = 0; c < S8_C; ++c) { rs[c] = s_sc[c]; rq[c] = s_sh[c]; }
+    for (int c = 0; c < S8_C; ++c) rq[c] = s_sh[c];
+    const float kinv = s_kinv;
     for (long long t = blockIdx.x; t < pg.n_items; t += gridDim.x) {
       const long long n = t / pg.bands_per_frame;
       const int b = (int)(t - n * pg.bands_per_frame);
       const int i0 = 2 * S8_P * b - 1;                              // first convolution row of the band
-      for (int sb = eg; sb < sub; sb += 2) {
+      for (int sb = eg; sb < sub; sb += S8_EG) {
         const uint32_t use = acc_cnt + sb;
         const int slot = use % S8_SLOTS;
         mbar_wait(&bar_acc_full[slot], (use / S8_SLOTS) & 1);
@@ -401,10 +416,10 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
           uint32_t* pk = p ? pk1 : pk0;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const float y0 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c]), rs[2 * c], rq[2 * c]), 0.f);
-            const float y1 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c + 1]), rs[2 * c + 1], rq[2 * c + 1]), 0.f);
-            const float z0 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c]), rs[16 + 2 * c], rq[16 + 2 * c]), 0.f);
-            const float z1 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c + 1]), rs[16 + 2 * c + 1], rq[16 + 2 * c + 1]), 0.f);
+            const float y0 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c]), kinv, rq[2 * c]), 0.f);
+            const float y1 = fmaxf(fmaf(__uint_as_float(acc[2 * p][2 * c + 1]), kinv, rq[2 * c + 1]), 0.f);
+            const float z0 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c]), kinv, rq[16 + 2 * c]), 0.f);
+            const float z1 = fmaxf(fmaf(__uint_as_float(acc[2 * p + 1][2 * c + 1]), kinv, rq[16 + 2 * c + 1]), 0.f);
             __nv_bfloat162 h0 = __floats2bfloat162_rn(y0, y1), h1 = __floats2bfloat162_rn(z0, z1);
             pk[c] = *reinterpret_cast<uint32_t*>(&h0);
             pk[8 + c] = *reinterpret_cast<uint32_t*>(&h1);
@@ -434,10 +449,10 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
         }
       }
       acc_cnt += sub;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band is complete
+      asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");        // the band is complete
       // ---- pool: pooled rows S8_P*b .. S8_P*b + S8_P - 1 (band rows 2k, 2k+1, 2k+2 for the k-th of them), padded-flat output
       const int rowlen = (pg.PW + 2) * groups;                       // vectors per padded output row
-      for (int v = et; v < S8_P * rowlen; v += 256) {
+      for (int v = et; v < S8_P * rowlen; v += ET) {
         const int k = v / rowlen, vv = v - k * rowlen;
         const int ph = S8_P * b + k;
         if (ph >= pg.PH) continue;
@@ -468,11 +483,11 @@ __global__ void __launch_bounds__(384, 1) stem8_pool_kernel(const __grid_constan
       }
       // the frame's top / bottom border rows belong to its first / last band
       if (b == 0)
-        for (int v = et; v < rowlen; v += 256) reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2)) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
+        for (int v = et; v < rowlen; v += ET) reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2)) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
       if (b == pg.bands_per_frame - 1)
-        for (int v = et; v < rowlen; v += 256)
+        for (int v = et; v < rowlen; v += ET)
           reinterpret_cast<uint4*>(out)[(n * (pg.PH + 2) + pg.PH + 1) * (long long)rowlen + v] = make_uint4(0, 0, 0, 0);
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");              // the band buffer may be overwritten
+      asm volatile("bar.sync 1, %0;\n" ::"n"(ET) : "memory");        // the band buffer may be overwritten
     }
   }
   tc_fence_before();
@@ -621,7 +636,7 @@ CVAD_API int cvad_stem8_f16_bn_relu_maxpool(const void* x8, const float* w, cons
   if (ce != cudaSuccess) return (int)ce;
   long long grid = cvad_num_sms();
   if (grid > pg.n_items) grid = pg.n_items;
-  stem8_pool_kernel<<<(unsigned)grid, 384, smem, (cudaStream_t)stream>>>(mx, w, bias, g, pg, mean, invstd, gamma, beta, (__nv_bfloat16*)out);
+  stem8_pool_kernel<<<(unsigned)grid, 128 + 128 * S8_EG, smem, (cudaStream_t)stream>>>(mx, w, bias, g, pg, mean, invstd, gamma, beta, (__nv_bfloat16*)out);
   CVAD_LAUNCH_CHECK();
   return 0;
 }
