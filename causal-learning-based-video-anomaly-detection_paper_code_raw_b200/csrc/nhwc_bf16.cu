@@ -342,8 +342,9 @@ __global__ void __launch_bounds__(256, 3) pad_reduce_kernel(const __nv_bfloat16*
 // ReLU + BatchNorm backward: draw (plain padded, ZERO border) from raw and dact (plain or phase planes)
 // FOLD: block 0 also adds the two sums into dgamma / dbeta and the last block past the prologue re-zeroes ws (bn_bwd_params_nhwc_kernel's
 // work): no third launch.
-template <int PHASE, int R, bool FOLD>
-__global__ void __launch_bounds__(256) pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
+// OCC: resident CTAs per SM the register allocation is held to (98 registers = 2 CTAs when left alone; 3 CTAs cost ~20 spilled registers)
+template <int PHASE, int R, bool FOLD, int OCC>
+__global__ void __launch_bounds__(256, OCC) pad_bn_relu_bwd_apply_kernel(const __nv_bfloat16* __restrict__ raw, const __nv_bfloat16* __restrict__ dact,
                                                                     __nv_bfloat16* __restrict__ draw, PadGeo g, const float* __restrict__ mean,
                                                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, double* __restrict__ ws, double count,
@@ -660,9 +661,14 @@ int launch_bwd_apply(const __nv_bfloat16* r, const __nv_bfloat16* d, __nv_bfloat
   const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
   const int ab = want < cap ? want : cap;
   const double count = (double)N * H * W;
-#define CVAD_BAPPLY(PH, RR, FO) \
-  pad_bn_relu_bwd_apply_kernel<PH, RR, FO><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training, dgamma, dbeta)
-#define CVAD_BAPPLY2(PH, FO) { if (R == 2) CVAD_BAPPLY(PH, 2, FO); else CVAD_BAPPLY(PH, 4, FO); }
+  static int occ3 = -1;
+  if (occ3 < 0) {
+    const char* e = getenv("CVAD_BN_OCC");
+    occ3 = e ? (atoi(e) >= 3) : 0;          // measured: 3 CTAs per SM (80 registers, ~20 spilled) is 75 us per step slower than 2 (98 registers)
+  }
+#define CVAD_BAPPLY(PH, RR, FO, OC) \
+  pad_bn_relu_bwd_apply_kernel<PH, RR, FO, OC><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training, dgamma, dbeta)
+#define CVAD_BAPPLY2(PH, FO) { if (R == 2) { if (occ3) CVAD_BAPPLY(PH, 2, FO, 3); else CVAD_BAPPLY(PH, 2, FO, 2); } else CVAD_BAPPLY(PH, 4, FO, 1); }
   if (phase_in) { if (fold) CVAD_BAPPLY2(1, true) else CVAD_BAPPLY2(1, false) }
   else { if (fold) CVAD_BAPPLY2(0, true) else CVAD_BAPPLY2(0, false) }
 #undef CVAD_BAPPLY2
