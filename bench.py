@@ -529,7 +529,9 @@ def run_ma_train(args, rank, local, world, dev, dp):
                              "(bit-identical to the host-side fp32 path)" if args.frames == "u8" else "fp32 frames normalised on the host (cad:1177-1179)",
                    "e2e_path": "pinned host batch -> H2D (copy stream, overlapped with the previous step) -> graph -> D2H loss",
                    "initial_state": "synth_fill seed 3 (stock detector-bias init: saturated detector), identical on every rank",
-                   "precision": "bf16 operands, fp32 accumulate (tcgen05), fp32 stem/tail" if args.precision == "bf16" else "fp32"},
+                   "precision": ("bf16 operands, fp32 accumulate (tcgen05 kind::f16) in the eight 3x3 layers; stem: fp16 operands (the uint8 frames and "
+                                 "their Normalize(0.5,0.5) images are exact in fp16), fp32 accumulate; dense tail fp32 (6144-wide projections 3xTF32)")
+                   if args.precision == "bf16" else "fp32"},
         "e2e": {"value": world * B / (ms_e2e / args.steps / 1e3), "unit": unit, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
