@@ -613,6 +613,30 @@ void launch_reduce(const __nv_bfloat16* r, const __nv_bfloat16* d, const PadGeo&
   else pad_reduce_kernel<BWD, 0><<<blocks, 256, sm, st>>>(r, d, g, mean, invstd, gamma, beta, ws);
 }
 
+// Grid of a row-walking apply kernel: as many CTAs as are RESIDENT at once (occupancy x SMs), each walking its share of the rows.  A
+// CTA's prologue is ~50 dependent loads of per-channel constants; with 8 x SMs CTAs -- four waves at 2 resident CTAs per SM -- the small
+// layers paid it once per 2-3 row iterations (ncu: 36 us for 54 MB at 8x12x256), and the waves ended unevenly on the large ones.  Measured
+// on the M-A step (A/B twice on one box): 8 x SMs CTAs everywhere 3.960 ms; resident-only for tensors with < 4 / < 8 row iterations per CTA
+// 3.903 / 3.888 ms; resident-only everywhere 3.873 ms.  CVAD_BN_SMALL_GRID=k applies the rule below k iterations only (0 = never).
+template <typename K>
+int apply_grid(K kernel, int want) {
+  const int cap = bn_ctas_per_sm() * cvad_num_sms();
+  int blocks = want < cap ? want : cap;
+  static int small_rule = -1;
+  if (small_rule < 0) {
+    const char* e = getenv("CVAD_BN_SMALL_GRID");
+    small_rule = e ? atoi(e) : (1 << 20);
+  }
+  if (small_rule && want < small_rule * cap) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) == cudaSuccess && per_sm > 0) {
+      const int resident = per_sm * cvad_num_sms();
+      if (resident < blocks) blocks = resident;
+    }
+  }
+  return blocks;
+}
+
 inline int bn_apply_reverse() {
   static int v = -1;
   if (v < 0) {
@@ -628,9 +652,9 @@ int launch_apply(const __nv_bfloat16* r, __nv_bfloat16* a, const PadGeo& g, int 
   fin.reverse = bn_apply_reverse();
   const int rows = phase_out ? 2 * N * g.Hq : N * (H + 2);
   const int R = bn_rows_per_iter() == 4 ? 4 : 2;
-  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
-  const int blocks = want < cap ? want : cap;
-#define CVAD_APPLY(PH, RR, FI) pad_bn_apply_relu_kernel<PH, RR, FI><<<blocks, 256, 0, st>>>(r, a, g, mean, invstd, gamma, beta, fin)
+  const int want = (rows + R - 1) / R;
+#define CVAD_APPLY(PH, RR, FI) \
+  pad_bn_apply_relu_kernel<PH, RR, FI><<<apply_grid(pad_bn_apply_relu_kernel<PH, RR, FI>, want), 256, 0, st>>>(r, a, g, mean, invstd, gamma, beta, fin)
 #define CVAD_APPLY2(PH, FI) { if (R == 2) CVAD_APPLY(PH, 2, FI); else CVAD_APPLY(PH, 4, FI); }
   if (phase_out) { if (finalize) CVAD_APPLY2(1, true) else CVAD_APPLY2(1, false) }
   else { if (finalize) CVAD_APPLY2(0, true) else CVAD_APPLY2(0, false) }
@@ -658,16 +682,16 @@ int launch_bwd_apply(const __nv_bfloat16* r, const __nv_bfloat16* d, __nv_bfloat
                      float* dgamma, float* dbeta, cudaStream_t st) {
   const int rows = N * (H + 2);
   const int R = bn_rows_per_iter() == 4 ? 4 : 2;
-  const int want = (rows + R - 1) / R, cap = bn_ctas_per_sm() * cvad_num_sms();
-  const int ab = want < cap ? want : cap;
+  const int want = (rows + R - 1) / R;
   const double count = (double)N * H * W;
   static int occ3 = -1;
   if (occ3 < 0) {
     const char* e = getenv("CVAD_BN_OCC");
     occ3 = e ? (atoi(e) >= 3) : 0;          // measured: 3 CTAs per SM (80 registers, ~20 spilled) is 75 us per step slower than 2 (98 registers)
   }
-#define CVAD_BAPPLY(PH, RR, FO, OC) \
-  pad_bn_relu_bwd_apply_kernel<PH, RR, FO, OC><<<ab, 256, 0, st>>>(r, d, draw, g, mean, invstd, gamma, beta, ws, count, training, dgamma, dbeta)
+#define CVAD_BAPPLY(PH, RR, FO, OC)                                                                                                         \
+  pad_bn_relu_bwd_apply_kernel<PH, RR, FO, OC><<<apply_grid(pad_bn_relu_bwd_apply_kernel<PH, RR, FO, OC>, want), 256, 0, st>>>(               \
+      r, d, draw, g, mean, invstd, gamma, beta, ws, count, training, dgamma, dbeta)
 #define CVAD_BAPPLY2(PH, FO) { if (R == 2) { if (occ3) CVAD_BAPPLY(PH, 2, FO, 3); else CVAD_BAPPLY(PH, 2, FO, 2); } else CVAD_BAPPLY(PH, 4, FO, 1); }
   if (phase_in) { if (fold) CVAD_BAPPLY2(1, true) else CVAD_BAPPLY2(1, false) }
   else { if (fold) CVAD_BAPPLY2(0, true) else CVAD_BAPPLY2(0, false) }
