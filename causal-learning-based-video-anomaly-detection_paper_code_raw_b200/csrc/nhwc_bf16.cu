@@ -80,6 +80,9 @@ struct PadGeo {
   int Hq, Wq;           // phase-plane geometry (Ho+2, Wo+2) when a phase layout is involved
   int lg;               // log2(C/8)
   unsigned mulW, shrW, mulH, shrH;     // x / W and x / H as umulhi(x, mul) >> shr for 0 <= x < 2^31 (mul = 0: divisor 1)
+  // the same for H + 2, Hq and N: the row-walking kernels decode their row index with them (an emulated 32-bit division is ~25
+  // instructions, and ncu counted 85-118 instructions per 16-byte vector in the apply kernels before these replaced four of them per row)
+  unsigned mulHp, shrHp, mulHq, shrHq, mulN, shrN;
 };
 
 
@@ -181,16 +184,16 @@ __global__ void __launch_bounds__(256) pad_bn_apply_relu_kernel(const __nv_bfloa
         long long row0 = 0, row1 = 0;                              // first vector of the output row(s)
         if (r >= 0 && r < items) {
           if (PHASE) {
-            const int i = r % g.Hq;
-            const int t = r / g.Hq;
-            n = t % g.N;
-            a = t / g.N;
+            const int t = fast_div(r, g.mulHq, g.shrHq);
+            const int i = r - t * g.Hq;
+            a = fast_div(t, g.mulN, g.shrN);
+            n = t - a * g.N;
             hp = 2 * (i - 1) + a;
             row0 = ((((long long)(2 * a) * g.N + n) * g.Hq) + i) * rowlen;
             row1 = ((((long long)(2 * a + 1) * g.N + n) * g.Hq) + i) * rowlen;
           } else {
-            hp = r % Hp;
-            n = r / Hp;
+            n = fast_div(r, g.mulHp, g.shrHp);
+            hp = r - n * Hp;
             row0 = (long long)r * rowlen;
           }
         }
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(256, OCC) pad_bn_relu_bwd_apply_kernel(const _
 #pragma unroll
       for (int rr = 0; rr < R; ++rr) {
         const int r = r0 + rr;
-        const int hp = r % Hp, n = r / Hp;
+        const int n = fast_div(r, g.mulHp, g.shrHp), hp = r - n * Hp;
         const bool row_ok = r < rows && hp >= 1 && hp <= g.H;
         const long long vbase = (long long)r * rowlen;
 #pragma unroll
@@ -598,6 +601,9 @@ inline int make_geo(PadGeo& g, int N, int H, int W, int C, int phase) {
   while ((8 << g.lg) < C) ++g.lg;
   fast_div_init((unsigned)W, g.mulW, g.shrW);
   fast_div_init((unsigned)H, g.mulH, g.shrH);
+  fast_div_init((unsigned)(H + 2), g.mulHp, g.shrHp);
+  fast_div_init((unsigned)(g.Hq > 0 ? g.Hq : 1), g.mulHq, g.shrHq);
+  fast_div_init((unsigned)N, g.mulN, g.shrN);
   return 0;
 }
 
