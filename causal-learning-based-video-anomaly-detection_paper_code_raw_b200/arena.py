@@ -68,7 +68,8 @@ class FlatArena:
         return buf[o:o + p.numel()].view(p.shape)
 
     def zero_grad(self):
-        self.g.zero_()
+        from .ops import _call, _ptr, _st
+        _call("cvad_fill_f32", _ptr(self.g), self.g.numel(), 0.0, _st())
         for p, o in zip(self.params, self.offsets):   # re-attach if something detached the views (e.g. set_to_none)
             if p.grad is None or p.grad.data_ptr() != self.g.data_ptr() + 4 * o:
                 p.grad = self.g[o:o + p.numel()].view(p.shape)

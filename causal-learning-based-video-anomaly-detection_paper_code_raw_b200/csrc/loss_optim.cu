@@ -255,8 +255,18 @@ __global__ void opt_finish_kernel(cvad_opt_state* __restrict__ st, const float* 
   }
 }
 
+// 16-byte stores over the aligned body, scalars over the (at most 3 + 3) elements around it
 __global__ void fill_kernel(float* __restrict__ x, long long n, float v) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] = v;
+  const long long head = (4 - (((uintptr_t)x >> 2) & 3)) & 3;          // elements before the first 16-byte boundary
+  const long long h = head < n ? head : n;
+  const long long n4 = (n - h) >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x + h);
+  const float4 v4 = make_float4(v, v, v, v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) x4[i] = v4;
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < h; i += blockDim.x) x[i] = v;
+    for (long long i = h + 4 * n4 + threadIdx.x; i < n; i += blockDim.x) x[i] = v;
+  }
 }
 
 // out[i] = a * x[i*xs] + b * y[i*ys]
@@ -330,8 +340,9 @@ CVAD_API int cvad_adam_flat_f32(float* p, const float* g, float* m, float* v, lo
 
 CVAD_API int cvad_fill_f32(float* x, long long n, float value, void* stream) {
   if (n <= 0) return 0;
-  int blocks = (int)((n + 255) / 256);
+  int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > 8 * cvad_num_sms()) blocks = 8 * cvad_num_sms();
+  if (blocks < 1) blocks = 1;
   fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, n, value);
   CVAD_LAUNCH_CHECK();
   return 0;

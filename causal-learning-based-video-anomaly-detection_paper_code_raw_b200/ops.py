@@ -140,6 +140,14 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def zeros_f32(shape, device):
+    """fp32 zeros through the library's own fill kernel (the accumulating GEMMs / reductions need zeroed outputs every step)."""
+    t = torch.empty(shape, device=device, dtype=torch.float32)
+    if t.numel():
+        _call("cvad_fill_f32", _ptr(t), t.numel(), 0.0, _st())
+    return t
+
+
 def u8_normalize(x: torch.Tensor, mean: float, std: float) -> torch.Tensor:
     """uint8 frames -> fp32 ``(x - mean) / std`` (torchvision Normalize on the reference's FloatTensor frames, cad:1177-1179)."""
     _cuda(x)
@@ -275,12 +283,12 @@ class _LinearAct(torch.autograd.Function):
             mask = _f32c(mask).reshape(M, O)
         if TF32X3 and K >= 2048 and K % 32 == 0 and O >= 128 and x2.data_ptr() % 16 == 0 and weight.data_ptr() % 16 == 0:
             # the two 6144 -> 512 projections: tcgen05 kind::tf32 with the 3xTF32 split (fp32-level accuracy), split-K + atomic reduction
-            y = torch.zeros((M, O), device=x.device, dtype=torch.float32)
+            y = zeros_f32((M, O), x.device)
             _call("cvad_linear_fwd_tf32x3", _ptr(x2), _ptr(weight), _ptr(y), M, O, K, _st())
             if bias is not None or act != ACT_NONE or mask is not None:
                 _call("cvad_bias_act_mask_f32", _ptr(y), M, O, _ptr(bias), act, _ptr(mask), float(mask_scale), _st())
         elif splits > 1:
-            y = torch.zeros((M, O), device=x.device, dtype=torch.float32)
+            y = zeros_f32((M, O), x.device)
             _sgemm(M, O, K, x2, K, True, weight, K, True, y, O, splits=splits)
             if bias is not None or act != ACT_NONE or mask is not None:
                 _call("cvad_bias_act_mask_f32", _ptr(y), M, O, _ptr(bias), act, _ptr(mask), float(mask_scale), _st())
@@ -319,7 +327,7 @@ class _LinearAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:  # dx[m][i] = sum_o dz[m][o] W[o][i]
             splits = _splits_for(M, K, O)
             if splits > 1 or gate is not None:
-                dx = torch.zeros((M, K), device=dz.device, dtype=torch.float32)
+                dx = zeros_f32((M, K), dz.device)
             else:
                 dx = torch.empty((M, K), device=dz.device, dtype=torch.float32)
             _sgemm(M, K, O, dz, O, True, weight, K, False, dx, K, splits=splits, gate=gate)
@@ -663,7 +671,7 @@ class _LinComb2(torch.autograd.Function):
         g = _f32c(g)
         dx = torch.empty_like(g)
         _call("cvad_lincomb2_f32", _ptr(dx), _ptr(g), 1, float(a), _ptr(g), 1, 0.0, g.numel(), _st())
-        dy = torch.zeros(yshape, device=g.device, dtype=torch.float32)
+        dy = zeros_f32(yshape, g.device)
         tgt = dy[:, col] if len(yshape) == 2 else dy
         tmp = torch.empty_like(g)
         _call("cvad_lincomb2_f32", _ptr(tmp), _ptr(g), 1, float(b), _ptr(g), 1, 0.0, g.numel(), _st())

@@ -344,3 +344,17 @@ def test_linear_fwd_tf32x3_matches_fp32(dev, M, N, K):
     e32 = rel(x @ w.t(), ref)
     print(f"[tf32x3] M{M} N{N} K{K}: rel err {e:.2e} (torch fp32 matmul: {e32:.2e})")
     assert e < 5e-6
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 17, 1023, 4096, 1000003])
+@pytest.mark.parametrize("offset", [0, 1, 2, 3])
+def test_fill_f32_any_alignment(dev, n, offset):
+    """cvad_fill_f32 (zero-initialises the accumulating GEMMs' outputs and the gradient arena every step): 16-byte stores over the aligned
+    body, scalars around it -- every element written, nothing outside the range touched."""
+    from cvad_b200.ops import _call, _ptr, _st
+    buf = torch.full((n + 8,), 7.0, device=dev)
+    view = buf[offset + 1: offset + 1 + n]
+    _call("cvad_fill_f32", view.data_ptr(), n, -2.5, _st())
+    torch.cuda.synchronize()
+    assert bool((view == -2.5).all())
+    assert float(buf[: offset + 1].min()) == 7.0 and float(buf[offset + 1 + n:].min()) == 7.0
